@@ -1,0 +1,507 @@
+// HBM-bound kernels around the contractions: operand re-layout (fp32 -> bf16 hi/lo, transposes), CSR ->
+// dense interaction rows, fused forward noising (q_sample + dropout), the 2-state discrete noise of the
+// one-hot branch, the sparse one-hot encoder used at inference, user-tower finish (mix + row norms),
+// loss rows, and fused AdamW. All are single-pass, vectorised, grid-stride over 148*k CTAs.
+//
+// Reference call sites are cited at each entry point in include/gdmcf_sm100.h.
+#include "common.cuh"
+#include "api_internal.h"
+
+namespace gd {
+namespace ew {
+
+constexpr int TPB = 256;
+
+static int grid_1d(long long work_items, int per_cta = TPB) {
+  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  const long long ctas = (work_items + per_cta - 1) / per_cta;
+  return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sms * 8));
+}
+
+GD_DEV void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ---------------------------------------------------------------------------------------------
+// cast fp32 -> bf16 (hi[, lo]) with zero padding up to ld_out
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, long long ld_out, int rows, int cols) {
+  const long long total = (long long)rows * ld_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld_out);
+    const int c = (int)(i % ld_out);
+    const float v = (c < cols) ? in[(long long)r * ld_in + c] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// out[c, r] = in[r, c]; 32x32 tiles through shared memory, both sides coalesced.
+__global__ void cast_bf16_transpose_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ hi,
+                                           __nv_bfloat16* __restrict__ lo, long long ld_out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int tiles_c = (cols + 31) / 32;
+  const int tiles_r = (int)((ld_out + 31) / 32);  // output columns (= input rows) incl. padding
+  const long long ntiles = (long long)tiles_c * tiles_r;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int r0 = (int)(t % tiles_r) * 32, c0 = (int)(t / tiles_r) * 32;
+    for (int j = ty; j < 32; j += 8) {
+      const int r = r0 + j, c = c0 + tx;
+      tile[j][tx] = (r < rows && c < cols) ? in[(long long)r * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j, r = r0 + tx;  // output row c, output column r
+      if (c < cols && r < ld_out) {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[tx][j], h, l);
+        hi[(long long)c * ld_out + r] = h;
+        if (lo) lo[(long long)c * ld_out + r] = l;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR rows -> dense {0,1} rows. One CTA per output row.
+// ---------------------------------------------------------------------------------------------
+__global__ void densify_rows_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                    const int* __restrict__ users, int n_rows, int n_items, float* __restrict__ out_f32,
+                                    long long ld_f32, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16) {
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    if (out_f32) {
+      float4* p = reinterpret_cast<float4*>(out_f32 + (long long)r * ld_f32);
+      for (long long i = threadIdx.x; i < ld_f32 / 4; i += blockDim.x) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (out_bf16) {
+      uint4* p = reinterpret_cast<uint4*>(out_bf16 + (long long)r * ld_bf16);
+      for (long long i = threadIdx.x; i < ld_bf16 / 8; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const int u = users ? users[r] : r;
+    const int b = rowptr[u], e = rowptr[u + 1];
+    for (int j = b + threadIdx.x; j < e; j += blockDim.x) {
+      const int c = col[j];
+      if (c < n_items) {
+        if (out_f32) out_f32[(long long)r * ld_f32 + c] = 1.0f;
+        if (out_bf16) out_bf16[(long long)r * ld_bf16 + c] = __float2bfloat16_rn(1.0f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// q_sample fused with dropout and the bf16 operand cast. One thread per 4 consecutive columns.
+// ---------------------------------------------------------------------------------------------
+__global__ void qsample_dropout_kernel(const float* __restrict__ x0, long long ld_x0, const int* __restrict__ row_t,
+                                       int t_const, const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab,
+                                       const float* __restrict__ noise, const uint8_t* __restrict__ keep, float dropout_p,
+                                       uint64_t seed, uint64_t offset, float* __restrict__ xt_f32, long long ld_xt,
+                                       __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, long long ld_a,
+                                       int rows, int cols) {
+  const int groups = (int)(ld_a / 4);  // ld_a % 8 == 0
+  const long long total = (long long)rows * groups;
+  const Philox rng(seed);
+  const float keep_scale = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / groups);
+    const int c0 = (int)(i % groups) * 4;
+    const int t = row_t ? row_t[r] : t_const;
+    const bool noisy = sqrt_ab != nullptr;  // NULL tables: x_t = x0 (p_sample with sampling_steps == 0)
+    const float ca = noisy ? sqrt_ab[t] : 1.f, cb = noisy ? sqrt_1mab[t] : 0.f;
+    float eps[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 ur = make_uint4(0, 0, 0, 0);
+    if (noisy && !noise) {
+      const uint4 g = rng(offset + (uint64_t)i, 0ull);
+      const float2 n0 = box_muller(g.x, g.y), n1 = box_muller(g.z, g.w);
+      eps[0] = n0.x; eps[1] = n0.y; eps[2] = n1.x; eps[3] = n1.y;
+    }
+    if (dropout_p > 0.f && !keep) ur = rng(offset + (uint64_t)i, 1ull);
+    const uint32_t urr[4] = {ur.x, ur.y, ur.z, ur.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      float xt = 0.f, a = 0.f;
+      if (c < cols) {
+        const float x = x0[(long long)r * ld_x0 + c];
+        if (noisy) {
+          const float e = noise ? noise[(long long)r * cols + c] : eps[j];
+          xt = ca * x + cb * e;  // same association as gaussian_diffusion.py:993-996
+        } else {
+          xt = x;
+        }
+        if (xt_f32) xt_f32[(long long)r * ld_xt + c] = xt;
+        a = xt;
+        if (dropout_p > 0.f) {
+          const bool k = keep ? (keep[(long long)r * cols + c] != 0) : (u32_to_unit_open(urr[j]) > dropout_p);
+          a = k ? xt * keep_scale : 0.f;
+        }
+      }
+      split_bf16(a, h[j], l[j]);
+    }
+    __nv_bfloat16* ph = a_hi + (long long)r * ld_a + c0;
+    *reinterpret_cast<uint2*>(ph) =
+        make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+                   (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+    if (a_lo) {
+      __nv_bfloat16* pl = a_lo + (long long)r * ld_a + c0;
+      *reinterpret_cast<uint2*>(pl) =
+          make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+                     (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Discrete (2-state) noise on the one-hot branch + dropout. One thread per 4 items -> 8 outputs.
+// ---------------------------------------------------------------------------------------------
+__global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x0, const int* __restrict__ ts,
+                                    float discrete, float dropout_p, const float* __restrict__ u_keep,
+                                    const float* __restrict__ u_drop, uint64_t seed, uint64_t offset,
+                                    __nv_bfloat16* __restrict__ out, long long ld_out, int rows, int cols) {
+  const int groups = (int)(ld_out / 8);  // 8 outputs = 4 items per thread
+  const long long total = (long long)rows * groups;
+  const Philox rng(seed);
+  const float keep_val = dropout_p > 0.f ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  const __nv_bfloat16 one = __float2bfloat16_rn(keep_val), zero = __float2bfloat16_rn(0.f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / groups);
+    const int i0 = (int)(i % groups) * 4;
+    // a = ts / batch_size in fp32 (gaussian_diffusion.py:775); Q_bar = a*I + (1-a)*u_x (:601)
+    const float a = ts ? (float)ts[r] / (float)rows : 1.0f;  // ts == NULL: no discrete noise (p_sample, steps == 0)
+    const float q_one = a * 1.0f + (1.0f - a) * (1.0f - discrete);  // x0 == 1 keeps channel 1
+    const float q_zero = a * 1.0f + (1.0f - a) * discrete;          // x0 == 0 keeps channel 0
+    uint4 g0 = make_uint4(0, 0, 0, 0), g1 = make_uint4(0, 0, 0, 0);
+    if (!u_keep && ts) g0 = rng(offset + (uint64_t)i, 2ull);
+    if (!u_drop && dropout_p > 0.f) g1 = rng(offset + (uint64_t)i, 3ull);
+    const uint32_t gk[4] = {g0.x, g0.y, g0.z, g0.w}, gd_[4] = {g1.x, g1.y, g1.z, g1.w};
+    __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int it = i0 + j;
+      o[2 * j] = zero;
+      o[2 * j + 1] = zero;
+      if (it < cols) {
+        const int c = x0[(long long)r * ld_x0 + it] > 0.5f ? 1 : 0;
+        bool kept = true;
+        if (ts) {
+          const float u = u_keep ? u_keep[(long long)r * cols + it] : (1.0f - u32_to_unit_open(gk[j]));  // [0,1)
+          kept = u < (c ? q_one : q_zero);
+        }
+        if (kept && dropout_p > 0.f) {
+          const float u = u_drop ? u_drop[(long long)r * 2 * cols + 2 * it + c] : (1.0f - u32_to_unit_open(gd_[j]));
+          kept = u >= dropout_p;
+        }
+        if (kept) o[2 * j + c] = one;
+      }
+    }
+    uint4 pk;
+    pk.x = (uint32_t)__bfloat16_as_ushort(o[0]) | ((uint32_t)__bfloat16_as_ushort(o[1]) << 16);
+    pk.y = (uint32_t)__bfloat16_as_ushort(o[2]) | ((uint32_t)__bfloat16_as_ushort(o[3]) << 16);
+    pk.z = (uint32_t)__bfloat16_as_ushort(o[4]) | ((uint32_t)__bfloat16_as_ushort(o[5]) << 16);
+    pk.w = (uint32_t)__bfloat16_as_ushort(o[6]) | ((uint32_t)__bfloat16_as_ushort(o[7]) << 16);
+    *reinterpret_cast<uint4*>(out + (long long)r * ld_out + 2 * i0) = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sparse one-hot encoder (inference): S[r,:] = base + sum_{i in row} delta[i,:]
+// ---------------------------------------------------------------------------------------------
+// delta[i,k] = W2[k,2i+1] - W2[k,2i] via 32x32 transposing tiles; base accumulated separately.
+__global__ void onehot_delta_kernel(const float* __restrict__ w2, long long ld_w, int d, int n_items,
+                                    float* __restrict__ delta, long long ld_delta) {
+  __shared__ float tile[32][33];
+  const int tiles_i = (n_items + 31) / 32, tiles_k = (d + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long t = blockIdx.x; t < (long long)tiles_i * tiles_k; t += gridDim.x) {
+    const int i0 = (int)(t % tiles_i) * 32, k0 = (int)(t / tiles_i) * 32;
+    for (int j = ty; j < 32; j += 8) {
+      const int k = k0 + j, i = i0 + tx;
+      float v = 0.f;
+      if (k < d && i < n_items) {
+        const float2 w = *reinterpret_cast<const float2*>(w2 + (long long)k * ld_w + 2 * i);  // ld_w even, base 8B aligned
+        v = w.y - w.x;
+      }
+      tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int i = i0 + j, k = k0 + tx;
+      if (i < n_items && k < d) delta[(long long)i * ld_delta + k] = tile[tx][j];
+    }
+    __syncthreads();
+  }
+}
+// base[k] = sum_i W2[k, 2i]  (fp64 accumulation, one CTA per k)
+__global__ void onehot_base_kernel(const float* __restrict__ w2, long long ld_w, int d, int n_items, float* __restrict__ base) {
+  __shared__ double red[TPB / 32];
+  for (int k = blockIdx.x; k < d; k += gridDim.x) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) s += (double)w2[(long long)k * ld_w + 2 * i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < TPB / 32; ++w) tot += red[w];
+      base[k] = (float)tot;
+    }
+    __syncthreads();
+  }
+}
+// one CTA per user row; threads stride over d.
+__global__ void encode_onehot_gather_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                            const int* __restrict__ users, int n_rows, const float* __restrict__ base,
+                                            const float* __restrict__ delta, long long ld_delta, int d,
+                                            float* __restrict__ out, long long ld_out) {
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const int u = users ? users[r] : r;
+    const int b = rowptr[u], e = rowptr[u + 1];
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+      float s = base[k];
+      for (int j = b; j < e; ++j) s += __ldg(delta + (long long)__ldg(col + j) * ld_delta + k);
+      out[(long long)r * ld_out + k] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// user tower finish: mix + row norm; plain row norms
+// ---------------------------------------------------------------------------------------------
+GD_DEV float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+  __syncthreads();
+  return tot;
+}
+
+__global__ void mix_rownorm_kernel(const float* __restrict__ hc, long long ld_hc, const float* __restrict__ g,
+                                   long long ld_g, const float* __restrict__ sumw, float* __restrict__ out_f32,
+                                   long long ld_of, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                   long long ld_ob, float* __restrict__ inv_norm, int rows, int cols) {
+  __shared__ float red[TPB / 32];
+  const float w = (g && sumw) ? sumw[0] : 1.0f;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    float ss = 0.f;
+    for (int c = threadIdx.x; c < (int)ld_ob; c += blockDim.x) {
+      float v = 0.f;
+      if (c < cols) {
+        const float h = hc[(long long)r * ld_hc + c];
+        // hc * sumW + all_embeddings[:B] * (1 - sumW)   (models/DNN.py:1288)
+        v = g ? h * w + g[(long long)r * ld_g + c] * (1.0f - w) : h;
+        ss += v * v;
+        if (out_f32) out_f32[(long long)r * ld_of + c] = v;
+      }
+      if (out_hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        out_hi[(long long)r * ld_ob + c] = h;
+        if (out_lo) out_lo[(long long)r * ld_ob + c] = l;
+      }
+    }
+    const float tot = block_sum(ss, red);
+    if (threadIdx.x == 0 && inv_norm) inv_norm[r] = 1.0f / sqrtf(tot);
+  }
+}
+
+__global__ void row_inv_norm_kernel(const float* __restrict__ x, long long ld, float* __restrict__ inv_norm, int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp0; r < rows; r += nwarps) {
+    float ss = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = x[(long long)r * ld + c];
+      ss += v * v;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) inv_norm[r] = 1.0f / sqrtf(ss);
+  }
+}
+
+__global__ void mse_rows_kernel(const float* __restrict__ out, long long ld_out, const float* __restrict__ x0,
+                                long long ld_x0, int rows, int cols, float* __restrict__ mse) {
+  __shared__ float red[TPB / 32];
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    float ss = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float dlt = x0[(long long)r * ld_x0 + c] - out[(long long)r * ld_out + c];
+      ss += dlt * dlt;
+    }
+    const float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) mse[r] = tot / (float)cols;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdamW (torch.optim.AdamW, amsgrad=False, maximize=False)
+// ---------------------------------------------------------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float grad = g[i] * grad_scale;
+    float param = p[i];
+    param *= 1.0f - lr * weight_decay;
+    const float mi = m[i] + (grad - m[i]) * (1.0f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + (1.0f - beta2) * grad * grad;      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    param -= step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = param;
+  }
+}
+
+}  // namespace ew
+}  // namespace gd
+
+using namespace gd;
+using namespace gd::ew;
+
+#define GD_PRE()                               \
+  int rc = gdmcf_device_check();               \
+  if (rc) return rc;                           \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int gdmcf_cast_bf16(const float* in, int64_t ld_in, void* out_hi, void* out_lo, int64_t ld_out, int rows,
+                               int cols, gdmcf_stream_t stream) {
+  if (!in || !out_hi || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols) { set_error("cast_bf16: bad arguments"); return GDMCF_EBADARG; }
+  GD_PRE();
+  cast_bf16_kernel<<<grid_1d((long long)rows * ld_out), TPB, 0, st>>>(in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
+  return cuda_check_launch("cast_bf16_kernel");
+}
+
+extern "C" int gdmcf_cast_bf16_transpose(const float* in, int64_t ld_in, void* out_hi, void* out_lo, int64_t ld_out,
+                                         int rows, int cols, gdmcf_stream_t stream) {
+  if (!in || !out_hi || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < rows) { set_error("cast_bf16_transpose: bad arguments"); return GDMCF_EBADARG; }
+  GD_PRE();
+  const long long ntiles = (long long)((cols + 31) / 32) * ((ld_out + 31) / 32);
+  cast_bf16_transpose_kernel<<<grid_1d(ntiles, 1), TPB, 0, st>>>(in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
+  return cuda_check_launch("cast_bf16_transpose_kernel");
+}
+
+extern "C" int gdmcf_densify_rows(const int32_t* rowptr, const int32_t* col, const int32_t* users, int n_rows,
+                                  int n_items, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
+                                  gdmcf_stream_t stream) {
+  if (!rowptr || !col || n_rows <= 0 || n_items <= 0 || (!out_f32 && !out_bf16) ||
+      (out_f32 && ((ld_f32 & 3) || ld_f32 < n_items || ((uintptr_t)out_f32 & 15))) ||
+      (out_bf16 && ((ld_bf16 & 7) || ld_bf16 < n_items || ((uintptr_t)out_bf16 & 15)))) {
+    set_error("densify_rows: need ld_f32 %% 4 == 0, ld_bf16 %% 8 == 0, ld >= n_items, 16B-aligned outputs");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  densify_rows_kernel<<<grid_1d(n_rows, 1), TPB, 0, st>>>(rowptr, col, users, n_rows, n_items, out_f32, ld_f32, (__nv_bfloat16*)out_bf16, ld_bf16);
+  return cuda_check_launch("densify_rows_kernel");
+}
+
+extern "C" int gdmcf_qsample_dropout(const float* x0, int64_t ld_x0, const int32_t* row_t, int t_const,
+                                     const float* sqrt_ab, const float* sqrt_1mab, const float* noise,
+                                     const uint8_t* keep, float dropout_p, uint64_t seed, uint64_t offset, float* xt_f32,
+                                     int64_t ld_xt, void* a_bf16, void* a_lo, int64_t ld_a, int rows, int cols,
+                                     gdmcf_stream_t stream) {
+  if (!x0 || !a_bf16 || rows <= 0 || cols <= 0 || (ld_a & 7) || ld_a < cols || ld_x0 < cols || ((uintptr_t)a_bf16 & 15) ||
+      ((uintptr_t)a_lo & 15) || (xt_f32 && ld_xt < cols) || dropout_p < 0.f || dropout_p >= 1.f || ((sqrt_ab == nullptr) != (sqrt_1mab == nullptr))) {
+    set_error("qsample_dropout: bad arguments (ld_a %% 8 == 0, 0 <= dropout_p < 1, both or neither coefficient tables)");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  qsample_dropout_kernel<<<grid_1d((long long)rows * (ld_a / 4)), TPB, 0, st>>>(
+      x0, ld_x0, row_t, t_const, sqrt_ab, sqrt_1mab, noise, keep, dropout_p, seed, offset, xt_f32, ld_xt,
+      (__nv_bfloat16*)a_bf16, (__nv_bfloat16*)a_lo, ld_a, rows, cols);
+  return cuda_check_launch("qsample_dropout_kernel");
+}
+
+extern "C" int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t* ts, float discrete, float dropout_p,
+                                  const float* u_keep, const float* u_drop, uint64_t seed, uint64_t offset, void* out_bf16,
+                                  int64_t ld_out, int rows, int cols, gdmcf_stream_t stream) {
+  if (!x0 || !out_bf16 || rows <= 0 || cols <= 0 || (ld_out & 7) || ld_out < 2LL * cols || ld_x0 < cols ||
+      ((uintptr_t)out_bf16 & 15) || dropout_p < 0.f || dropout_p >= 1.f) {
+    set_error("onehot_noise: bad arguments (ld_out %% 8 == 0 and >= 2*cols)");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  onehot_noise_kernel<<<grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st>>>(
+      x0, ld_x0, ts, discrete, dropout_p, u_keep, u_drop, seed, offset, (__nv_bfloat16*)out_bf16, ld_out, rows, cols);
+  return cuda_check_launch("onehot_noise_kernel");
+}
+
+extern "C" int gdmcf_onehot_tables(const float* w2, int64_t ld_w, int d, int n_items, float* base, float* delta,
+                                   int64_t ld_delta, gdmcf_stream_t stream) {
+  if (!w2 || !base || !delta || d <= 0 || n_items <= 0 || (ld_w & 1) || ld_w < 2LL * n_items || ld_delta < d || ((uintptr_t)w2 & 7)) {
+    set_error("onehot_tables: bad arguments (ld_w even and >= 2*n_items, ld_delta >= d)");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  const long long ntiles = (long long)((n_items + 31) / 32) * ((d + 31) / 32);
+  onehot_delta_kernel<<<grid_1d(ntiles, 1), TPB, 0, st>>>(w2, ld_w, d, n_items, delta, ld_delta);
+  if ((rc = cuda_check_launch("onehot_delta_kernel"))) return rc;
+  onehot_base_kernel<<<grid_1d(d, 1), TPB, 0, st>>>(w2, ld_w, d, n_items, base);
+  return cuda_check_launch("onehot_base_kernel");
+}
+
+extern "C" int gdmcf_encode_onehot_gather(const int32_t* rowptr, const int32_t* col, const int32_t* users, int n_rows,
+                                          const float* base, const float* delta, int64_t ld_delta, int d, float* out,
+                                          int64_t ld_out, gdmcf_stream_t stream) {
+  if (!rowptr || !col || !base || !delta || !out || n_rows <= 0 || d <= 0 || ld_delta < d || ld_out < d) {
+    set_error("encode_onehot_gather: bad arguments");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  encode_onehot_gather_kernel<<<grid_1d(n_rows, 1), TPB, 0, st>>>(rowptr, col, users, n_rows, base, delta, ld_delta, d, out, ld_out);
+  return cuda_check_launch("encode_onehot_gather_kernel");
+}
+
+extern "C" int gdmcf_mix_rownorm(const float* hc, int64_t ld_hc, const float* g, int64_t ld_g, const float* sumw,
+                                 float* out_f32, int64_t ld_of, void* out_bf16, void* out_lo, int64_t ld_ob,
+                                 float* inv_norm, int rows, int cols, gdmcf_stream_t stream) {
+  if (!hc || rows <= 0 || cols <= 0 || ld_hc < cols || (g && (ld_g < cols || !sumw)) || (out_f32 && ld_of < cols) ||
+      (out_bf16 && ld_ob < cols) || (!out_bf16 && out_lo)) {
+    set_error("mix_rownorm: bad arguments");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  if (!out_bf16) ld_ob = cols;
+  mix_rownorm_kernel<<<grid_1d(rows, 1), TPB, 0, st>>>(hc, ld_hc, g, ld_g, sumw, out_f32, ld_of, (__nv_bfloat16*)out_bf16,
+                                                       (__nv_bfloat16*)out_lo, ld_ob, inv_norm, rows, cols);
+  return cuda_check_launch("mix_rownorm_kernel");
+}
+
+extern "C" int gdmcf_row_inv_norm(const float* x, int64_t ld, float* inv_norm, int rows, int cols, gdmcf_stream_t stream) {
+  if (!x || !inv_norm || rows <= 0 || cols <= 0 || ld < cols) { set_error("row_inv_norm: bad arguments"); return GDMCF_EBADARG; }
+  GD_PRE();
+  row_inv_norm_kernel<<<grid_1d((long long)rows * 32), TPB, 0, st>>>(x, ld, inv_norm, rows, cols);
+  return cuda_check_launch("row_inv_norm_kernel");
+}
+
+extern "C" int gdmcf_mse_rows(const float* out, int64_t ld_out, const float* x0, int64_t ld_x0, int rows, int cols,
+                              float* mse, gdmcf_stream_t stream) {
+  if (!out || !x0 || !mse || rows <= 0 || cols <= 0 || ld_out < cols || ld_x0 < cols) { set_error("mse_rows: bad arguments"); return GDMCF_EBADARG; }
+  GD_PRE();
+  mse_rows_kernel<<<grid_1d(rows, 1), TPB, 0, st>>>(out, ld_out, x0, ld_x0, rows, cols, mse);
+  return cuda_check_launch("mse_rows_kernel");
+}
+
+extern "C" int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                 gdmcf_stream_t stream) {
+  if (!p || !g || !m || !v || n <= 0 || step < 1) { set_error("adamw_fused: bad arguments (step counts from 1)"); return GDMCF_EBADARG; }
+  GD_PRE();
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adamw_kernel<<<grid_1d(n), TPB, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+  return cuda_check_launch("adamw_kernel");
+}

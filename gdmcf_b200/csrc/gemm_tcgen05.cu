@@ -1,0 +1,474 @@
+// Denoiser contractions on the 5th-gen tensor cores.
+//
+//   C[M,N] = sum_s A_s[M,K_s] * B_s[N,K_s]^T        (bf16 operands, fp32 accumulation)
+//
+// One persistent CTA per SM walks work units (m-block fastest so that the CTAs running side by side
+// share the weight tile in L2). Per CTA, warp-specialised:
+//   warp 0     TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 4-stage smem ring
+//   warp 1     MMA issuer     : one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
+//   warp 2     TMEM allocator : 2 accumulator stages (double-buffered against the epilogue)
+//   warps 4-7  epilogue       : tcgen05.ld 32x32b -> fused epilogue (bias/tanh/relu, cosine scale +
+//                               posterior mean) -> vectorised global stores (fp32 and/or bf16 hi/lo)
+// Split-K units write fp32 partial slabs; splitk_reduce_kernel sums them in fixed order
+// (deterministic) and applies the same epilogue.
+//
+// Reference call sites replaced: nn.Linear at models/DNN.py:79-86, :1240-1252, GCNConv linears on the
+// user rows :1082-1100, torch.mm + norm division :1320-1325, posterior mean
+// models/gaussian_diffusion.py:1041-1050.
+#include <cuda.h>
+#include "common.cuh"
+#include "api_internal.h"
+
+namespace gd {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // power of two: 256 or 512
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for alignment slack
+};
+
+struct TmaMaps {
+  CUtensorMap a[GDMCF_MAX_SEG];
+  CUtensorMap b[GDMCF_MAX_SEG];
+};
+
+struct Shape {
+  int m, n;
+  int n_seg;
+  int kb[GDMCF_MAX_SEG];  // k-blocks per segment
+  int total_kb;
+  int tiles_m, tiles_n;
+  int splits, kb_per_split;
+  long long slab_stride;  // elements between split slabs (fp32)
+  int ld_ws;              // leading dim of a slab
+  float* ws;              // split-K workspace (NULL when splits == 1)
+};
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue on 8 consecutive columns of one row (shared by the GEMM and the split-K reducer).
+// ---------------------------------------------------------------------------------------------
+GD_DEV void store8_f32(float* dst, const float (&o)[8], int valid, bool vec_ok) {
+  if (valid == 8 && vec_ok) {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < valid) dst[j] = o[j];
+  }
+}
+GD_DEV void store8_bf16(__nv_bfloat16* dst, const __nv_bfloat16 (&h)[8], int valid) {
+  if (valid == 8) {
+    uint4 pk;
+    pk.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    pk.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    pk.z = (uint32_t)__bfloat16_as_ushort(h[4]) | ((uint32_t)__bfloat16_as_ushort(h[5]) << 16);
+    pk.w = (uint32_t)__bfloat16_as_ushort(h[6]) | ((uint32_t)__bfloat16_as_ushort(h[7]) << 16);
+    *reinterpret_cast<uint4*>(dst) = pk;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < valid) dst[j] = h[j];
+  }
+}
+
+// acc: 8 accumulator values of row m, columns n0..n0+7 (n0 % 8 == 0); N = logical column count.
+GD_DEV void epilogue8(const gdmcf_epilogue& e, int m, int n0, int N, const float (&acc)[8]) {
+  const int valid = min(8, N - n0);
+  if (valid <= 0) return;
+  float o[8];
+  const int t = e.row_t ? e.row_t[m] : e.t_const;
+  if (e.mode == GDMCF_EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = e.alpha * acc[j];
+  } else if (e.mode == GDMCF_EPI_BIAS_ACT) {
+    const float* bias = e.bias ? e.bias + (long long)t * e.ld_bias + n0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = e.alpha * acc[j] + ((bias && j < valid) ? bias[j] : 0.f);
+      if (e.act == GDMCF_ACT_TANH) v = tanhf(v);
+      else if (e.act == GDMCF_ACT_RELU) v = fmaxf(v, 0.f);
+      o[j] = v;
+    }
+  } else {  // GDMCF_EPI_COSINE
+    const float rs = e.alpha * e.row_scale[m];
+    float c1 = 1.f, c2 = 0.f;
+    const float* xt = nullptr;
+    if (e.c1) {
+      c1 = e.c1[t];
+      c2 = e.c2[t];
+      xt = e.xt + (long long)m * e.ld_xt + n0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = (j < valid) ? acc[j] * rs * e.col_scale[n0 + j] : 0.f;
+      // same association as the reference: coef1 * pred_xstart + coef2 * x_t
+      o[j] = (xt && j < valid) ? c1 * s + c2 * xt[j] : s;
+    }
+  }
+  if (e.out_f32) {
+    float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
+    store8_f32(dst, o, valid, (e.ld_f32 & 3) == 0);
+  }
+  if (e.out_bf16) {
+    __nv_bfloat16 h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __float2bfloat16_rn(o[j]);
+    store8_bf16(reinterpret_cast<__nv_bfloat16*>(e.out_bf16) + (long long)m * e.ld_bf16 + n0, h, valid);
+    if (e.out_bf16_lo) {
+      __nv_bfloat16 l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) l[j] = __float2bfloat16_rn(o[j] - __bfloat162float(h[j]));
+      store8_bf16(reinterpret_cast<__nv_bfloat16*>(e.out_bf16_lo) + (long long)m * e.ld_bf16 + n0, l, valid);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Main kernel
+// ---------------------------------------------------------------------------------------------
+struct UnitCoord {
+  int m_blk, n_blk, split, kb_begin, kb_end;
+};
+GD_DEV UnitCoord unit_coord(const Shape& s, int unit) {
+  UnitCoord u;
+  u.m_blk = unit % s.tiles_m;
+  int r = unit / s.tiles_m;
+  u.n_blk = r % s.tiles_n;
+  u.split = r / s.tiles_n;
+  u.kb_begin = u.split * s.kb_per_split;
+  u.kb_end = min(u.kb_begin + s.kb_per_split, s.total_kb);
+  return u;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, const gdmcf_epilogue epi) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024 B alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_units = shape.tiles_m * shape.tiles_n * shape.splits;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < shape.n_seg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    mbar_init_fence();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const UnitCoord u = unit_coord(shape, unit);
+        // locate (segment, k-block within segment) of kb_begin
+        int seg = 0, kb_in_seg = u.kb_begin;
+        while (kb_in_seg >= shape.kb[seg]) { kb_in_seg -= shape.kb[seg]; ++seg; }
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_2d(sa, &maps.a[seg], &full_bar[stage], kb_in_seg * BK, u.m_blk * BM);
+          tma_load_2d(sb, &maps.b[seg], &full_bar[stage], kb_in_seg * BK, u.n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++kb_in_seg == shape.kb[seg]) { kb_in_seg = 0; ++seg; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local) {
+        const UnitCoord u = unit_coord(shape, unit);
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                      (kb > u.kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ================= epilogue =================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local) {
+      const UnitCoord u = unit_coord(shape, unit);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = u.m_blk * BM + ew * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const int n_tile0 = u.n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n_tile0 + c >= shape.n) break;  // warp-uniform
+        float v[32];
+        tmem_ld_32x32(t_row + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (m < shape.m) {
+          if (shape.ws) {
+            float* dst = shape.ws + (long long)u.split * shape.slab_stride + (long long)m * shape.ld_ws + n_tile0 + c;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (n_tile0 + c + q * 4 < shape.ld_ws)
+                reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) a8[j] = v[q * 8 + j];
+              epilogue8(epi, m, n_tile0 + c + q * 8, shape.n, a8);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// Sum split-K slabs in fixed order and apply the epilogue. One thread per 8 columns.
+__global__ void splitk_reduce_kernel(const Shape shape, const gdmcf_epilogue epi) {
+  const int groups = (shape.n + 7) / 8;
+  const long long total = (long long)shape.m * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / groups);
+    const int n0 = (int)(i % groups) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = shape.ws + (long long)m * shape.ld_ws + n0;
+    for (int s = 0; s < shape.splits; ++s) {
+      const float4 x = reinterpret_cast<const float4*>(src)[0];
+      const float4 y = reinterpret_cast<const float4*>(src)[1];
+      acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+      acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
+      src += shape.slab_stride;
+    }
+    epilogue8(epi, m, n0, shape.n, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dim ld; box = [box_rows, 64 cols], 128B swizzle,
+// out-of-bounds elements are zero-filled (K tails and M/N tails need no special casing).
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return GDMCF_ECUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (rows=%d cols=%d ld=%lld ptr=%p) -> %d", rows, cols, ld, ptr, (int)r);
+    return GDMCF_EBADARG;
+  }
+  return GDMCF_OK;
+}
+
+static int pick_bn(int n) { return n <= 128 ? 128 : 256; }
+
+template <int BN>
+static int launch(const TmaMaps& maps, const Shape& shape, const gdmcf_epilogue& epi, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<BN>::SMEM_BYTES);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(gemm)");
+    attr_set = true;
+  }
+  gemm_bf16_tn_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps, shape, epi);
+  return cuda_check_launch("gemm_bf16_tn_kernel");
+}
+
+}  // namespace gemm
+}  // namespace gd
+
+using namespace gd;
+using namespace gd::gemm;
+
+extern "C" int gdmcf_gemm_auto_splits(int m, int n, int k_total) {
+  if (m <= 0 || n <= 0 || k_total <= 0) return 1;
+  const int bn = pick_bn(n);
+  const int tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
+  const int total_kb = (k_total + BK - 1) / BK;
+  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  if (tiles >= sms) return 1;
+  int splits = sms / tiles;
+  // keep at least 4 k-blocks per split so the pipeline prologue stays amortised
+  splits = std::min(splits, std::max(1, total_kb / 4));
+  splits = std::max(splits, 1);
+  const int per = (total_kb + splits - 1) / splits;
+  return (total_kb + per - 1) / per;
+}
+
+extern "C" size_t gdmcf_gemm_workspace_bytes(int m, int n, int splits) {
+  if (splits <= 1) return 0;
+  const size_t ld = ((size_t)n + 31) / 32 * 32;
+  return (size_t)splits * (size_t)m * ld * sizeof(float);
+}
+
+extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue* e, int splits, void* workspace,
+                                  size_t workspace_bytes, gdmcf_stream_t stream) {
+  if (!g || !e) { set_error("gemm: null descriptor"); return GDMCF_EBADARG; }
+  if (g->m <= 0 || g->n <= 0 || g->n_seg < 1 || g->n_seg > GDMCF_MAX_SEG) {
+    set_error("gemm: bad shape m=%d n=%d n_seg=%d", g->m, g->n, g->n_seg);
+    return GDMCF_EBADARG;
+  }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  const int bn = pick_bn(g->n);
+  Shape shape{};
+  shape.m = g->m;
+  shape.n = g->n;
+  shape.n_seg = g->n_seg;
+  shape.total_kb = 0;
+  TmaMaps maps;
+  for (int s = 0; s < g->n_seg; ++s) {
+    if (g->k[s] <= 0 || (g->lda[s] & 7) || (g->ldb[s] & 7) || ((uintptr_t)g->a[s] & 15) || ((uintptr_t)g->b[s] & 15) ||
+        g->lda[s] < g->k[s] || g->ldb[s] < g->k[s]) {
+      set_error("gemm: segment %d needs k>0, ld%%8==0, ld>=k, 16B-aligned pointers (k=%d lda=%lld ldb=%lld)", s,
+                g->k[s], (long long)g->lda[s], (long long)g->ldb[s]);
+      return GDMCF_EBADARG;
+    }
+    shape.kb[s] = (g->k[s] + BK - 1) / BK;
+    shape.total_kb += shape.kb[s];
+    if ((rc = make_map(&maps.a[s], g->a[s], g->m, g->k[s], g->lda[s], BM))) return rc;
+    if ((rc = make_map(&maps.b[s], g->b[s], g->n, g->k[s], g->ldb[s], bn))) return rc;
+  }
+  if (e->mode < 0 || e->mode > GDMCF_EPI_COSINE) { set_error("gemm: bad epilogue mode %d", e->mode); return GDMCF_EBADARG; }
+  if (e->mode == GDMCF_EPI_COSINE && (!e->row_scale || !e->col_scale || (e->c1 && (!e->c2 || !e->xt)))) {
+    set_error("gemm: cosine epilogue needs row_scale, col_scale (and c2, xt with c1)");
+    return GDMCF_EBADARG;
+  }
+  if ((e->out_bf16 && ((e->ld_bf16 & 7) || ((uintptr_t)e->out_bf16 & 15))) ||
+      (e->out_f32 && ((uintptr_t)e->out_f32 & 15)) || (!e->out_f32 && !e->out_bf16)) {
+    set_error("gemm: epilogue outputs need 16B alignment, ld_bf16%%8==0, and at least one output");
+    return GDMCF_EBADARG;
+  }
+  shape.tiles_m = (g->m + BM - 1) / BM;
+  shape.tiles_n = (g->n + bn - 1) / bn;
+  splits = std::max(1, std::min(splits, shape.total_kb));
+  shape.kb_per_split = (shape.total_kb + splits - 1) / splits;
+  shape.splits = (shape.total_kb + shape.kb_per_split - 1) / shape.kb_per_split;
+  shape.ws = nullptr;
+  if (shape.splits > 1) {
+    const size_t need = gdmcf_gemm_workspace_bytes(g->m, g->n, shape.splits);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15)) {
+      set_error("gemm: split-K workspace too small (%zu < %zu) or misaligned", workspace_bytes, need);
+      return GDMCF_EBADARG;
+    }
+    shape.ws = reinterpret_cast<float*>(workspace);
+    shape.ld_ws = (g->n + 31) / 32 * 32;
+    shape.slab_stride = (long long)g->m * shape.ld_ws;
+  }
+  const int num_units = shape.tiles_m * shape.tiles_n * shape.splits;
+  const int sms = gdmcf_num_sms();
+  const int grid = std::min(num_units, sms > 0 ? sms : 148);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  rc = (bn == 256) ? launch<256>(maps, shape, *e, grid, st) : launch<128>(maps, shape, *e, grid, st);
+  if (rc) return rc;
+  if (shape.splits > 1) {
+    const long long total = (long long)g->m * ((g->n + 7) / 8);
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)(sms > 0 ? sms : 148) * 8);
+    splitk_reduce_kernel<<<blocks, threads, 0, st>>>(shape, *e);
+    rc = cuda_check_launch("splitk_reduce_kernel");
+  }
+  return rc;
+}

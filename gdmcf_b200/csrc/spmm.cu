@@ -1,0 +1,288 @@
+// K1 — normalized-adjacency propagation: Y = alpha * (A~ X) + beta * Z on a CSR adjacency.
+//
+// HBM-bound gather kernel (no tensor cores: there is no dense operand to feed them).
+//  * Work is pre-split on the host (gdmcf_spmm_plan) into items of <= chunk non-zeros, so hub rows
+//    (Zipf-head items touch tens of thousands of users) are spread over many warps; their partial sums
+//    land in a scratch slab and a second tiny kernel reduces them in fixed order (deterministic, no atomics).
+//  * One warp per item: the 32 lanes load 32 (col,val) pairs with one coalesced, L1-bypassing request,
+//    broadcast them by shuffle, and gather the neighbour rows as float2 per lane (a 64-float row = two
+//    fully-used 128 B lines per request), 8 independent gathers in flight per warp. Gathers allocate in
+//    L1 (hot Zipf-head rows hit there); streams (col/val/Z/Y) do not.
+//  * The LightGCN layer mean is folded in as a Horner recurrence T <- A~ T + E0, so no per-layer
+//    embedding stack is ever materialised (lightGCN.py:188-189 does stack + mean).
+//
+// Reference: lightGCN.py:145-194 (get_A_tilda, propagate_through_layers); GCNConv propagate at
+// models/DNN.py:1095,1100.
+#include "common.cuh"
+#include "api_internal.h"
+
+namespace gd {
+namespace spmm {
+
+GD_DEV int ld_stream_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+GD_DEV float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+GD_DEV float2 ld_stream_f32x2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
+constexpr int GATHER_UNROLL = 8;
+constexpr int WARPS_PER_CTA = 8;
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, const int4* __restrict__ items,
+                  int n_items, const float* __restrict__ X, const float* __restrict__ Z, float* __restrict__ Y,
+                  float* __restrict__ scratch, int d, float alpha, float beta) {
+  const int lane = threadIdx.x & 31;
+  const int slabs = d >> 6;
+  const long long total = (long long)n_items * slabs;
+  const long long warp0 = (long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * WARPS_PER_CTA;
+  for (long long w = warp0; w < total; w += nwarps) {
+    const int item = (int)(w / slabs);
+    const int coff = (int)(w % slabs) * 64 + lane * 2;
+    const int4 it = __ldg(&items[item]);  // {row, begin, end, slot}
+    float2 acc = make_float2(0.f, 0.f);
+    for (int base = it.y; base < it.z; base += 32) {
+      const int n = min(32, it.z - base);
+      int my_c = 0;
+      float my_v = 0.f;
+      if (lane < n) {
+        my_c = ld_stream_i32(col + base + lane);
+        my_v = ld_stream_f32(val + base + lane);
+      }
+      for (int j0 = 0; j0 < n; j0 += GATHER_UNROLL) {
+        float2 x[GATHER_UNROLL];
+        float v[GATHER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; ++u) {
+          const int c = __shfl_sync(0xffffffffu, my_c, (j0 + u) & 31);
+          v[u] = __shfl_sync(0xffffffffu, my_v, (j0 + u) & 31);
+          x[u] = make_float2(0.f, 0.f);
+          if (j0 + u < n) x[u] = __ldg(reinterpret_cast<const float2*>(X + (long long)c * d + coff));
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; ++u) {
+          if (j0 + u < n) {  // warp-uniform; keeps the CSR summation order
+            acc.x = fmaf(v[u], x[u].x, acc.x);
+            acc.y = fmaf(v[u], x[u].y, acc.y);
+          }
+        }
+      }
+    }
+    if (it.w < 0) {
+      float2 o = make_float2(alpha * acc.x, alpha * acc.y);
+      if (Z) {
+        const float2 z = ld_stream_f32x2(Z + (long long)it.x * d + coff);
+        o.x = fmaf(beta, z.x, o.x);
+        o.y = fmaf(beta, z.y, o.y);
+      }
+      *reinterpret_cast<float2*>(Y + (long long)it.x * d + coff) = o;
+    } else {
+      *reinterpret_cast<float2*>(scratch + (long long)it.w * d + coff) = acc;
+    }
+  }
+}
+
+// long_rows: {row, first_slot, n_slots}; one warp per (row, 64-column slab).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+spmm_long_reduce_kernel(const int* __restrict__ long_rows, int n_long, const float* __restrict__ scratch,
+                        const float* __restrict__ Z, float* __restrict__ Y, int d, float alpha, float beta) {
+  const int lane = threadIdx.x & 31;
+  const int slabs = d >> 6;
+  const long long total = (long long)n_long * slabs;
+  const long long warp0 = (long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * WARPS_PER_CTA;
+  for (long long w = warp0; w < total; w += nwarps) {
+    const int lr = (int)(w / slabs);
+    const int coff = (int)(w % slabs) * 64 + lane * 2;
+    const int row = long_rows[3 * lr], first = long_rows[3 * lr + 1], cnt = long_rows[3 * lr + 2];
+    float2 acc = make_float2(0.f, 0.f);
+    for (int s = 0; s < cnt; ++s) {
+      const float2 p = *reinterpret_cast<const float2*>(scratch + (long long)(first + s) * d + coff);
+      acc.x += p.x;
+      acc.y += p.y;
+    }
+    float2 o = make_float2(alpha * acc.x, alpha * acc.y);
+    if (Z) {
+      const float2 z = *reinterpret_cast<const float2*>(Z + (long long)row * d + coff);
+      o.x = fmaf(beta, z.x, o.x);
+      o.y = fmaf(beta, z.y, o.y);
+    }
+    *reinterpret_cast<float2*>(Y + (long long)row * d + coff) = o;
+  }
+}
+
+// A~ = D^-1/2 [[0,R],[R^T,0]] D^-1/2, d_inv = (rowsum + 1e-9)^-1/2 (lightGCN.py:145-178). One thread per row.
+__global__ void norm_adj_rowptr_kernel(const int* __restrict__ r_rowptr, const int* __restrict__ rt_rowptr,
+                                       int n_users, int n_items, int* __restrict__ rowptr_out) {
+  const int n = n_users + n_items;
+  const int nnz = r_rowptr[n_users];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x)
+    rowptr_out[r] = (r <= n_users) ? r_rowptr[r] : nnz + rt_rowptr[r - n_users];
+}
+GD_DEV float d_inv_of(int deg) { return 1.0f / sqrtf((float)deg + 1e-9f); }
+__global__ void norm_adj_fill_kernel(const int* __restrict__ r_rowptr, const int* __restrict__ r_col,
+                                     const int* __restrict__ rt_rowptr, const int* __restrict__ rt_col, int n_users,
+                                     int n_items, int* __restrict__ col_out, float* __restrict__ val_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = n_users + n_items;
+  const int nnz = r_rowptr[n_users];
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp0; r < n; r += nwarps) {
+    if (r < n_users) {
+      const int b = r_rowptr[r], e = r_rowptr[r + 1];
+      const float du = d_inv_of(e - b);
+      for (int j = b + lane; j < e; j += 32) {
+        const int i = r_col[j];
+        const float di = d_inv_of(rt_rowptr[i + 1] - rt_rowptr[i]);
+        col_out[j] = n_users + i;
+        val_out[j] = du * di;
+      }
+    } else {
+      const int i = r - n_users;
+      const int b = rt_rowptr[i], e = rt_rowptr[i + 1];
+      const float di = d_inv_of(e - b);
+      for (int j = b + lane; j < e; j += 32) {
+        const int u = rt_col[j];
+        const float du = d_inv_of(r_rowptr[u + 1] - r_rowptr[u]);
+        col_out[nnz + j] = u;
+        val_out[nnz + j] = di * du;
+      }
+    }
+  }
+}
+
+static int grid_for_warps(long long warps) {
+  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  const long long ctas = (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sms * 16));
+}
+
+}  // namespace spmm
+}  // namespace gd
+
+using namespace gd;
+using namespace gd::spmm;
+
+extern "C" int gdmcf_spmm_plan(const int32_t* rowptr, int n_rows, int chunk, int32_t* items_out, int cap_items,
+                               int32_t* long_out, int cap_long, int* n_items, int* n_long, int* n_slots) {
+  if (!rowptr || n_rows < 0 || chunk < 32) { set_error("spmm_plan: bad arguments (chunk must be >= 32)"); return GDMCF_EBADARG; }
+  // Long-row chunks first (they are the heaviest items), then whole rows.
+  long long ni = 0, nl = 0, ns = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int r = 0; r < n_rows; ++r) {
+      const int b = rowptr[r], e = rowptr[r + 1];
+      const int deg = e - b;
+      if (deg < 0) { set_error("spmm_plan: rowptr not monotone at row %d", r); return GDMCF_EBADARG; }
+      const bool is_long = deg > chunk;
+      if (pass == 0 && is_long) {
+        const int pieces = (deg + chunk - 1) / chunk;
+        if (long_out) {
+          if (nl >= cap_long) { set_error("spmm_plan: long_out capacity %d too small", cap_long); return GDMCF_EBADARG; }
+          long_out[3 * nl] = r; long_out[3 * nl + 1] = (int)ns; long_out[3 * nl + 2] = pieces;
+        }
+        for (int p = 0; p < pieces; ++p) {
+          if (items_out) {
+            if (ni >= cap_items) { set_error("spmm_plan: items_out capacity %d too small", cap_items); return GDMCF_EBADARG; }
+            items_out[4 * ni] = r;
+            items_out[4 * ni + 1] = b + p * chunk;
+            items_out[4 * ni + 2] = std::min(e, b + (p + 1) * chunk);
+            items_out[4 * ni + 3] = (int)(ns + p);
+          }
+          ++ni;
+        }
+        ns += pieces;
+        ++nl;
+      } else if (pass == 1 && !is_long) {
+        if (items_out) {
+          if (ni >= cap_items) { set_error("spmm_plan: items_out capacity %d too small", cap_items); return GDMCF_EBADARG; }
+          items_out[4 * ni] = r; items_out[4 * ni + 1] = b; items_out[4 * ni + 2] = e; items_out[4 * ni + 3] = -1;
+        }
+        ++ni;
+      }
+    }
+  }
+  if (n_items) *n_items = (int)ni;
+  if (n_long) *n_long = (int)nl;
+  if (n_slots) *n_slots = (int)ns;
+  return GDMCF_OK;
+}
+
+extern "C" int gdmcf_spmm_csr_f32(const int32_t* col, const float* val, const int32_t* items, int n_items,
+                                  const int32_t* long_rows, int n_long, const float* X, const float* Z, float* Y,
+                                  float* scratch, int n_rows, int d, float alpha, float beta, gdmcf_stream_t stream) {
+  (void)n_rows;
+  if (!col || !val || !items || !X || !Y || n_items < 0 || d <= 0 || (d & 63)) {
+    set_error("spmm: need col/val/items/X/Y and d %% 64 == 0 (d=%d)", d);
+    return GDMCF_EBADARG;
+  }
+  if (n_long > 0 && (!long_rows || !scratch)) { set_error("spmm: long rows need long_rows and scratch"); return GDMCF_EBADARG; }
+  if (((uintptr_t)X | (uintptr_t)Y | (uintptr_t)Z | (uintptr_t)scratch | (uintptr_t)items) & 15) {
+    set_error("spmm: X/Y/Z/scratch/items must be 16B aligned");
+    return GDMCF_EBADARG;
+  }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int slabs = d >> 6;
+  if (n_items > 0) {
+    spmm_items_kernel<<<grid_for_warps((long long)n_items * slabs), WARPS_PER_CTA * 32, 0, st>>>(
+        col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y, scratch, d, alpha, beta);
+    if ((rc = cuda_check_launch("spmm_items_kernel"))) return rc;
+  }
+  if (n_long > 0) {
+    spmm_long_reduce_kernel<<<grid_for_warps((long long)n_long * slabs), WARPS_PER_CTA * 32, 0, st>>>(
+        long_rows, n_long, scratch, Z, Y, d, alpha, beta);
+    if ((rc = cuda_check_launch("spmm_long_reduce_kernel"))) return rc;
+  }
+  return GDMCF_OK;
+}
+
+extern "C" int gdmcf_lightgcn_propagate_f32(const int32_t* col, const float* val, const int32_t* items, int n_items,
+                                            const int32_t* long_rows, int n_long, const float* E0, float* tmp0,
+                                            float* tmp1, float* out, float* scratch, int n, int d, int n_layers,
+                                            gdmcf_stream_t stream) {
+  if (n_layers < 1 || !E0 || !out || (n_layers > 1 && !tmp0) || (n_layers > 2 && !tmp1)) {
+    set_error("lightgcn_propagate: need n_layers >= 1, E0, out and ping-pong buffers");
+    return GDMCF_EBADARG;
+  }
+  // T_1 = A E0 + E0; T_{k+1} = A T_k + E0; out = T_K / (K + 1)  ==  mean_k A^k E0.
+  const float* src = E0;
+  for (int l = 0; l < n_layers; ++l) {
+    const bool last = (l == n_layers - 1);
+    float* dst = last ? out : ((l & 1) ? tmp1 : tmp0);
+    const float s = last ? 1.0f / (float)(n_layers + 1) : 1.0f;
+    int rc = gdmcf_spmm_csr_f32(col, val, items, n_items, long_rows, n_long, src, E0, dst, scratch, n, d, s, s, stream);
+    if (rc) return rc;
+    src = dst;
+  }
+  return GDMCF_OK;
+}
+
+extern "C" int gdmcf_build_norm_adj(const int32_t* r_rowptr, const int32_t* r_col, const int32_t* rt_rowptr,
+                                    const int32_t* rt_col, int n_users, int n_items, int32_t* rowptr_out,
+                                    int32_t* col_out, float* val_out, gdmcf_stream_t stream) {
+  if (!r_rowptr || !r_col || !rt_rowptr || !rt_col || !rowptr_out || !col_out || !val_out || n_users <= 0 || n_items <= 0) {
+    set_error("build_norm_adj: null pointer or empty shape");
+    return GDMCF_EBADARG;
+  }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n = n_users + n_items;
+  norm_adj_rowptr_kernel<<<std::min(1024, ceil_div(n + 1, 256)), 256, 0, st>>>(r_rowptr, rt_rowptr, n_users, n_items, rowptr_out);
+  if ((rc = cuda_check_launch("norm_adj_rowptr_kernel"))) return rc;
+  norm_adj_fill_kernel<<<std::min(148 * 16, ceil_div(n, 8)), 256, 0, st>>>(r_rowptr, r_col, rt_rowptr, rt_col, n_users, n_items, col_out, val_out);
+  return cuda_check_launch("norm_adj_fill_kernel");
+}

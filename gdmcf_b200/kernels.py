@@ -1,0 +1,330 @@
+"""Typed Python wrappers over the C ABI (one function per entry point of include/gdmcf_sm100.h).
+
+Tensors are only containers for device memory; all arithmetic happens in libgdmcf_sm100.so.
+Padded matrices: bf16 operands live in `[rows, ld]` tensors with `ld = round_up(cols, 64)` so every
+TMA row stride is 16-byte aligned and K tails are zero.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BIAS_ACT, EPI_COSINE, EPI_STORE, Epilogue, GemmDesc,
+                   check, load, ptr, require_cuda, stream)
+
+__all__ = [
+    "ACT_NONE", "ACT_RELU", "ACT_TANH", "EPI_BIAS_ACT", "EPI_COSINE", "EPI_STORE", "round_up", "Bf16Mat",
+    "SpmmPlan", "spmm_plan", "spmm_csr", "lightgcn_propagate", "build_norm_adj", "gemm", "cast_bf16",
+    "cast_bf16_transpose", "densify_rows", "qsample_dropout", "onehot_noise", "onehot_tables",
+    "encode_onehot_gather", "mix_rownorm", "row_inv_norm", "mask_topk", "topn_metrics", "colsum_f64",
+    "mse_rows", "adamw_fused",
+]
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class Bf16Mat:
+    """bf16 operand [rows, cols] stored with leading dimension ld; `lo` holds the residual for fp32 mode."""
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor]
+    rows: int
+    cols: int
+
+    @property
+    def ld(self) -> int:
+        return self.hi.shape[1]
+
+    @staticmethod
+    def empty(rows: int, cols: int, device, with_lo: bool = False, zero: bool = True) -> "Bf16Mat":
+        ld = round_up(cols, 64)
+        mk = torch.zeros if zero else torch.empty
+        hi = mk(rows, ld, dtype=torch.bfloat16, device=device)
+        lo = mk(rows, ld, dtype=torch.bfloat16, device=device) if with_lo else None
+        return Bf16Mat(hi, lo, rows, cols)
+
+    def float(self) -> torch.Tensor:
+        """Debug/test helper: reconstruct fp32 [rows, cols]."""
+        x = self.hi[:, : self.cols].float()
+        if self.lo is not None:
+            x = x + self.lo[:, : self.cols].float()
+        return x
+
+
+# ----------------------------------------------------------------------------------------------
+# SpMM
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class SpmmPlan:
+    items: torch.Tensor       # int32 [n_items, 4]
+    long_rows: torch.Tensor   # int32 [n_long, 3]
+    n_items: int
+    n_long: int
+    n_slots: int
+    n_rows: int
+    chunk: int
+
+
+def spmm_plan(rowptr, chunk: int = 256, device="cuda") -> SpmmPlan:
+    """Host-side work split (gdmcf_spmm_plan). rowptr: int32 numpy/CPU tensor [n_rows + 1]."""
+    lib = load()
+    rp = np.ascontiguousarray(rowptr.cpu().numpy() if isinstance(rowptr, torch.Tensor) else rowptr, dtype=np.int32)
+    n_rows = rp.shape[0] - 1
+    ni, nl, ns = C.c_int(0), C.c_int(0), C.c_int(0)
+    rpp = rp.ctypes.data_as(C.c_void_p)
+    check(lib.gdmcf_spmm_plan(rpp, n_rows, chunk, None, 0, None, 0, C.byref(ni), C.byref(nl), C.byref(ns)), "spmm_plan(query)")
+    items = np.empty((max(ni.value, 1), 4), dtype=np.int32)
+    longs = np.empty((max(nl.value, 1), 3), dtype=np.int32)
+    check(lib.gdmcf_spmm_plan(rpp, n_rows, chunk, items.ctypes.data_as(C.c_void_p), ni.value,
+                              longs.ctypes.data_as(C.c_void_p), nl.value, C.byref(ni), C.byref(nl), C.byref(ns)), "spmm_plan")
+    return SpmmPlan(torch.from_numpy(items).to(device), torch.from_numpy(longs).to(device), ni.value, nl.value,
+                    ns.value, n_rows, chunk)
+
+
+def spmm_csr(plan: SpmmPlan, col, val, X, Z=None, alpha: float = 1.0, beta: float = 0.0, out=None, scratch=None):
+    require_cuda(col, val, X, Z)
+    n_rows, d = plan.n_rows, X.shape[1]
+    assert X.dtype == torch.float32 and X.is_contiguous()
+    if out is None:
+        out = torch.empty(n_rows, d, dtype=torch.float32, device=X.device)
+    if scratch is None and plan.n_slots > 0:
+        scratch = torch.empty(plan.n_slots, d, dtype=torch.float32, device=X.device)
+    check(load().gdmcf_spmm_csr_f32(ptr(col), ptr(val), ptr(plan.items), plan.n_items, ptr(plan.long_rows), plan.n_long,
+                                    ptr(X), ptr(Z), ptr(out), ptr(scratch), n_rows, d, alpha, beta, stream()), "spmm_csr_f32")
+    return out
+
+
+def lightgcn_propagate(plan: SpmmPlan, col, val, E0, n_layers: int, out=None, work=None):
+    """mean_{k<=K} A^k E0 (lightGCN.py:180-194). `work` = (tmp0, tmp1, scratch) to avoid reallocation."""
+    require_cuda(col, val, E0)
+    n, d = E0.shape
+    assert n == plan.n_rows and E0.dtype == torch.float32 and E0.is_contiguous()
+    if out is None:
+        out = torch.empty_like(E0)
+    if work is None:
+        work = (torch.empty_like(E0), torch.empty_like(E0),
+                torch.empty(max(plan.n_slots, 1), d, dtype=torch.float32, device=E0.device))
+    tmp0, tmp1, scratch = work
+    check(load().gdmcf_lightgcn_propagate_f32(ptr(col), ptr(val), ptr(plan.items), plan.n_items, ptr(plan.long_rows),
+                                              plan.n_long, ptr(E0), ptr(tmp0), ptr(tmp1), ptr(out), ptr(scratch), n, d,
+                                              n_layers, stream()), "lightgcn_propagate_f32")
+    return out
+
+
+def build_norm_adj(r_rowptr, r_col, rt_rowptr, rt_col, n_users: int, n_items: int):
+    require_cuda(r_rowptr, r_col, rt_rowptr, rt_col)
+    nnz = r_col.numel()
+    dev = r_col.device
+    rowptr = torch.empty(n_users + n_items + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(2 * nnz, dtype=torch.int32, device=dev)
+    val = torch.empty(2 * nnz, dtype=torch.float32, device=dev)
+    check(load().gdmcf_build_norm_adj(ptr(r_rowptr), ptr(r_col), ptr(rt_rowptr), ptr(rt_col), n_users, n_items,
+                                      ptr(rowptr), ptr(col), ptr(val), stream()), "build_norm_adj")
+    return rowptr, col, val
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM
+# ----------------------------------------------------------------------------------------------
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def gemm(a: Sequence[torch.Tensor], b: Sequence[torch.Tensor], m: int, n: int, k: Sequence[int], *,
+         mode: int = EPI_STORE, act: int = ACT_NONE, alpha: float = 1.0, out_f32=None, out_bf16=None, out_bf16_lo=None,
+         bias=None, ld_bias: int = 0, row_t=None, t_const: int = 0, row_scale=None, col_scale=None, c1=None, c2=None,
+         xt=None, splits: Optional[int] = None) -> None:
+    """C[m,n] = sum_s a[s][m,k[s]] @ b[s][n,k[s]]^T with a fused epilogue (gdmcf_gemm_bf16_tn).
+
+    a[s]/b[s]: 2-D bf16 tensors whose stride(0) is the leading dimension (stride(1) == 1)."""
+    lib = load()
+    g = GemmDesc()
+    assert 1 <= len(a) == len(b) == len(k) <= _lib.MAX_SEG
+    for s, (ta, tb, ks) in enumerate(zip(a, b, k)):
+        require_cuda(ta, tb)
+        assert ta.dtype == torch.bfloat16 and tb.dtype == torch.bfloat16 and ta.stride(1) == 1 and tb.stride(1) == 1
+        g.a[s], g.b[s] = ta.data_ptr(), tb.data_ptr()
+        g.lda[s], g.ldb[s] = ta.stride(0), tb.stride(0)
+        g.k[s] = ks
+    g.n_seg, g.m, g.n = len(a), m, n
+    e = Epilogue()
+    e.mode, e.act, e.alpha, e.t_const = mode, act, alpha, t_const
+    for t in (out_f32, out_bf16, out_bf16_lo, xt):
+        assert t is None or t.stride(1) == 1
+    e.out_f32, e.ld_f32 = ptr(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
+    e.out_bf16, e.ld_bf16 = ptr(out_bf16), (out_bf16.stride(0) if out_bf16 is not None else 0)
+    e.out_bf16_lo = ptr(out_bf16_lo)
+    if out_bf16_lo is not None:
+        assert out_bf16 is not None and out_bf16_lo.stride(0) == out_bf16.stride(0)
+    e.bias, e.ld_bias = ptr(bias), ld_bias
+    e.row_t = ptr(row_t)
+    e.row_scale, e.col_scale = ptr(row_scale), ptr(col_scale)
+    e.c1, e.c2 = ptr(c1), ptr(c2)
+    e.xt, e.ld_xt = ptr(xt), (xt.stride(0) if xt is not None else 0)
+    if splits is None:
+        splits = lib.gdmcf_gemm_auto_splits(m, n, int(sum(round_up(x, 64) for x in k)))
+    ws, ws_bytes = None, 0
+    if splits > 1:
+        ws_bytes = lib.gdmcf_gemm_workspace_bytes(m, n, splits)
+        ws = _workspace(ws_bytes, a[0].device)
+    check(lib.gdmcf_gemm_bf16_tn(C.byref(g), C.byref(e), splits, ptr(ws), ws_bytes, stream()), "gemm_bf16_tn")
+
+
+# ----------------------------------------------------------------------------------------------
+# elementwise / layout
+# ----------------------------------------------------------------------------------------------
+def cast_bf16(x: torch.Tensor, with_lo: bool = False, out: Optional[Bf16Mat] = None) -> Bf16Mat:
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = Bf16Mat.empty(rows, cols, x.device, with_lo, zero=False)
+    check(load().gdmcf_cast_bf16(ptr(x), x.stride(0), ptr(out.hi), ptr(out.lo), out.ld, rows, cols, stream()), "cast_bf16")
+    return out
+
+
+def cast_bf16_transpose(x: torch.Tensor, with_lo: bool = False, out: Optional[Bf16Mat] = None) -> Bf16Mat:
+    """Returns x^T as a bf16 operand [cols, rows]."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = Bf16Mat.empty(cols, rows, x.device, with_lo, zero=False)
+    check(load().gdmcf_cast_bf16_transpose(ptr(x), x.stride(0), ptr(out.hi), ptr(out.lo), out.ld, rows, cols, stream()),
+          "cast_bf16_transpose")
+    return out
+
+
+def densify_rows(rowptr, col, users, n_rows: int, n_items: int, out_f32=None, out_bf16=None) -> None:
+    require_cuda(rowptr, col, users, out_f32, out_bf16)
+    check(load().gdmcf_densify_rows(ptr(rowptr), ptr(col), ptr(users), n_rows, n_items, ptr(out_f32),
+                                    out_f32.stride(0) if out_f32 is not None else 0, ptr(out_bf16),
+                                    out_bf16.stride(0) if out_bf16 is not None else 0, stream()), "densify_rows")
+
+
+def qsample_dropout(x0, rows: int, cols: int, a_out: Bf16Mat, *, row_t=None, t_const: int = 0, sqrt_ab=None,
+                    sqrt_1mab=None, noise=None, keep=None, dropout_p: float = 0.0, seed: int = 0, offset: int = 0,
+                    xt_out=None) -> None:
+    require_cuda(x0, a_out.hi, row_t, sqrt_ab, sqrt_1mab, noise, keep, xt_out)
+    if noise is not None:
+        assert noise.is_contiguous() and noise.shape == (rows, cols) and noise.dtype == torch.float32
+    if keep is not None:
+        assert keep.is_contiguous() and keep.shape == (rows, cols) and keep.dtype == torch.uint8
+    check(load().gdmcf_qsample_dropout(ptr(x0), x0.stride(0), ptr(row_t), t_const, ptr(sqrt_ab), ptr(sqrt_1mab), ptr(noise),
+                                       ptr(keep), dropout_p, seed, offset, ptr(xt_out),
+                                       xt_out.stride(0) if xt_out is not None else 0, ptr(a_out.hi), ptr(a_out.lo),
+                                       a_out.ld, rows, cols, stream()), "qsample_dropout")
+
+
+def onehot_noise(x0, rows: int, cols: int, out: torch.Tensor, *, ts=None, discrete: float = 0.9995,
+                 dropout_p: float = 0.0, u_keep=None, u_drop=None, seed: int = 0, offset: int = 0) -> None:
+    require_cuda(x0, out, ts, u_keep, u_drop)
+    assert out.dtype == torch.bfloat16 and out.stride(1) == 1
+    check(load().gdmcf_onehot_noise(ptr(x0), x0.stride(0), ptr(ts), discrete, dropout_p, ptr(u_keep), ptr(u_drop), seed,
+                                    offset, ptr(out), out.stride(0), rows, cols, stream()), "onehot_noise")
+
+
+def onehot_tables(w2: torch.Tensor, d: int, n_items: int):
+    require_cuda(w2)
+    assert w2.dtype == torch.float32 and w2.stride(1) == 1
+    ld_delta = round_up(d, 4)
+    base = torch.empty(d, dtype=torch.float32, device=w2.device)
+    delta = torch.empty(n_items, ld_delta, dtype=torch.float32, device=w2.device)
+    # in_layers2.0.weight is [d, 2I + e]: its row stride is odd when e is; the kernel needs float2-aligned
+    # (2i, 2i+1) pairs, so stage the [d, 2I] block with an even leading dimension first when required.
+    if w2.stride(0) % 2 or w2.data_ptr() % 8:
+        w2 = w2[:, : 2 * n_items].contiguous()
+    check(load().gdmcf_onehot_tables(ptr(w2), w2.stride(0), d, n_items, ptr(base), ptr(delta), ld_delta, stream()),
+          "onehot_tables")
+    return base, delta
+
+
+def encode_onehot_gather(rowptr, col, users, n_rows: int, base, delta, d: int, out: torch.Tensor) -> None:
+    require_cuda(rowptr, col, users, base, delta, out)
+    check(load().gdmcf_encode_onehot_gather(ptr(rowptr), ptr(col), ptr(users), n_rows, ptr(base), ptr(delta),
+                                            delta.stride(0), d, ptr(out), out.stride(0), stream()), "encode_onehot_gather")
+
+
+def mix_rownorm(hc, rows: int, cols: int, *, g=None, sumw=None, out_f32=None, out: Optional[Bf16Mat] = None,
+                inv_norm=None) -> None:
+    require_cuda(hc, g, sumw, out_f32, inv_norm)
+    check(load().gdmcf_mix_rownorm(ptr(hc), hc.stride(0), ptr(g), g.stride(0) if g is not None else 0, ptr(sumw),
+                                   ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+                                   ptr(out.hi) if out is not None else None, ptr(out.lo) if out is not None else None,
+                                   out.ld if out is not None else 0, ptr(inv_norm), rows, cols, stream()), "mix_rownorm")
+
+
+def row_inv_norm(x: torch.Tensor, out=None) -> torch.Tensor:
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    check(load().gdmcf_row_inv_norm(ptr(x), x.stride(0), ptr(out), x.shape[0], x.shape[1], stream()), "row_inv_norm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# ranking
+# ----------------------------------------------------------------------------------------------
+def mask_topk(scores, n_rows: int, n_items: int, k: int, *, users=None, hist=None, hist2=None, with_values=False):
+    """hist / hist2: (rowptr, col) int32 device CSR pairs. Returns idx int32 [n_rows, k] (and values)."""
+    require_cuda(scores, users)
+    assert scores.dtype == torch.float32 and scores.stride(1) == 1
+    idx = torch.empty(n_rows, k, dtype=torch.int32, device=scores.device)
+    val = torch.empty(n_rows, k, dtype=torch.float32, device=scores.device) if with_values else None
+    h1 = hist if hist is not None else (None, None)
+    h2 = hist2 if hist2 is not None else (None, None)
+    check(load().gdmcf_mask_topk(ptr(scores), scores.stride(0), n_rows, n_items, ptr(users), ptr(h1[0]), ptr(h1[1]),
+                                 ptr(h2[0]), ptr(h2[1]), k, ptr(idx), ptr(val), stream()), "mask_topk")
+    return (idx, val) if with_values else idx
+
+
+def topn_metrics(topk_idx, users, gt_rowptr, gt_col, topn_dev, n_topn: int) -> torch.Tensor:
+    require_cuda(topk_idx, users, gt_rowptr, gt_col, topn_dev)
+    n_rows = topk_idx.shape[0]
+    stats = torch.empty(n_rows, n_topn, 4, dtype=torch.float64, device=topk_idx.device)
+    check(load().gdmcf_topn_metrics(ptr(topk_idx), topk_idx.stride(0), n_rows, ptr(users), ptr(gt_rowptr), ptr(gt_col),
+                                    ptr(topn_dev), n_topn, ptr(stats), stream()), "topn_metrics")
+    return stats
+
+
+def colsum_f64(x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x)
+    x2 = x.reshape(x.shape[0], -1)
+    assert x2.dtype == torch.float64 and x2.is_contiguous()
+    out = torch.empty(x2.shape[1], dtype=torch.float64, device=x.device)
+    check(load().gdmcf_colsum_f64(ptr(x2), x2.shape[0], x2.shape[1], ptr(out), stream()), "colsum_f64")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# training
+# ----------------------------------------------------------------------------------------------
+def mse_rows(out, x0, rows: int, cols: int) -> torch.Tensor:
+    require_cuda(out, x0)
+    mse = torch.empty(rows, dtype=torch.float32, device=out.device)
+    check(load().gdmcf_mse_rows(ptr(out), out.stride(0), ptr(x0), x0.stride(0), rows, cols, ptr(mse), stream()), "mse_rows")
+    return mse
+
+
+def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                weight_decay: float = 0.0, step: int = 1, grad_scale: float = 1.0) -> None:
+    require_cuda(p, g, m, v)
+    assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    check(load().gdmcf_adamw_fused(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                   grad_scale, stream()), "adamw_fused")

@@ -1,0 +1,368 @@
+"""Kernel-level parity tests (GPU, through the C ABI). Floating-point kernels are compared against a plain
+PyTorch fp32 evaluation of the same op on the same device inputs; integer/index kernels bit-exactly."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K(lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gdmcf_b200 import kernels
+    assert lib.gdmcf_device_check() == 0, "not an sm_100 device"
+    return kernels
+
+
+def _bf16_operand(rows, cols, seed, scale=1.0):
+    from gdmcf_b200.kernels import round_up
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ld = round_up(cols, 64)
+    t = torch.zeros(rows, ld, dtype=torch.bfloat16, device="cuda")
+    t[:, :cols] = (torch.randn(rows, cols, generator=g, device="cuda") * scale).to(torch.bfloat16)
+    return t
+
+
+def _ref_mm(a, b, k):
+    return a[:, :k].float() @ b[:, :k].float().t()
+
+
+@pytest.mark.parametrize("m,n,k,splits", [
+    (128, 256, 64, 1),      # one tile, one k-block
+    (128, 128, 256, 1),     # BN=128 variant
+    (400, 1000, 3000, 1),   # ragged M/N/K tails
+    (400, 1000, 34395, None),  # encoder shape (Yelp), auto split-K
+    (512, 34395, 3000, 1),  # scorer shape (Yelp)
+    (37, 50, 100, 3),       # tiny with explicit split-K
+])
+def test_gemm_store(K, m, n, k, splits):
+    a = _bf16_operand(m, k, 1)
+    b = _bf16_operand(n, k, 2)
+    out = torch.full((m, K.round_up(n, 4)), float("nan"), device="cuda")
+    K.gemm([a], [b], m, n, [k], out_f32=out, splits=splits)
+    torch.cuda.synchronize()
+    ref = _ref_mm(a, b, k)
+    got = out[:, :n]
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-5 * scale * math.sqrt(k / 64 + 1), f"max err {err} vs scale {scale}"
+
+
+def test_gemm_multi_segment_bias_tanh(K):
+    m, n = 400, 512
+    ks = [1000, 1000, 1000]
+    a = [_bf16_operand(m, k, 10 + i, 0.05) for i, k in enumerate(ks)]
+    b = [_bf16_operand(n, k, 20 + i, 0.05) for i, k in enumerate(ks)]
+    bias = torch.randn(5, n, device="cuda") * 0.1
+    row_t = torch.randint(0, 5, (m,), device="cuda", dtype=torch.int32)
+    out = torch.empty(m, n, device="cuda")
+    ob = K.Bf16Mat.empty(m, n, "cuda", with_lo=True)
+    K.gemm(a, b, m, n, ks, mode=K.EPI_BIAS_ACT, act=K.ACT_TANH, out_f32=out, out_bf16=ob.hi, out_bf16_lo=ob.lo,
+           bias=bias, ld_bias=n, row_t=row_t, splits=1)
+    ref = sum(_ref_mm(x, y, k) for x, y, k in zip(a, b, ks))
+    ref = torch.tanh(ref + bias[row_t.long()])
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 2e-5
+    assert (ob.float() - out).abs().max().item() < 1e-5  # hi + lo carries ~16 mantissa bits
+    assert (ob.hi[:, :n].float() - out).abs().max().item() < 4e-3
+
+
+def test_gemm_relu_splitk(K):
+    m, n, k = 256, 512, 3000
+    a, b = _bf16_operand(m, k, 3, 0.05), _bf16_operand(n, k, 4, 0.05)
+    bias = torch.randn(n, device="cuda") * 0.1
+    out = torch.empty(m, n, device="cuda")
+    K.gemm([a], [b], m, n, [k], mode=K.EPI_BIAS_ACT, act=K.ACT_RELU, out_f32=out, bias=bias, splits=None)
+    ref = torch.relu(_ref_mm(a, b, k) + bias)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+def test_gemm_cosine_posterior(K):
+    m, n, k = 300, 1000, 3000
+    a, b = _bf16_operand(m, k, 5), _bf16_operand(n, k, 6)
+    rs = torch.rand(m, device="cuda") + 0.5
+    cs = torch.rand(n, device="cuda") + 0.5
+    c1 = torch.tensor([1.0, 0.69, 0.41], device="cuda")
+    c2 = torch.tensor([0.0, 0.31, 0.59], device="cuda")
+    xt = torch.randn(m, n, device="cuda")
+    out = torch.empty(m, n, device="cuda")
+    ob = K.Bf16Mat.empty(m, n, "cuda")
+    K.gemm([a], [b], m, n, [k], mode=K.EPI_COSINE, out_f32=out, out_bf16=ob.hi, row_scale=rs, col_scale=cs, c1=c1,
+           c2=c2, xt=xt, t_const=2, splits=1)
+    s = _ref_mm(a, b, k) * rs[:, None] * cs[None, :]
+    ref = c1[2] * s + c2[2] * xt
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 3e-5 * ref.abs().max().item()
+    assert torch.equal(ob.hi[:, :n], out.to(torch.bfloat16))
+    assert ob.hi[:, n:].abs().max().item() == 0  # padding untouched
+
+
+def test_gemm_fp32_mode_split_precision(K):
+    """hi/lo bf16 split of both operands, three segments: a_hi*b_hi + a_hi*b_lo + a_lo*b_hi ~ fp32 product."""
+    m, n, k = 200, 300, 2000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.randn(m, k, generator=g, device="cuda")
+    B = torch.randn(n, k, generator=g, device="cuda")
+    a, b = K.cast_bf16(A, with_lo=True), K.cast_bf16(B, with_lo=True)
+    out = torch.empty(m, n, device="cuda")
+    K.gemm([a.hi, a.hi, a.lo], [b.hi, b.lo, b.hi], m, n, [k, k, k], out_f32=out, splits=1)
+    ref = (A.double() @ B.double().t()).float()
+    torch.cuda.synchronize()
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert rel < 1e-5, rel
+
+
+def test_gemm_bad_args(K):
+    a = _bf16_operand(8, 64, 1)
+    with pytest.raises(AssertionError):
+        K.gemm([a[:, 1:]], [a], 8, 8, [63], out_f32=torch.empty(8, 8, device="cuda"))  # misaligned pointer
+
+
+# ---------------------------------------------------------------------------------------------
+def _random_bipartite(n_users, n_items, avg_deg, seed, zipf=True):
+    rng = np.random.default_rng(seed)
+    deg = np.clip(rng.lognormal(np.log(avg_deg) - 0.5, 1.0, n_users).astype(np.int64), 1, n_items // 2)
+    if zipf:
+        p = 1.0 / np.arange(1, n_items + 1)
+        p /= p.sum()
+    rows, cols = [], []
+    for u in range(n_users):
+        c = rng.choice(n_items, size=deg[u], replace=False, p=p if zipf else None)
+        rows.append(np.full(deg[u], u)); cols.append(np.sort(c))
+    return np.concatenate(rows), np.concatenate(cols)
+
+
+def _csr(rows, cols, n_rows):
+    order = np.lexsort((cols, rows))
+    rows, cols = rows[order], cols[order]
+    rowptr = np.zeros(n_rows + 1, dtype=np.int32)
+    np.add.at(rowptr, rows + 1, 1)
+    return np.cumsum(rowptr).astype(np.int32), cols.astype(np.int32)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_and_lightgcn(K, d):
+    U, I = 700, 500
+    r, c = _random_bipartite(U, I, 12, 0)
+    r_rowptr, r_col = _csr(r, c, U)
+    rt_rowptr, rt_col = _csr(c, r, I)
+    dev = "cuda"
+    rowptr, col, val = K.build_norm_adj(*(torch.from_numpy(x).to(dev) for x in (r_rowptr, r_col, rt_rowptr, rt_col)), U, I)
+    # dense reference of A~ (lightGCN.py:145-178)
+    N = U + I
+    A = torch.zeros(N, N, dtype=torch.float64)
+    A[r, U + c] = 1.0
+    A[U + c, r] = 1.0
+    dinv = (A.sum(1) + 1e-9).pow(-0.5)
+    An = (dinv[:, None] * A * dinv[None, :]).float().to(dev)
+    rp = rowptr.cpu().numpy()
+    assert rp[-1] == 2 * len(r)
+    dense_from_csr = torch.zeros(N, N, device=dev)
+    rows_idx = torch.repeat_interleave(torch.arange(N, device=dev), torch.from_numpy(np.diff(rp)).to(dev))
+    dense_from_csr[rows_idx, col.long()] = val
+    assert (dense_from_csr - An).abs().max().item() < 1e-6
+    plan = K.spmm_plan(rp, chunk=32)  # small chunk -> exercises the long-row path
+    assert plan.n_long > 0
+    E0 = torch.randn(N, d, device=dev)
+    Y = K.spmm_csr(plan, col, val, E0)
+    ref = An @ E0
+    assert (Y - ref).abs().max().item() < 2e-5
+    out = K.lightgcn_propagate(plan, col, val, E0, 3)
+    layers = [E0]
+    for _ in range(3):
+        layers.append(An @ layers[-1])
+    ref = torch.stack(layers).mean(0)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+def test_spmm_empty_rows_and_beta(K):
+    rowptr = np.array([0, 0, 3, 3, 4], dtype=np.int32)
+    col = torch.tensor([0, 2, 3, 1], dtype=torch.int32, device="cuda")
+    val = torch.tensor([0.5, -1.0, 2.0, 3.0], device="cuda")
+    plan = K.spmm_plan(rowptr, chunk=32)
+    X = torch.randn(4, 64, device="cuda")
+    Z = torch.randn(4, 64, device="cuda")
+    Y = K.spmm_csr(plan, col, val, X, Z=Z, alpha=2.0, beta=-1.0)
+    A = torch.zeros(4, 4, device="cuda")
+    A[1, 0], A[1, 2], A[1, 3], A[3, 1] = 0.5, -1.0, 2.0, 3.0
+    assert torch.allclose(Y, 2.0 * (A @ X) - Z, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_items,k", [(34395, 100), (1000, 20), (94949, 100), (130, 128)])
+def test_mask_topk(K, n_items, k):
+    B = 64
+    g = torch.Generator(device="cuda").manual_seed(n_items)
+    ld = K.round_up(n_items, 4)
+    scores = torch.randn(B, ld, generator=g, device="cuda")
+    scores[3, :50] = 0.25  # ties: lowest ids must win
+    hist_rows = [np.sort(np.random.default_rng(b).choice(n_items, size=min(n_items // 2, 5 + 7 * b), replace=False))
+                 for b in range(B)]
+    rowptr = np.zeros(B + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum([len(x) for x in hist_rows])
+    hcol = np.concatenate(hist_rows).astype(np.int32)
+    hist = (torch.from_numpy(rowptr).cuda(), torch.from_numpy(hcol).cuda())
+    idx, val = K.mask_topk(scores, B, n_items, k, hist=hist, with_values=True)
+    ref = scores[:, :n_items].clone()
+    for b in range(B):
+        ref[b, torch.from_numpy(hist_rows[b]).cuda()] = float("-inf")
+    rv, ri = torch.topk(ref, k, dim=1)
+    torch.cuda.synchronize()
+    assert torch.equal(val, rv)
+    # indices: equal wherever values are distinct; tie groups resolved by ascending id
+    got_vals = torch.gather(ref, 1, idx.long())
+    assert torch.equal(got_vals, rv)
+    for b in range(B):
+        assert len(set(idx[b].tolist())) == k
+    assert idx[3].tolist() == sorted(idx[3].tolist(), key=lambda i: (-ref[3, i].item(), i))
+
+
+def test_topn_metrics_kat(K):
+    """computeTopNAccuracy known-answer vector from SURVEY.md §8c (reference evaluate_utils.py:6-52)."""
+    GT = [[1, 5, 7], [], [2], [9, 3]]
+    pred = [[5, 0, 7, 2, 4], [1, 2, 3, 4, 5], [0, 1, 3, 4, 5], [3, 9, 1, 2, 0]]
+    topN = [1, 3, 5]
+    rowptr = np.zeros(5, dtype=np.int32)
+    rowptr[1:] = np.cumsum([len(g) for g in GT])
+    col = np.concatenate([np.sort(g) for g in GT if g]).astype(np.int32)
+    stats = K.topn_metrics(torch.tensor(pred, dtype=torch.int32, device="cuda"), None, torch.from_numpy(rowptr).cuda(),
+                           torch.from_numpy(col).cuda(), torch.tensor(topN, dtype=torch.int32, device="cuda"), 3)
+    sums = K.colsum_f64(stats).reshape(3, 4).cpu().numpy() / 4
+    got = [[round(float(sums[j, q]), 4) for j in range(3)] for q in range(4)]
+    assert got == [[0.5, 0.3333, 0.2], [0.2083, 0.4167, 0.4167], [0.5, 0.426, 0.426], [0.5, 0.5, 0.5]]
+
+
+# ---------------------------------------------------------------------------------------------
+def test_cast_and_transpose(K):
+    x = torch.randn(37, 131, device="cuda")
+    m = K.cast_bf16(x, with_lo=True)
+    assert torch.equal(m.hi[:, :131], x.to(torch.bfloat16)) and m.hi[:, 131:].abs().max().item() == 0
+    assert (m.float() - x).abs().max().item() < 2e-5
+    t = K.cast_bf16_transpose(x, with_lo=True)
+    assert t.rows == 131 and torch.equal(t.hi[:, :37], x.t().contiguous().to(torch.bfloat16))
+    assert t.hi[:, 37:].abs().max().item() == 0
+
+
+def test_densify_and_encoder(K):
+    n_users, n_items, d = 50, 333, 96
+    r, c = _random_bipartite(n_users, n_items, 9, 3, zipf=False)
+    rowptr, col = _csr(r, c, n_users)
+    rp, cl = torch.from_numpy(rowptr).cuda(), torch.from_numpy(col).cuda()
+    users = torch.tensor([5, 0, 49, 7], dtype=torch.int32, device="cuda")
+    xf = torch.full((4, K.round_up(n_items, 4)), 7.0, device="cuda")
+    xb = K.Bf16Mat.empty(4, n_items, "cuda")
+    K.densify_rows(rp, cl, users, 4, n_items, out_f32=xf, out_bf16=xb.hi)
+    dense = torch.zeros(n_users, n_items)
+    dense[r, c] = 1.0
+    assert torch.equal(xf[:, :n_items].cpu(), dense[users.cpu().long()])
+    assert torch.equal(xb.hi[:, :n_items].float().cpu(), dense[users.cpu().long()])
+    # one-hot encoder: W2 [d, 2I + e]; x_U interleaved one-hot of x0 (models/DNN.py:1224)
+    e = 10
+    W2 = torch.randn(d, 2 * n_items + e, device="cuda") * 0.05
+    base, delta = K.onehot_tables(W2, d, n_items)
+    S = torch.empty(4, d, device="cuda")
+    K.encode_onehot_gather(rp, cl, users, 4, base, delta, d, S)
+    x0 = dense[users.cpu().long()].cuda()
+    x_U = torch.nn.functional.one_hot(x0.long(), 2).float().reshape(4, -1)
+    ref = x_U @ W2[:, : 2 * n_items].t()
+    assert (S - ref).abs().max().item() < 5e-5
+
+
+def test_qsample_dropout_injected(K):
+    rows, cols, T = 16, 203, 5
+    x0 = (torch.rand(rows, cols, device="cuda") < 0.1).float()
+    ts = torch.randint(0, T, (rows,), device="cuda", dtype=torch.int32)
+    sa = torch.rand(T, device="cuda")
+    sb = torch.rand(T, device="cuda")
+    noise = torch.randn(rows, cols, device="cuda")
+    keep = (torch.rand(rows, cols, device="cuda") < 0.5).to(torch.uint8)
+    a = K.Bf16Mat.empty(rows, cols, "cuda", with_lo=True)
+    xt = torch.empty(rows, cols, device="cuda")
+    K.qsample_dropout(x0, rows, cols, a, row_t=ts, sqrt_ab=sa, sqrt_1mab=sb, noise=noise, keep=keep, dropout_p=0.5, xt_out=xt)
+    ref = sa[ts.long()][:, None] * x0 + sb[ts.long()][:, None] * noise
+    assert torch.equal(xt, ref)
+    assert (a.float() - ref * keep * 2.0).abs().max().item() < 1e-5
+
+
+def test_qsample_philox_distribution(K):
+    rows, cols = 64, 4096
+    x0 = torch.zeros(rows, cols, device="cuda")
+    sa = torch.ones(1, device="cuda")
+    sb = torch.ones(1, device="cuda")
+    a = K.Bf16Mat.empty(rows, cols, "cuda")
+    xt = torch.empty(rows, cols, device="cuda")
+    K.qsample_dropout(x0, rows, cols, a, sqrt_ab=sa, sqrt_1mab=sb, dropout_p=0.5, seed=123, offset=0, xt_out=xt)
+    n = rows * cols
+    assert abs(xt.mean().item()) < 5 / math.sqrt(n)
+    assert abs(xt.var().item() - 1.0) < 0.02
+    assert abs((xt ** 4).mean().item() - 3.0) < 0.15
+    kept = (a.hi[:, :cols].float() != 0).float().mean().item()
+    assert abs(kept - 0.5) < 0.01
+    xt2 = torch.empty_like(xt)
+    K.qsample_dropout(x0, rows, cols, a, sqrt_ab=sa, sqrt_1mab=sb, dropout_p=0.5, seed=123, offset=0, xt_out=xt2)
+    assert torch.equal(xt, xt2)  # counter-based: reproducible
+    K.qsample_dropout(x0, rows, cols, a, sqrt_ab=sa, sqrt_1mab=sb, dropout_p=0.5, seed=124, offset=0, xt_out=xt2)
+    assert not torch.equal(xt, xt2)
+
+
+def test_onehot_noise(K):
+    rows, cols = 400, 1000
+    x0 = (torch.rand(rows, cols, device="cuda") < 0.05).float()
+    ts = torch.randint(0, 5, (rows,), device="cuda", dtype=torch.int32)
+    uk = torch.rand(rows, cols, device="cuda")
+    ud = torch.rand(rows, 2 * cols, device="cuda")
+    out = torch.zeros(rows, K.round_up(2 * cols, 64), dtype=torch.bfloat16, device="cuda")
+    K.onehot_noise(x0, rows, cols, out, ts=ts, discrete=0.9995, dropout_p=0.5, u_keep=uk, u_drop=ud)
+    a = ts.float() / rows
+    q1 = a + (1 - a) * (1 - 0.9995)
+    q0 = a + (1 - a) * 0.9995
+    c = x0.long()
+    q = torch.where(c == 1, q1[:, None], q0[:, None])
+    kept = uk < q
+    ref = torch.zeros(rows, cols, 2, device="cuda")
+    drop_u = torch.gather(ud.reshape(rows, cols, 2), 2, c[..., None]).squeeze(-1)
+    ref.scatter_(2, c[..., None], (kept & (drop_u >= 0.5)).float()[..., None] * 2.0)
+    assert torch.equal(out[:, : 2 * cols].float(), ref.reshape(rows, -1))
+    # no-noise mode (p_sample, sampling_steps == 0): plain interleaved one-hot
+    K.onehot_noise(x0, rows, cols, out)
+    assert torch.equal(out[:, : 2 * cols].float(), torch.nn.functional.one_hot(c, 2).float().reshape(rows, -1))
+    # in-kernel RNG: keep rate of true interactions ~ q1
+    K.onehot_noise(torch.ones(rows, cols, device="cuda"), rows, cols, out, ts=torch.full((rows,), 4, dtype=torch.int32, device="cuda"), seed=9)
+    rate = out[:, 1: 2 * cols: 2].float().mean().item()
+    assert abs(rate - (4 / 400 + (1 - 4 / 400) * 0.0005)) < 2e-3
+
+
+def test_mix_rownorm_mse_adamw(K):
+    rows, cols = 33, 3000
+    hc = torch.randn(rows, cols, device="cuda")
+    g = torch.randn(rows, cols, device="cuda")
+    w = torch.tensor(0.8, device="cuda")
+    of = torch.empty(rows, cols, device="cuda")
+    ob = K.Bf16Mat.empty(rows, cols, "cuda", with_lo=True)
+    inv = torch.empty(rows, device="cuda")
+    K.mix_rownorm(hc, rows, cols, g=g, sumw=w, out_f32=of, out=ob, inv_norm=inv)
+    ref = hc * w + g * (1 - w)
+    assert (of - ref).abs().max().item() < 1e-6
+    assert torch.allclose(inv, 1.0 / ref.norm(dim=1), rtol=1e-5)
+    assert (ob.float() - ref).abs().max().item() < 3e-5
+    assert torch.allclose(K.row_inv_norm(hc), 1.0 / hc.norm(dim=1), rtol=1e-5)
+    mse = K.mse_rows(of, hc, rows, cols)
+    assert torch.allclose(mse, ((hc - of) ** 2).mean(1), rtol=1e-5)
+    # AdamW vs torch.optim.AdamW over 3 steps
+    p = torch.randn(10007, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-2, weight_decay=0.01)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn_like(p)
+        pr.grad = grad.clone()
+        opt.step()
+        K.adamw_fused(p, grad, m, v, lr=1e-2, weight_decay=0.01, step=step)
+    assert (p - pr.detach()).abs().max().item() < 2e-6
