@@ -24,6 +24,7 @@ GD_DEV uint32_t f32_key(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 GD_DEV float key_f32(uint32_t k) {
+  if (k == 0u) return __uint_as_float(0xFF800000u);  // masked history item: reported as -inf like main.py:299
   const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
   return __uint_as_float(b);
 }
