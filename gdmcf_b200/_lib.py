@@ -80,6 +80,11 @@ SIGNATURES = {
     "gdmcf_onehot_noise": (_I, [_P, _L, _P, _F, _F, _P, _P, _U64, _U64, _P, _L, _I, _I, _P]),
     "gdmcf_encode_onehot_gather": (_I, [_P, _P, _P, _I, _P, _P, _L, _I, _P, _L, _P]),
     "gdmcf_onehot_tables": (_I, [_P, _L, _I, _I, _P, _P, _L, _P]),
+    "gdmcf_time_bias_table": (_I, [_P, _P, _P, _L, _P, _I, _I, _I, _P, _P, _L, _P]),
+    "gdmcf_bias_act_rows": (_I, [_P, _L, _P, _L, _P, _I, _I, _P, _L, _P, _P, _L, _I, _I, _P]),
+    "gdmcf_gather_rows": (_I, [_P, _L, _P, _P, _L, _P, _P, _L, _I, _I, _P]),
+    "gdmcf_sgemm_small": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _F, _F, _P]),
+    "gdmcf_colsum_f32": (_I, [_P, _L, _I, _I, _P, _P]),
     "gdmcf_mix_rownorm": (_I, [_P, _L, _P, _L, _P, _P, _L, _P, _P, _L, _P, _I, _I, _P]),
     "gdmcf_row_inv_norm": (_I, [_P, _L, _P, _I, _I, _P]),
     "gdmcf_mask_topk": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
@@ -87,6 +92,12 @@ SIGNATURES = {
     "gdmcf_colsum_f64": (_I, [_P, _I, _I, _P, _P]),
     "gdmcf_mse_rows": (_I, [_P, _L, _P, _L, _I, _I, _P, _P]),
     "gdmcf_adamw_fused": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "gdmcf_loss_grad": (_I, [_P, _L, _P, _L, _P, _P, _P, _I, _P, _L, _P, _L, _P, _P, _I, _I, _P]),
+    "gdmcf_transpose_bf16": (_I, [_P, _L, _P, _L, _I, _I, _P]),
+    "gdmcf_ew_binary": (_I, [_I, _P, _L, _P, _L, _F, _F, _P, _L, _P, _P, _L, _I, _I, _P]),
+    "gdmcf_mix_backward": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _I, _I, _P]),
+    "gdmcf_ntxent_rows": (_I, [_P, _L, _I, _F, _F, _P, _P, _P, _L, _P]),
+    "gdmcf_scatter_rows_add": (_I, [_P, _L, _P, _P, _L, _I, _I, _P]),
 }
 
 _lib = None

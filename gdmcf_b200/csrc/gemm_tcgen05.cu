@@ -90,33 +90,30 @@ GD_DEV void epilogue8(const gdmcf_epilogue& e, int m, int n0, int N, const float
   if (valid <= 0) return;
   float o[8];
   const int t = e.row_t ? e.row_t[m] : e.t_const;
-  if (e.mode == GDMCF_EPI_STORE) {
+  // One formula for every fused form:  s = act(alpha*acc*row_scale[m]*col_scale[n] + bias[t,n]);
+  //                                     out = c1 ? c1[t]*s + c2[t]*xt[m,n] : s
+  const float rs = e.alpha * (e.row_scale ? e.row_scale[m] : 1.0f);
+  const float* bias = e.bias ? e.bias + (long long)t * e.ld_bias + n0 : nullptr;
+  float c1 = 1.f, c2 = 0.f;
+  const float* xt = nullptr;
+  if (e.c1) {
+    c1 = e.c1[t];
+    c2 = e.c2[t];
+    xt = e.xt + (long long)m * e.ld_xt + n0;
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = e.alpha * acc[j];
-  } else if (e.mode == GDMCF_EPI_BIAS_ACT) {
-    const float* bias = e.bias ? e.bias + (long long)t * e.ld_bias + n0 : nullptr;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = e.alpha * acc[j] + ((bias && j < valid) ? bias[j] : 0.f);
+  for (int j = 0; j < 8; ++j) {
+    float v = 0.f;
+    if (j < valid) {
+      v = acc[j] * rs;
+      if (e.col_scale) v *= e.col_scale[n0 + j];
+      if (bias) v += bias[j];
       if (e.act == GDMCF_ACT_TANH) v = tanhf(v);
       else if (e.act == GDMCF_ACT_RELU) v = fmaxf(v, 0.f);
-      o[j] = v;
+      // same association as the reference: coef1 * pred_xstart + coef2 * x_t (gaussian_diffusion.py:1047-1050)
+      if (xt) v = c1 * v + c2 * xt[j];
     }
-  } else {  // GDMCF_EPI_COSINE
-    const float rs = e.alpha * e.row_scale[m];
-    float c1 = 1.f, c2 = 0.f;
-    const float* xt = nullptr;
-    if (e.c1) {
-      c1 = e.c1[t];
-      c2 = e.c2[t];
-      xt = e.xt + (long long)m * e.ld_xt + n0;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = (j < valid) ? acc[j] * rs * e.col_scale[n0 + j] : 0.f;
-      // same association as the reference: coef1 * pred_xstart + coef2 * x_t
-      o[j] = (xt && j < valid) ? c1 * s + c2 * xt[j] : s;
-    }
+    o[j] = v;
   }
   if (e.out_f32) {
     float* dst = e.out_f32 + (long long)m * e.ld_f32 + n0;
@@ -432,8 +429,8 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
     if ((rc = make_map(&maps.b[s], g->b[s], g->n, g->k[s], g->ldb[s], bn))) return rc;
   }
   if (e->mode < 0 || e->mode > GDMCF_EPI_COSINE) { set_error("gemm: bad epilogue mode %d", e->mode); return GDMCF_EBADARG; }
-  if (e->mode == GDMCF_EPI_COSINE && (!e->row_scale || !e->col_scale || (e->c1 && (!e->c2 || !e->xt)))) {
-    set_error("gemm: cosine epilogue needs row_scale, col_scale (and c2, xt with c1)");
+  if (e->c1 && (!e->c2 || !e->xt)) {
+    set_error("gemm: the posterior-mean epilogue needs c1, c2 and xt together");
     return GDMCF_EBADARG;
   }
   if ((e->out_bf16 && ((e->ld_bf16 & 7) || ((uintptr_t)e->out_bf16 & 15))) ||

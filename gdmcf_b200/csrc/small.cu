@@ -1,0 +1,212 @@
+// Small glue kernels of the denoiser (O(B*d) work, never on the roofline): per-timestep bias tables,
+// bias+activation rows, embedding row gathers, and a plain fp32 CUDA-core GEMM for the tiny contractions
+// (time-embedding columns, nt_xent logits) where a 128x256 tensor-core tile would be >90 % padding.
+#include "common.cuh"
+#include "api_internal.h"
+
+namespace gd {
+namespace small {
+
+constexpr int TPB = 256;
+
+static int grid_1d(long long work_items, int per_cta = TPB) {
+  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  const long long ctas = (work_items + per_cta - 1) / per_cta;
+  return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sms * 8));
+}
+
+// timestep_embedding (models/DNN.py:1806-1825) for integer t, dim e: [cos(t f_k) | sin(t f_k) | 0 if odd]
+GD_DEV float temb_at(int t, int j, int e) {
+  const int half = e / 2;
+  if (j >= 2 * half) return 0.f;
+  const int k = j < half ? j : j - half;
+  const float freq = expf(-logf(10000.0f) * (float)k / (float)half);
+  const float arg = (float)t * freq;
+  return j < half ? cosf(arg) : sinf(arg);
+}
+
+// emb_table[t, i] = b_emb[i] + sum_j w_emb[i, j] * temb(t)[j]        (emb_layer, models/DNN.py:24/1122)
+__global__ void time_emb_table_kernel(const float* __restrict__ w_emb, const float* __restrict__ b_emb, int T, int e,
+                                      float* __restrict__ emb_table) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T * e; i += gridDim.x * blockDim.x) {
+    const int t = i / e, r = i % e;
+    float s = b_emb[r];
+    for (int j = 0; j < e; ++j) s += w_emb[r * e + j] * temb_at(t, j, e);
+    emb_table[i] = s;
+  }
+}
+// bias_table[t, k] = b[k] + sum_j w_time[k, j] * emb_table[t, j]   (the `cat([x, emb])` columns of the first layer)
+__global__ void time_bias_table_kernel(const float* __restrict__ emb_table, const float* __restrict__ w_time, long long ld_w,
+                                       const float* __restrict__ b, int T, int e, int d, float* __restrict__ out, long long ld_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)T * d; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / d), k = (int)(i % d);
+    float s = b ? b[k] : 0.f;
+    for (int j = 0; j < e; ++j) s += w_time[(long long)k * ld_w + j] * emb_table[t * e + j];
+    out[(long long)t * ld_out + k] = s;
+  }
+}
+
+GD_DEV void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// out[r, c] = act(in[r, c] + bias[t(r), c])
+__global__ void bias_act_rows_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ bias,
+                                     long long ld_bias, const int* __restrict__ row_t, int t_const, int act,
+                                     float* __restrict__ out_f32, long long ld_of, __nv_bfloat16* __restrict__ out_hi,
+                                     __nv_bfloat16* __restrict__ out_lo, long long ld_ob, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const int t = row_t ? row_t[r] : t_const;
+    float v = in[(long long)r * ld_in + c] + (bias ? bias[(long long)t * ld_bias + c] : 0.f);
+    if (act == GDMCF_ACT_TANH) v = tanhf(v);
+    else if (act == GDMCF_ACT_RELU) v = fmaxf(v, 0.f);
+    if (out_f32) out_f32[(long long)r * ld_of + c] = v;
+    if (out_hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      out_hi[(long long)r * ld_ob + c] = h;
+      if (out_lo) out_lo[(long long)r * ld_ob + c] = l;
+    }
+  }
+}
+
+// out[r, :] = table[idx[r], :]    (nn.Embedding lookup, models/DNN.py:1265)
+__global__ void gather_rows_kernel(const float* __restrict__ table, long long ld_t, const int* __restrict__ idx,
+                                   float* __restrict__ out_f32, long long ld_of, __nv_bfloat16* __restrict__ out_hi,
+                                   __nv_bfloat16* __restrict__ out_lo, long long ld_ob, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = table[(long long)idx[r] * ld_t + c];
+    if (out_f32) out_f32[(long long)r * ld_of + c] = v;
+    if (out_hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      out_hi[(long long)r * ld_ob + c] = h;
+      if (out_lo) out_lo[(long long)r * ld_ob + c] = l;
+    }
+  }
+}
+
+// C[m, n] = alpha * sum_k opA(A)[m, k] * opB(B)[k, n] + beta * C[m, n]   (fp32, 32x32 tiles through smem)
+// ta == 0: A is [M, K] (lda); ta == 1: A is [K, M].  tb == 0: B is [K, N] (ldb); tb == 1: B is [N, K].
+__global__ void sgemm_small_kernel(const float* __restrict__ A, long long lda, int ta, const float* __restrict__ B,
+                                   long long ldb, int tb, float* __restrict__ C, long long ldc, int M, int N, int K,
+                                   float alpha, float beta) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int tiles_n = (N + 31) / 32;
+  const int ntiles = ((M + 31) / 32) * tiles_n;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m0 = (tile / tiles_n) * 32, n0 = (tile % tiles_n) * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      for (int j = ty; j < 32; j += 8) {
+        // sa[m][k], sb[k][n]
+        float va = 0.f, vb = 0.f;
+        if (!ta) { const int m = m0 + j, k = k0 + tx; if (m < M && k < K) va = A[(long long)m * lda + k]; sa[j][tx] = va; }
+        else     { const int k = k0 + j, m = m0 + tx; if (m < M && k < K) va = A[(long long)k * lda + m]; sa[tx][j] = va; }
+        if (!tb) { const int k = k0 + j, n = n0 + tx; if (k < K && n < N) vb = B[(long long)k * ldb + n]; sb[j][tx] = vb; }
+        else     { const int n = n0 + j, k = k0 + tx; if (k < K && n < N) vb = B[(long long)n * ldb + k]; sb[tx][j] = vb; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int mi = ty + 8 * q;
+        float s = acc[q];
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) s = fmaf(sa[mi][k], sb[k][tx], s);
+        acc[q] = s;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int m = m0 + ty + 8 * q, n = n0 + tx;
+      if (m < M && n < N) {
+        float* c = C + (long long)m * ldc + n;
+        *c = alpha * acc[q] + (beta != 0.f ? beta * (*c) : 0.f);
+      }
+    }
+  }
+}
+
+// out[c] = sum_r x[r, c] (fp32 in, fp32 accumulate in fixed order per column; deterministic)
+__global__ void colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += x[(long long)r * ld + c];
+    out[c] = s;
+  }
+}
+
+}  // namespace small
+}  // namespace gd
+
+using namespace gd;
+using namespace gd::small;
+
+#define GD_PRE()                 \
+  int rc = gdmcf_device_check(); \
+  if (rc) return rc;             \
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int gdmcf_time_bias_table(const float* w_emb, const float* b_emb, const float* w_time, int64_t ld_w,
+                                     const float* b, int T, int e, int d, float* emb_table, float* out, int64_t ld_out,
+                                     gdmcf_stream_t stream) {
+  if (!w_emb || !b_emb || !w_time || !emb_table || !out || T <= 0 || e <= 0 || d <= 0 || ld_w < e || ld_out < d) {
+    set_error("time_bias_table: bad arguments");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  time_emb_table_kernel<<<grid_1d(T * e), TPB, 0, st>>>(w_emb, b_emb, T, e, emb_table);
+  if ((rc = cuda_check_launch("time_emb_table_kernel"))) return rc;
+  time_bias_table_kernel<<<grid_1d((long long)T * d), TPB, 0, st>>>(emb_table, w_time, ld_w, b, T, e, d, out, ld_out);
+  return cuda_check_launch("time_bias_table_kernel");
+}
+
+extern "C" int gdmcf_bias_act_rows(const float* in, int64_t ld_in, const float* bias, int64_t ld_bias, const int32_t* row_t,
+                                   int t_const, int act, float* out_f32, int64_t ld_of, void* out_bf16, void* out_lo,
+                                   int64_t ld_ob, int rows, int cols, gdmcf_stream_t stream) {
+  if (!in || rows <= 0 || cols <= 0 || ld_in < cols || (!out_f32 && !out_bf16) || (out_f32 && ld_of < cols) ||
+      (out_bf16 && ld_ob < cols) || (out_lo && !out_bf16)) {
+    set_error("bias_act_rows: bad arguments");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  bias_act_rows_kernel<<<grid_1d((long long)rows * cols), TPB, 0, st>>>(in, ld_in, bias, ld_bias, row_t, t_const, act, out_f32, ld_of,
+                                                                        (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_lo, ld_ob, rows, cols);
+  return cuda_check_launch("bias_act_rows_kernel");
+}
+
+extern "C" int gdmcf_gather_rows(const float* table, int64_t ld_t, const int32_t* idx, float* out_f32, int64_t ld_of,
+                                 void* out_bf16, void* out_lo, int64_t ld_ob, int rows, int cols, gdmcf_stream_t stream) {
+  if (!table || !idx || rows <= 0 || cols <= 0 || ld_t < cols || (!out_f32 && !out_bf16) || (out_f32 && ld_of < cols) ||
+      (out_bf16 && ld_ob < cols) || (out_lo && !out_bf16)) {
+    set_error("gather_rows: bad arguments");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  gather_rows_kernel<<<grid_1d((long long)rows * cols), TPB, 0, st>>>(table, ld_t, idx, out_f32, ld_of, (__nv_bfloat16*)out_bf16,
+                                                                      (__nv_bfloat16*)out_lo, ld_ob, rows, cols);
+  return cuda_check_launch("gather_rows_kernel");
+}
+
+extern "C" int gdmcf_sgemm_small(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
+                                 int64_t ldc, int m, int n, int k, float alpha, float beta, gdmcf_stream_t stream) {
+  if (!A || !B || !C || m <= 0 || n <= 0 || k <= 0 || ldc < n) { set_error("sgemm_small: bad arguments"); return GDMCF_EBADARG; }
+  GD_PRE();
+  const int ntiles = ((m + 31) / 32) * ((n + 31) / 32);
+  sgemm_small_kernel<<<grid_1d(ntiles, 1), TPB, 0, st>>>(A, lda, trans_a, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
+  return cuda_check_launch("sgemm_small_kernel");
+}
+
+extern "C" int gdmcf_colsum_f32(const float* x, int64_t ld, int rows, int cols, float* out, gdmcf_stream_t stream) {
+  if (!x || !out || rows <= 0 || cols <= 0 || ld < cols) { set_error("colsum_f32: bad arguments"); return GDMCF_EBADARG; }
+  GD_PRE();
+  colsum_f32_kernel<<<grid_1d(cols), TPB, 0, st>>>(x, ld, rows, cols, out);
+  return cuda_check_launch("colsum_f32_kernel");
+}

@@ -21,7 +21,7 @@ __all__ = [
     "ACT_NONE", "ACT_RELU", "ACT_TANH", "EPI_BIAS_ACT", "EPI_COSINE", "EPI_STORE", "round_up", "Bf16Mat",
     "SpmmPlan", "spmm_plan", "spmm_csr", "lightgcn_propagate", "build_norm_adj", "gemm", "cast_bf16",
     "cast_bf16_transpose", "densify_rows", "qsample_dropout", "onehot_noise", "onehot_tables",
-    "encode_onehot_gather", "mix_rownorm", "row_inv_norm", "mask_topk", "topn_metrics", "colsum_f64",
+    "encode_onehot_gather", "time_bias_table", "bias_act_rows", "gather_rows", "sgemm_small", "colsum_f32", "mix_rownorm", "row_inv_norm", "mask_topk", "topn_metrics", "colsum_f64",
     "mse_rows", "adamw_fused",
 ]
 
@@ -260,6 +260,50 @@ def encode_onehot_gather(rowptr, col, users, n_rows: int, base, delta, d: int, o
                                             delta.stride(0), d, ptr(out), out.stride(0), stream()), "encode_onehot_gather")
 
 
+def time_bias_table(w_emb, b_emb, w_layer: torch.Tensor, n_in: int, bias, T: int):
+    """[T, d] table of first-layer biases; w_layer is the layer's full fp32 weight [d, n_in + e]."""
+    require_cuda(w_emb, b_emb, w_layer, bias)
+    d, e = w_layer.shape[0], w_layer.shape[1] - n_in
+    assert w_emb.shape == (e, e) and w_emb.is_contiguous() and w_layer.stride(1) == 1
+    emb_table = torch.empty(T, e, dtype=torch.float32, device=w_layer.device)
+    out = torch.empty(T, d, dtype=torch.float32, device=w_layer.device)
+    w_time = w_layer[:, n_in:]
+    check(load().gdmcf_time_bias_table(ptr(w_emb), ptr(b_emb), w_time.data_ptr(), w_layer.stride(0), ptr(bias), T, e, d,
+                                       ptr(emb_table), ptr(out), d, stream()), "time_bias_table")
+    return out, emb_table
+
+
+def bias_act_rows(x, rows: int, cols: int, *, bias=None, ld_bias: int = 0, row_t=None, t_const: int = 0,
+                  act: int = ACT_NONE, out_f32=None, out_bf16=None, out_bf16_lo=None) -> None:
+    require_cuda(x, bias, row_t, out_f32, out_bf16, out_bf16_lo)
+    check(load().gdmcf_bias_act_rows(ptr(x), x.stride(0), ptr(bias), ld_bias, ptr(row_t), t_const, act, ptr(out_f32),
+                                     out_f32.stride(0) if out_f32 is not None else 0, ptr(out_bf16), ptr(out_bf16_lo),
+                                     out_bf16.stride(0) if out_bf16 is not None else 0, rows, cols, stream()), "bias_act_rows")
+
+
+def gather_rows(table, idx, rows: int, cols: int, *, out_f32=None, out_bf16=None, out_bf16_lo=None) -> None:
+    require_cuda(table, idx, out_f32, out_bf16, out_bf16_lo)
+    assert idx.dtype == torch.int32
+    check(load().gdmcf_gather_rows(ptr(table), table.stride(0), ptr(idx), ptr(out_f32),
+                                   out_f32.stride(0) if out_f32 is not None else 0, ptr(out_bf16), ptr(out_bf16_lo),
+                                   out_bf16.stride(0) if out_bf16 is not None else 0, rows, cols, stream()), "gather_rows")
+
+
+def sgemm_small(A, B, C, m: int, n: int, k: int, *, trans_a=False, trans_b=False, alpha=1.0, beta=0.0) -> None:
+    require_cuda(A, B, C)
+    assert A.dtype == B.dtype == C.dtype == torch.float32 and A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
+    check(load().gdmcf_sgemm_small(ptr(A), A.stride(0), int(trans_a), ptr(B), B.stride(0), int(trans_b), ptr(C), C.stride(0),
+                                   m, n, k, alpha, beta, stream()), "sgemm_small")
+
+
+def colsum_f32(x, rows: int, cols: int, out=None) -> torch.Tensor:
+    require_cuda(x)
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    check(load().gdmcf_colsum_f32(ptr(x), x.stride(0), rows, cols, ptr(out), stream()), "colsum_f32")
+    return out
+
+
 def mix_rownorm(hc, rows: int, cols: int, *, g=None, sumw=None, out_f32=None, out: Optional[Bf16Mat] = None,
                 inv_norm=None) -> None:
     require_cuda(hc, g, sumw, out_f32, inv_norm)
@@ -328,3 +372,47 @@ def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.9
     assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
     check(load().gdmcf_adamw_fused(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
                                    grad_scale, stream()), "adamw_fused")
+
+
+def loss_grad(out, x0, gs, rows: int, cols: int, G: torch.Tensor, *, GT=None, row_scale=None, col_scale=None,
+              with_out: bool = False, colsum=None, rowpart=None) -> None:
+    require_cuda(out, x0, gs, G, GT, row_scale, col_scale, colsum, rowpart)
+    check(load().gdmcf_loss_grad(ptr(out), out.stride(0), ptr(x0), x0.stride(0), ptr(gs), ptr(row_scale), ptr(col_scale),
+                                 int(with_out), ptr(G), G.stride(0), ptr(GT), GT.stride(0) if GT is not None else 0,
+                                 ptr(colsum), ptr(rowpart), rows, cols, stream()), "loss_grad")
+
+
+def transpose_bf16(x: torch.Tensor, rows: int, cols: int, out: torch.Tensor) -> None:
+    require_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+    check(load().gdmcf_transpose_bf16(ptr(x), x.stride(0), ptr(out), out.stride(0), rows, cols, stream()), "transpose_bf16")
+
+
+EW_RELU_BWD, EW_TANH_BWD, EW_AXPBY = 0, 1, 2
+
+
+def ew_binary(op: int, a, b, rows: int, cols: int, *, alpha=1.0, beta=1.0, out_f32=None, out_bf16=None, out_bf16_lo=None) -> None:
+    require_cuda(a, b, out_f32, out_bf16, out_bf16_lo)
+    check(load().gdmcf_ew_binary(op, ptr(a), a.stride(0), ptr(b), b.stride(0), alpha, beta, ptr(out_f32),
+                                 out_f32.stride(0) if out_f32 is not None else 0, ptr(out_bf16), ptr(out_bf16_lo),
+                                 out_bf16.stride(0) if out_bf16 is not None else 0, rows, cols, stream()), "ew_binary")
+
+
+def mix_backward(d_hcp, hc, g2, sumw, d_hc, d_g2, dw_rows, rows: int, cols: int) -> None:
+    require_cuda(d_hcp, hc, g2, sumw, d_hc, d_g2, dw_rows)
+    check(load().gdmcf_mix_backward(ptr(d_hcp), d_hcp.stride(0), ptr(hc), hc.stride(0), ptr(g2), g2.stride(0), ptr(sumw),
+                                    ptr(d_hc), d_hc.stride(0), ptr(d_g2), d_g2.stride(0), ptr(dw_rows), rows, cols, stream()),
+          "mix_backward")
+
+
+def ntxent_rows(S, n: int, *, tau=0.1, eps=1e-5, dscale=None, loss_rows=None, dS=None) -> None:
+    require_cuda(S, dscale, loss_rows, dS)
+    check(load().gdmcf_ntxent_rows(ptr(S), S.stride(0), n, tau, eps, ptr(dscale), ptr(loss_rows), ptr(dS),
+                                   dS.stride(0) if dS is not None else 0, stream()), "ntxent_rows")
+
+
+def scatter_rows_add(v, idx, grad, rows: int, cols: int) -> None:
+    require_cuda(v, idx, grad)
+    assert idx.dtype == torch.int32
+    check(load().gdmcf_scatter_rows_add(ptr(v), v.stride(0), ptr(idx), ptr(grad), grad.stride(0), rows, cols, stream()),
+          "scatter_rows_add")

@@ -1,0 +1,187 @@
+"""Train a diffusion model for recommendation — mirror of the reference's main.py:108-384 (same flow, prints and
+model-selection rule), rebuilt CSR-native on the B200 engine:
+
+  * no dense n_user x n_item host tensors (main.py:143-156, D8): interactions live on the GPU as CSR;
+  * the train-loop body of main.py:331-351 actually runs (the reference's stray `continue` at :328 is D2);
+  * evaluate() (main.py:267-310) is fused: p_sample -> history mask -> top-K -> metric sums, all on the device;
+  * `--n_user` replaces the hard-coded `n_user = 3000` (D3); 0 means all users;
+  * data-parallel over logical user batches when launched under torchrun (gradient all-reduce + metric all-reduce
+    over NCCL; everything else is rank-local), see gdmcf_b200/dist_utils.py.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from . import data_utils, dist_utils, evaluate_utils
+from .models import gaussian_diffusion as gd
+from .models.DNN import DNN, DNNOneHotEmbeddingGCN
+from .optim import FusedAdamW
+from .parse_args_util import parse_args
+
+SYNTHETIC_SHAPES = {"yelp": (54574, 34395, 1402736, 0), "amazon": (108822, 94949, 3146256, 1),
+                    "scaled": (1000000, 200000, 50000000, 2)}
+
+
+def load_interactions(args):
+    if args.synthetic:
+        if args.synthetic in SYNTHETIC_SHAPES:
+            U, I, P, seed = SYNTHETIC_SHAPES[args.synthetic]
+        else:
+            U, I, P = (int(x) for x in args.synthetic.split(","))
+            seed = 0
+        tr, va, te = data_utils.synthetic_interactions(U, I, P, seed)
+        import scipy.sparse as sp
+        n_user, n_item = int(tr[:, 0].max()) + 1, int(tr[:, 1].max()) + 1
+        mk = lambda p: sp.csr_matrix((np.ones(len(p)), (p[:, 0], p[:, 1])), dtype="float64", shape=(n_user, n_item))  # noqa: E731
+        print(f'user num: {n_user}')
+        print(f'item num: {n_item}')
+        return mk(tr), mk(va), mk(te), n_user, n_item
+    return data_utils.data_load(args.data_path + 'train_list.npy', args.data_path + 'valid_list.npy',
+                                args.data_path + 'test_list.npy')
+
+
+def build(args, n_user_rows, n_item, device):
+    if args.mean_type == 'x0':
+        mean_type = gd.ModelMeanType.START_X
+    elif args.mean_type == 'eps':
+        mean_type = gd.ModelMeanType.EPSILON
+    else:
+        raise ValueError("Unimplemented mean type %s" % args.mean_type)
+    CatOneHot = args.OneHotMatrix == 2
+    diffusion = gd.GaussianDiffusionDiscrete(mean_type, args.noise_schedule, args.noise_scale, args.noise_min,
+                                             args.noise_max, args.steps, device, discrete=args.discrete,
+                                             CatOneHot=CatOneHot, args=args).to(device)
+    out_dims = args.dims + [n_item]
+    in_dims = out_dims[::-1]
+    print('in_dims:{} out_dims:{}'.format(in_dims, out_dims))
+    print('backbone:', args.backbone)
+    if args.backbone == 'DNN':
+        if CatOneHot:
+            raise ValueError("backbone DNN needs OneHotMatrix != 2")
+        model = DNN(in_dims, out_dims, args.emb_size, time_type="cat", norm=args.norm, precision=args.precision).to(device)
+    elif args.backbone == 'DNNOneHotEmbeddingGCN':
+        diffusion.indexIn = True
+        model = DNNOneHotEmbeddingGCN(in_dims, out_dims, args.emb_size, time_type="cat", norm=args.norm, item_num=n_item,
+                                      user_num=n_user_rows, args=args, precision=args.precision).to(device)
+    else:
+        print('not implemented!')  # the other --backbone values of main.py:212-256 are outside the hot path
+        sys.exit(1)
+    return diffusion, model
+
+
+def evaluate(diffusion, model, train_dev, gt_dev, hist_devs, n_user, batch_size, topN, sampling_steps, dist):
+    """main.py:267-310: rank the first floor(n_user / batch_size) * batch_size users (drop_last=True, :156)."""
+    model.eval()
+    k = topN[-1]
+    n_batches = n_user // batch_size
+    sums = torch.zeros(len(topN), 4, dtype=torch.float64, device=train_dev.device)
+    for b in range(dist.rank, n_batches, dist.world_size):
+        users = torch.arange(b * batch_size, (b + 1) * batch_size, dtype=torch.int32, device=train_dev.device)
+        batch = train_dev.batch(users)
+        idx = diffusion.rank(model, batch, k, hist=hist_devs[0].csr, hist2=hist_devs[1].csr if len(hist_devs) > 1 else None,
+                             steps=sampling_steps)
+        sums += evaluate_utils.metrics_from_device(idx, users, gt_dev.rowptr, gt_dev.col, topN)
+    dist.all_reduce(sums)
+    return evaluate_utils.finalize_metrics(sums, n_batches * batch_size)
+
+
+def main(args):
+    dist = dist_utils.init()
+    out_path = os.path.join(args.log_name, args.dataset, datetime.now().strftime('%Y%m%d'), args.out_name)
+    if dist.rank == 0:
+        os.makedirs(out_path, exist_ok=True)
+    out_path_file = os.path.join(out_path, 'output_NDCG.txt')
+    if not args.debug and dist.rank == 0:
+        sys.stdout = open(out_path_file, 'w')
+    elif dist.rank != 0:
+        sys.stdout = open(os.devnull, 'w')
+    print('out_path:', out_path, out_path_file)
+    print("args:", args)
+    print('random_seed:', args.random_seed)
+    torch.manual_seed(args.random_seed)  # the reference prints the seed but never applies it (main.py:123-127)
+    np.random.seed(args.random_seed)
+    if not torch.cuda.is_available():
+        raise RuntimeError("gdmcf_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    device = torch.device("cuda:{}".format(dist.local_rank if dist.world_size > 1 else args.gpu))
+    torch.cuda.set_device(device)
+    print('device:', device)
+    print("Starting time: ", time.strftime('%Y-%m-%d %H:%M:%S', time.localtime(time.time())))
+
+    train_data, valid_y_data, test_y_data, n_user, n_item = load_interactions(args)
+    n_rows = n_user if args.n_user <= 0 else min(args.n_user, n_user)
+    train_dev = data_utils.DeviceInteractions(train_data[:n_rows], device)
+    valid_dev = data_utils.DeviceInteractions(valid_y_data[:n_rows], device)
+    test_dev = data_utils.DeviceInteractions(test_y_data[:n_rows], device)
+    print('data ready.')
+
+    diffusion, model = build(args, n_rows, n_item, device)
+    diffusion.seed = model.seed = args.random_seed + 1000 * dist.rank
+    dist.broadcast_parameters(model)
+    optimizer = FusedAdamW(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, modules=[model])
+    print("models ready.")
+    param_num = sum(p.nelement() for p in model.parameters()) + sum(p.nelement() for p in diffusion.parameters())
+    print("Number of all parameters:", param_num)
+
+    topN = eval(args.topN) if isinstance(args.topN, str) else list(args.topN)
+    B = args.batch_size
+    eval_B = args.eval_batch_size or B
+    n_batches = n_rows // B  # drop_last=True (main.py:155)
+    best_recall, best_epoch = -100, 0
+    best_test_results = None
+    rng = np.random.default_rng(args.random_seed)
+    print("Start training...")
+    for epoch in range(1, args.epochs + 1):
+        if epoch - best_epoch >= 200:
+            print('-' * 18)
+            print('Exiting from training early')
+            break
+        model.train()
+        start_time = time.time()
+        total_loss = torch.zeros((), dtype=torch.float64, device=device)
+        perm = torch.from_numpy(rng.permutation(n_rows).astype(np.int32)).to(device)  # shuffle=True
+        # data parallel: G consecutive logical batches form one optimizer step
+        for b0 in range(0, n_batches - n_batches % dist.world_size, dist.world_size):
+            b = b0 + dist.rank
+            batch = train_dev.batch(perm[b * B:(b + 1) * B])
+            optimizer.zero_grad()
+            losses = diffusion.training_losses(model, batch, args.reweight, index=batch.users)
+            loss = losses["loss"].mean()
+            total_loss += loss.detach()
+            loss.backward()
+            dist.all_reduce_gradients(model)
+            optimizer.step(grad_scale=1.0 / dist.world_size)
+
+        if epoch % args.eval_every == 0:
+            valid_results = evaluate(diffusion, model, train_dev, valid_dev, [train_dev], n_rows, eval_B, topN,
+                                     args.sampling_steps, dist)
+            test_results = evaluate(diffusion, model, train_dev, test_dev, [train_dev, valid_dev], n_rows, eval_B, topN,
+                                    args.sampling_steps, dist)
+            evaluate_utils.print_results(None, valid_results, test_results)
+            sys.stdout.flush()
+            if valid_results[2][1] > best_recall:  # NDCG@topN[1] despite the name (main.py:362-363)
+                best_recall, best_epoch = test_results[2][1], epoch
+                best_test_results = test_results
+                if dist.rank == 0:
+                    model_path = os.path.join(out_path, 'model.pth')
+                    print('model_path:', model_path)
+                    torch.save(model, model_path)
+        print("Runing Epoch {:03d} ".format(epoch) + 'train loss {:.4f}'.format(float(total_loss)) + " costs " +
+              time.strftime("%H: %M: %S", time.gmtime(time.time() - start_time)))
+        print('---' * 18)
+
+    print('===' * 18)
+    print("End. Best Epoch {:03d} ".format(best_epoch))
+    evaluate_utils.print_results(None, None, best_test_results)
+    print("End time: ", time.strftime('%Y-%m-%d %H:%M:%S', time.localtime(time.time())))
+    dist.shutdown()
+    return best_test_results
+
+
+if __name__ == '__main__':
+    main(parse_args())

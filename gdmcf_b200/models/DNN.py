@@ -1,0 +1,460 @@
+"""Denoisers of the GDMCF hot path — host-side mirror of the reference's models/DNN.py.
+
+Same class names, constructor arguments, `forward` signatures and `state_dict` keys as the reference
+(`DNN` models/DNN.py:11-88; `DNNOneHotEmbeddingGCN` :1105-1327 with `LayerGCN` :1077-1103 and
+`nt_xent_loss` :479-508), so weights copy both ways with `load_state_dict`. The modules only own fp32
+master parameters; every contraction runs in libgdmcf_sm100.so (tcgen05 GEMMs with fused epilogues)
+on bf16 operand copies that are re-derived whenever a parameter changes. There is no torch compute path.
+
+Differences by design:
+  * the GCN is evaluated on the B user rows only: edges are user->item and GCNConv aggregates at the
+    target, so user rows see only their self loop (weight 1) — item rows are dead work in the reference;
+  * the last `emb_size` input columns of the first layers (`cat([x, emb])`) are folded into a per-timestep
+    bias table [steps, d] instead of widening K to a non-multiple of 8;
+  * at inference with `x_tU = one_hot(x0)` the one-hot encoder is a sparse gather-sum
+    (`base + sum_{i in row} delta[i]`) and is hoisted out of the reverse loop.
+`precision="fp32"` runs every contraction as a 3-segment hi/lo bf16 split (~1e-5); default "bf16" (~1e-3).
+"""
+from __future__ import annotations
+
+import copy
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from ..kernels import Bf16Mat
+
+_MAX_T_TABLE = 1024
+
+
+def _as_i32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.int32 else t.to(torch.int32)
+
+
+class _OperandCache:
+    """bf16 (hi[, lo]) operand copies and derived tables, keyed by name, invalidated by parameter version."""
+
+    def __init__(self):
+        self._items: Dict[str, tuple] = {}
+        self.epoch = 0  # bumped by optimizers that write parameters behind torch's version counter
+
+    def get(self, name: str, params, build):
+        ver = (self.epoch,) + tuple((p._version, p.data_ptr()) for p in params)
+        hit = self._items.get(name)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = build()
+        self._items[name] = (ver, val)
+        return val
+
+    def clear(self):
+        self._items.clear()
+
+
+class _EngineModule(nn.Module):
+    """Shared plumbing: precision mode, operand cache, GEMM helper."""
+
+    def _engine_init(self, precision: str):
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self._ops = _OperandCache()
+        self._bufs: Dict[tuple, object] = {}
+        self._rng_calls = 0
+        self.seed = 0
+
+    @property
+    def _lo(self) -> bool:
+        return self.precision == "fp32"
+
+    def weights_updated(self):
+        """Called by optimizers that update parameters through raw pointers (gdmcf_b200.optim.FusedAdamW)."""
+        self._ops.epoch += 1
+
+    def _next_offset(self) -> int:
+        self._rng_calls += 1
+        return self._rng_calls << 40  # disjoint Philox counter ranges per call
+
+    def _buf(self, key, make):
+        b = self._bufs.get(key)
+        if b is None:
+            b = make()
+            self._bufs[key] = b
+        return b
+
+    def _mm(self, a: Bf16Mat, b: Bf16Mat, m: int, n: int, k: int, **epi):
+        """C[m,n] = a[m,k] @ b[n,k]^T (+ fused epilogue) in the module's precision mode."""
+        if self._lo:
+            K.gemm([a.hi, a.hi, a.lo], [b.hi, b.lo, b.hi], m, n, [k, k, k], **epi)
+        else:
+            K.gemm([a.hi], [b.hi], m, n, [k], **epi)
+
+    def _weight_operand(self, name: str, param: torch.Tensor, cols: Optional[int] = None, transpose: bool = False) -> Bf16Mat:
+        def build():
+            w = param.detach()
+            if cols is not None:
+                w = w[:, :cols]
+            return (K.cast_bf16_transpose if transpose else K.cast_bf16)(w, with_lo=self._lo)
+        return self._ops.get(name + (".T" if transpose else "") + self.precision, [param], build)
+
+    def __getstate__(self):  # torch.save(model) (main.py:375): drop device caches
+        st = self.__dict__.copy()
+        st["_ops"], st["_bufs"] = _OperandCache(), {}
+        return st
+
+
+def _init_linear(layer: nn.Linear):
+    """init_weights, models/DNN.py:39-70: N(0, sqrt(2/(fan_in+fan_out))) weights, N(0, 0.001) biases."""
+    fan_out, fan_in = layer.weight.shape
+    std = np.sqrt(2.0 / (fan_in + fan_out))
+    layer.weight.data.normal_(0.0, std)
+    layer.bias.data.normal_(0.0, 0.001)
+
+
+class DNN(_EngineModule):
+    """models/DNN.py:11-88 — `[x, emb(t)] -> tanh(Linear(n_item+e -> d)) -> Linear(d -> n_item)`."""
+
+    def __init__(self, in_dims, out_dims, emb_size, time_type="cat", norm=False, dropout=0.5, precision="bf16"):
+        super().__init__()
+        self.in_dims, self.out_dims = in_dims, out_dims
+        assert out_dims[0] == in_dims[-1], "In and out dimensions must equal to each other."
+        if time_type != "cat":
+            raise ValueError("Unimplemented timestep embedding type %s" % time_type)
+        if len(in_dims) != 2 or len(out_dims) != 2:
+            raise NotImplementedError("the hot path covers one hidden layer (dims=[d]); got %s" % (in_dims,))
+        if norm:
+            raise NotImplementedError("norm=True (F.normalize on the input) is outside the configured hot path")
+        self.time_type, self.time_emb_dim, self.norm = time_type, emb_size, norm
+        self.emb_layer = nn.Linear(emb_size, emb_size)
+        in_t = [in_dims[0] + emb_size] + list(in_dims[1:])
+        self.in_layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(in_t[:-1], in_t[1:])])
+        self.out_layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(out_dims[:-1], out_dims[1:])])
+        self.drop = nn.Dropout(dropout)
+        self.init_weights()
+        self._engine_init(precision)
+
+    def init_weights(self):
+        for layer in list(self.in_layers) + list(self.out_layers) + [self.emb_layer]:
+            _init_linear(layer)
+
+    # -- operands ------------------------------------------------------------------------------
+    @property
+    def n_item(self) -> int:
+        return self.in_dims[0]
+
+    @property
+    def hidden(self) -> int:
+        return self.in_dims[1]
+
+    def _tables(self, T: int):
+        l0 = self.in_layers[0]
+        return self._ops.get(f"tb{T}", [self.emb_layer.weight, self.emb_layer.bias, l0.weight, l0.bias],
+                             lambda: K.time_bias_table(self.emb_layer.weight.detach(), self.emb_layer.bias.detach(),
+                                                       l0.weight.detach(), self.n_item, l0.bias.detach(), T)[0])
+
+    # -- forward -------------------------------------------------------------------------------
+    def _encode(self, x_op: Bf16Mat, B: int, ts, t_const: int, T: int, h_out: Bf16Mat, h_f32=None):
+        w1 = self._weight_operand("in0", self.in_layers[0].weight, cols=self.n_item)
+        self._mm(x_op, w1, B, self.hidden, self.n_item, act=K.ACT_TANH, bias=self._tables(T), ld_bias=self.hidden,
+                 row_t=ts, t_const=t_const, out_bf16=h_out.hi, out_bf16_lo=h_out.lo, out_f32=h_f32)
+
+    def _decode(self, h: Bf16Mat, B: int, out_f32, out_op: Optional[Bf16Mat] = None, **post):
+        wo = self._weight_operand("out0", self.out_layers[0].weight)
+        self._mm(h, wo, B, self.n_item, self.hidden, bias=self.out_layers[0].bias.detach(), out_f32=out_f32,
+                 out_bf16=out_op.hi if out_op is not None else None, out_bf16_lo=out_op.lo if out_op is not None else None,
+                 **post)
+
+    @torch.no_grad()
+    def forward(self, x, timesteps):
+        """x: fp32 [B, n_item] CUDA tensor; timesteps: int [B]. Returns fp32 [B, n_item] (models/DNN.py:72-88)."""
+        K.require_cuda(x)
+        B, I = x.shape
+        assert I == self.n_item and timesteps.shape == (B,)
+        ts = _as_i32(timesteps)
+        x_op = self._buf(("x", B), lambda: Bf16Mat.empty(B, I, x.device, self._lo))
+        p = self.drop.p if self.training else 0.0
+        K.qsample_dropout(x, B, I, x_op, dropout_p=p, seed=self.seed, offset=self._next_offset())
+        h = self._buf(("h", B), lambda: Bf16Mat.empty(B, self.hidden, x.device, self._lo))
+        self._encode(x_op, B, ts, 0, _MAX_T_TABLE, h)
+        out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=x.device)
+        self._decode(h, B, out)
+        return out[:, :I]
+
+    @torch.no_grad()
+    def reverse_loop(self, x0_f32, B: int, index, steps_total: int, c1, c2, x0_op: Optional[Bf16Mat] = None,
+                     csr=None, users=None):
+        """The p_sample loop (models/gaussian_diffusion.py:695-752) for this backbone: x_t <- c1[t]*f(x_t,t) + c2[t]*x_t,
+        t = T-1..0, with the posterior mean fused into the output GEMM's epilogue. x0_f32: [B, ld4] fp32 start
+        (x_t = x_start, or its q_sample); returns the fp32 buffer [B, ld4] holding the final x_t."""
+        I, dev = self.n_item, x0_f32.device
+        ld4 = x0_f32.shape[1]
+        bufs = self._buf(("rev", B), lambda: dict(
+            xa=torch.empty(B, ld4, dtype=torch.float32, device=dev), xb=torch.empty(B, ld4, dtype=torch.float32, device=dev),
+            xop=Bf16Mat.empty(B, I, dev, self._lo), h=Bf16Mat.empty(B, self.hidden, dev, self._lo)))
+        x_op = x0_op
+        if x_op is None:
+            x_op = bufs["xop"]
+            K.qsample_dropout(x0_f32, B, I, x_op)
+        cur, nxt = x0_f32, bufs["xa"]
+        for t in reversed(range(steps_total)):
+            self._encode(x_op, B, None, t, steps_total, bufs["h"])
+            last = t == 0
+            self._decode(bufs["h"], B, nxt, None if last else bufs["xop"], c1=c1, c2=c2, xt=cur, t_const=t)
+            x_op = bufs["xop"]
+            cur, nxt = nxt, (bufs["xb"] if nxt is bufs["xa"] else bufs["xa"])
+        return cur
+
+
+class _GCNLin(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(o, i))
+        a = math.sqrt(6.0 / (i + o))  # PyG Linear(weight_initializer='glorot')
+        nn.init.uniform_(self.weight, -a, a)
+
+
+class GCNConvParams(nn.Module):
+    """Parameters of torch_geometric.nn.GCNConv with its state_dict keys (`bias`, `lin.weight`)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.lin = _GCNLin(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+
+class LayerGCN(nn.Module):
+    """models/DNN.py:1077-1103 (gcnLayerNum == 2). Holds the parameters; DNNOneHotEmbeddingGCN evaluates it on the
+    user rows (self loop only): conv2(relu(conv1(x))) = W2 relu(W1 x + b1) + b2."""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, residual=False, args=None):
+        super().__init__()
+        if args is not None and getattr(args, "gcnLayerNum", 2) != 2:
+            raise NotImplementedError("gcnLayerNum in {0,1} are ablations outside the hot path")
+        if residual:
+            raise NotImplementedError("residual=True is never used by the reference model")
+        self.conv1 = GCNConvParams(in_channels, hidden_channels)
+        self.conv2 = GCNConvParams(hidden_channels, out_channels)
+
+
+class DNNOneHotEmbeddingGCN(_EngineModule):
+    """models/DNN.py:1105-1327 — the GDMCF denoiser (noise_type=0, gcnLayerNum=2)."""
+
+    def __init__(self, in_dims, out_dims, emb_size, time_type="cat", norm=False, dropout=0.5, item_num=2810,
+                 user_num=5949, args=None, precision="bf16"):
+        super().__init__()
+        self.args = args
+        if args is not None and getattr(args, "noise_type", 0) != 0:
+            raise NotImplementedError("noise_type in {1,2} are ablations outside the hot path")
+        in_dims, out_dims = list(in_dims), list(out_dims)
+        self.in_dims = in_dims
+        self.in_dims2 = copy.deepcopy(in_dims)
+        self.in_dims2[0] *= 2
+        self.out_dims = out_dims
+        assert out_dims[0] == in_dims[-1], "In and out dimensions must equal to each other."
+        if time_type != "cat":
+            raise ValueError("Unimplemented timestep embedding type %s" % time_type)
+        if len(in_dims) != 2:
+            raise NotImplementedError("the hot path covers one hidden layer (dims=[d]); got %s" % (in_dims,))
+        if norm:
+            raise NotImplementedError("norm=True is outside the configured hot path")
+        if in_dims[1] % 8:
+            raise NotImplementedError("dims[0] must be a multiple of 8 (16-byte aligned segments of the user tower)")
+        self.time_type, self.time_emb_dim, self.norm = time_type, emb_size, norm
+        self.emb_layer = nn.Linear(emb_size, emb_size)
+        in_t = [in_dims[0] + emb_size] + in_dims[1:]
+        in_t2 = [self.in_dims2[0] + emb_size] + self.in_dims2[1:]
+        out_t = out_dims
+        out_t[0] += self.in_dims2[-1]  # models/DNN.py:1128 (mutates out_dims like the reference)
+        self.in_layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(in_t[:-1], in_t[1:])])
+        self.in_layers2 = nn.ModuleList([nn.Linear(a, b) for a, b in zip(in_t2[:-1], in_t2[1:])])
+        # out_layers is constructed by the reference but never used in forward (its grads stay None); it is kept
+        # so that parameter counts and state_dict keys match.
+        self.out_layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(out_t[:-1], out_t[1:])])
+        self.drop = nn.Dropout(dropout)
+        e_user = in_t[-1]
+        e_item = in_t[-1] + e_user + in_t2[-1]
+        self.embedding_item = nn.Embedding(item_num, e_item)
+        self.embedding_user = nn.Embedding(user_num, e_user)
+        self.gcn_model = LayerGCN(e_item, 512, e_item, residual=False, args=args)
+        self.init_weights()
+        self.sumW = nn.Parameter(torch.tensor(1.0))
+        self.item_num, self.user_num = item_num, user_num
+        self._engine_init(precision)
+
+    def init_weights(self):
+        for layer in list(self.in_layers) + list(self.in_layers2) + list(self.out_layers) + [self.emb_layer]:
+            _init_linear(layer)
+        nn.init.xavier_uniform_(self.embedding_item.weight)
+        nn.init.xavier_uniform_(self.embedding_user.weight)
+
+    # -- shapes --------------------------------------------------------------------------------
+    @property
+    def n_item(self) -> int:
+        return self.in_dims[0]
+
+    @property
+    def hidden(self) -> int:
+        return self.in_dims[1]
+
+    # -- operands ------------------------------------------------------------------------------
+    def _tables(self, T: int):
+        e = self.emb_layer
+        l1, l2 = self.in_layers[0], self.in_layers2[0]
+        tb1 = self._ops.get(f"tb1.{T}", [e.weight, e.bias, l1.weight, l1.bias],
+                            lambda: K.time_bias_table(e.weight.detach(), e.bias.detach(), l1.weight.detach(), self.n_item,
+                                                      l1.bias.detach(), T)[0])
+        tb2 = self._ops.get(f"tb2.{T}", [e.weight, e.bias, l2.weight, l2.bias],
+                            lambda: K.time_bias_table(e.weight.detach(), e.bias.detach(), l2.weight.detach(), 2 * self.n_item,
+                                                      l2.bias.detach(), T)[0])
+        return tb1, tb2
+
+    def _onehot_tables(self):
+        w2 = self.in_layers2[0].weight
+        return self._ops.get("onehot", [w2], lambda: K.onehot_tables(w2.detach(), self.hidden, self.n_item))
+
+    def _item_operands(self):
+        E = self.embedding_item.weight
+        e_op = self._weight_operand("E", E)
+        inv = self._ops.get("E.inv", [E], lambda: K.row_inv_norm(E.detach()))
+        return e_op, inv
+
+    # -- pieces of the forward -----------------------------------------------------------------
+    def _hc_buffers(self, B: int, dev):
+        d = self.hidden
+        return self._buf(("hc", B), lambda: dict(
+            hc_f32=torch.empty(B, 3 * d, dtype=torch.float32, device=dev), hc=Bf16Mat.empty(B, 3 * d, dev, self._lo),
+            g1=Bf16Mat.empty(B, 512, dev, self._lo), g2=torch.empty(B, 3 * d, dtype=torch.float32, device=dev),
+            hcp=Bf16Mat.empty(B, 3 * d, dev, self._lo), inv_u=torch.empty(B, dtype=torch.float32, device=dev),
+            xop=Bf16Mat.empty(B, self.n_item, dev, self._lo), S=torch.empty(B, d, dtype=torch.float32, device=dev)))
+
+    def _seg(self, bufs, s: int):
+        """fp32 / bf16 views of segment s (h | h_U | e_user) of the concatenated user tower."""
+        d = self.hidden
+        hc = bufs["hc"]
+        return (bufs["hc_f32"][:, s * d:(s + 1) * d], hc.hi[:, s * d:], hc.lo[:, s * d:] if hc.lo is not None else None)
+
+    def _encode_x(self, bufs, x_op: Bf16Mat, B: int, ts, t_const: int, T: int):
+        tb1, _ = self._tables(T)
+        w1 = self._weight_operand("in0", self.in_layers[0].weight, cols=self.n_item)
+        f32, hi, lo = self._seg(bufs, 0)
+        self._mm(x_op, w1, B, self.hidden, self.n_item, act=K.ACT_TANH, bias=tb1, ld_bias=self.hidden, row_t=ts,
+                 t_const=t_const, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+
+    def _encode_onehot_from_S(self, bufs, B: int, ts, t_const: int, T: int):
+        _, tb2 = self._tables(T)
+        f32, hi, lo = self._seg(bufs, 1)
+        K.bias_act_rows(bufs["S"], B, self.hidden, bias=tb2, ld_bias=self.hidden, row_t=ts, t_const=t_const,
+                        act=K.ACT_TANH, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+
+    def _encode_onehot_dense(self, bufs, xu_op_hi: torch.Tensor, B: int, ts, t_const: int, T: int, to_S: bool):
+        """h_U from a dense one-hot-branch operand [B, 2I] (training / noised inference): tensor-core GEMM."""
+        w2 = self._weight_operand("in2", self.in_layers2[0].weight, cols=2 * self.n_item)
+        k = 2 * self.n_item
+        if to_S:  # pre-activation only (step-invariant part, hoisted out of the reverse loop)
+            K.gemm([xu_op_hi], [w2.hi], B, self.hidden, [k], out_f32=bufs["S"]) if not self._lo else \
+                K.gemm([xu_op_hi, xu_op_hi], [w2.hi, w2.lo], B, self.hidden, [k, k], out_f32=bufs["S"])
+            return
+        _, tb2 = self._tables(T)
+        f32, hi, lo = self._seg(bufs, 1)
+        epi = dict(act=K.ACT_TANH, bias=tb2, ld_bias=self.hidden, row_t=ts, t_const=t_const, out_f32=f32, out_bf16=hi,
+                   out_bf16_lo=lo)
+        if self._lo:  # the one-hot operand is exact in bf16 ({0,1,2}): only the weight needs the lo term
+            K.gemm([xu_op_hi, xu_op_hi], [w2.hi, w2.lo], B, self.hidden, [k, k], **epi)
+        else:
+            K.gemm([xu_op_hi], [w2.hi], B, self.hidden, [k], **epi)
+
+    def _user_tower(self, bufs, B: int):
+        """GCN on the user rows + sumW mix + row norms (models/DNN.py:1274-1288, :1320)."""
+        d3 = 3 * self.hidden
+        c1, c2 = self.gcn_model.conv1, self.gcn_model.conv2
+        wc1 = self._weight_operand("gcn1", c1.lin.weight)
+        wc2 = self._weight_operand("gcn2", c2.lin.weight)
+        g1 = bufs["g1"]
+        self._mm(bufs["hc"], wc1, B, 512, d3, act=K.ACT_RELU, bias=c1.bias.detach(), out_bf16=g1.hi, out_bf16_lo=g1.lo)
+        self._mm(g1, wc2, B, d3, 512, bias=c2.bias.detach(), out_f32=bufs["g2"])
+        K.mix_rownorm(bufs["hc_f32"], B, d3, g=bufs["g2"], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
+
+    def _score(self, bufs, B: int, out_f32, out_op: Optional[Bf16Mat] = None, **post):
+        """cosine_similarity_cuda (models/DNN.py:1304-1327) with the norms applied in the GEMM epilogue."""
+        e_op, inv_i = self._item_operands()
+        self._mm(bufs["hcp"], e_op, B, self.n_item, 3 * self.hidden, row_scale=bufs["inv_u"], col_scale=inv_i,
+                 out_f32=out_f32, out_bf16=out_op.hi if out_op is not None else None,
+                 out_bf16_lo=out_op.lo if out_op is not None else None, **post)
+
+    # -- reference call surface ----------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, timesteps, x_U, index=None, graph=None, RCloss=False):
+        """models/DNN.py:1207-1302. x: fp32 [B, I]; x_U: [B, I, 2]; index: user ids [B]. `graph` is accepted and
+        ignored: it only feeds item rows of the GCN, which the model never reads (see module docstring).
+        Inference/eval forward (no autograd); training goes through GaussianDiffusionDiscrete.training_losses."""
+        if RCloss:
+            raise NotImplementedError("RCloss is produced by the fused training step (training_losses), not by forward()")
+        K.require_cuda(x, x_U)
+        B, I = x.shape
+        assert I == self.n_item and timesteps.shape == (B,) and index is not None
+        dev = x.device
+        ts = _as_i32(timesteps)
+        bufs = self._hc_buffers(B, dev)
+        p = self.drop.p if self.training else 0.0
+        K.qsample_dropout(x, B, I, bufs["xop"], dropout_p=p, seed=self.seed, offset=self._next_offset())
+        self._encode_x(bufs, bufs["xop"], B, ts, 0, _MAX_T_TABLE)
+        xu = self._buf(("xu", B), lambda: torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev))
+        xu_f = x_U.reshape(B, 2 * I).float()
+        tmp = Bf16Mat(xu, None, B, 2 * I)
+        K.qsample_dropout(xu_f, B, 2 * I, tmp, dropout_p=p, seed=self.seed + 1, offset=self._next_offset())
+        self._encode_onehot_dense(bufs, xu, B, ts, 0, _MAX_T_TABLE, to_S=False)
+        f32, hi, lo = self._seg(bufs, 2)
+        K.gather_rows(self.embedding_user.weight.detach(), _as_i32(index.to(dev)), B, self.hidden, out_f32=f32, out_bf16=hi,
+                      out_bf16_lo=lo)
+        self._user_tower(bufs, B)
+        out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
+        self._score(bufs, B, out)
+        return out[:, :I]
+
+    @torch.no_grad()
+    def reverse_loop(self, x0_f32, B: int, index, steps_total: int, c1, c2, x0_op: Optional[Bf16Mat] = None,
+                     csr=None, users=None, xu_op: Optional[torch.Tensor] = None):
+        """The p_sample loop (models/gaussian_diffusion.py:695-752) for GDMCF. The one-hot encoder's pre-activation
+        S(x_tU) does not depend on t and is computed once: sparse gather from the CSR rows when x_tU = one_hot(x0)
+        (csr=(rowptr, col), users), else one dense GEMM on `xu_op` [B, 2I]. Per step: encoder GEMM (split-K) ->
+        user tower -> scorer GEMM whose epilogue applies the cosine norms and the posterior mean."""
+        I, d, dev = self.n_item, self.hidden, x0_f32.device
+        ld4 = x0_f32.shape[1]
+        bufs = self._hc_buffers(B, dev)
+        rb = self._buf(("rev", B, ld4), lambda: dict(xa=torch.empty(B, ld4, dtype=torch.float32, device=dev),
+                                                     xb=torch.empty(B, ld4, dtype=torch.float32, device=dev)))
+        if xu_op is not None:
+            self._encode_onehot_dense(bufs, xu_op, B, None, 0, steps_total, to_S=True)
+        else:
+            base, delta = self._onehot_tables()
+            K.encode_onehot_gather(csr[0], csr[1], users, B, base, delta, d, bufs["S"])
+        f32, hi, lo = self._seg(bufs, 2)
+        K.gather_rows(self.embedding_user.weight.detach(), index, B, d, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+        x_op = x0_op
+        if x_op is None:
+            x_op = bufs["xop"]
+            K.qsample_dropout(x0_f32, B, I, x_op)
+        cur, nxt = x0_f32, rb["xa"]
+        for t in reversed(range(steps_total)):
+            self._encode_x(bufs, x_op, B, None, t, steps_total)
+            self._encode_onehot_from_S(bufs, B, None, t, steps_total)
+            self._user_tower(bufs, B)
+            last = t == 0
+            self._score(bufs, B, nxt, None if last else bufs["xop"], c1=c1, c2=c2, xt=cur, t_const=t)
+            x_op = bufs["xop"]
+            cur, nxt = nxt, (rb["xb"] if nxt is rb["xa"] else rb["xa"])
+        return cur
+
+
+def timestep_embedding(timesteps, dim, max_period=10000):
+    """models/DNN.py:1806-1825 (host-side helper kept for API parity; the kernels build their own tables)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(timesteps.device)
+    args = timesteps[:, None].float() * freqs[None]
+    embedding = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        embedding = torch.cat([embedding, torch.zeros_like(embedding[:, :1])], dim=-1)
+    return embedding

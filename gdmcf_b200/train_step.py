@@ -1,0 +1,392 @@
+"""Fused training step behind GaussianDiffusionDiscrete.training_losses (models/gaussian_diffusion.py:834-957).
+
+The reference builds the loss with autograd over ATen ops. Here one torch.autograd.Function wraps the whole
+denoiser: its forward launches the CUDA forward (noising, both encoders, nt_xent logits, user tower, cosine
+scorer, per-row MSE) and returns `(mse[B], closs)`; its backward launches the hand-written backward (loss-gradient
+pass, dgrad/wgrad contractions on the tensor cores, activation/mix/softmax backward) and hands one gradient per
+parameter back to autograd. The O(B) bookkeeping of training_losses (SNR reweighting, Lt_history, /pt, +0.1*closs)
+stays in torch on [B]-sized vectors so dtypes follow the reference (float64 loss). The caller keeps its loop:
+    losses = diffusion.training_losses(model, batch, reweight, index=index); losses["loss"].mean().backward()
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import kernels as K
+from .kernels import Bf16Mat
+from .models.DNN import DNN, DNNOneHotEmbeddingGCN, timestep_embedding
+
+
+def _vec_cache(model, name, make):
+    return model._buf(("vec", name), make)
+
+
+def _ones(model, n, dev):
+    return _vec_cache(model, f"ones{n}", lambda: torch.ones(n, dtype=torch.float32, device=dev))
+
+
+def _arange32(model, n, dev):
+    return _vec_cache(model, f"arange{n}", lambda: torch.arange(n, dtype=torch.int32, device=dev))
+
+
+def _temb_table(model, T, dev):
+    return _vec_cache(model, f"temb{T}", lambda: timestep_embedding(torch.arange(T), model.time_emb_dim).to(dev).contiguous())
+
+
+def _mm_auto(model, a: Bf16Mat, b: Bf16Mat, m, n, k, **epi):
+    """Contraction in the model's precision; operands that carry no lo part fall back to their hi part only."""
+    if model._lo and a.lo is not None and b.lo is not None:
+        K.gemm([a.hi, a.hi, a.lo], [b.hi, b.lo, b.hi], m, n, [k, k, k], **epi)
+    elif model._lo and b.lo is not None:
+        K.gemm([a.hi, a.hi], [b.hi, b.lo], m, n, [k, k], **epi)
+    elif model._lo and a.lo is not None:
+        K.gemm([a.hi, a.lo], [b.hi, b.hi], m, n, [k, k], **epi)
+    else:
+        K.gemm([a.hi], [b.hi], m, n, [k], **epi)
+
+
+def _mm3(a: Bf16Mat, b: Bf16Mat, m, n, k, **epi):
+    """Always split-precision (used for the nt_xent logits, whose softmax amplifies operand rounding 10x)."""
+    K.gemm([a.hi, a.hi, a.lo], [b.hi, b.lo, b.hi], m, n, [k, k, k], **epi)
+
+
+def _bf16_T(x: Bf16Mat, rows, cols, dev) -> Bf16Mat:
+    """Transpose a bf16 operand [rows, cols] -> [cols, rows] (hi and lo)."""
+    out = Bf16Mat.empty(cols, rows, dev, x.lo is not None, zero=False)
+    K.transpose_bf16(x.hi, rows, cols, out.hi)
+    if x.lo is not None:
+        K.transpose_bf16(x.lo, rows, cols, out.lo)
+    return out
+
+
+class _Ctx:
+    """Tensors the backward needs (kept alive between forward and backward of one step)."""
+
+
+# ======================================================================================================
+# GDMCF backbone
+# ======================================================================================================
+_GDMCF_PARAMS = ("emb_layer.weight", "emb_layer.bias", "in_layers.0.weight", "in_layers.0.bias", "in_layers2.0.weight",
+                 "in_layers2.0.bias", "embedding_item.weight", "embedding_user.weight", "gcn_model.conv1.bias",
+                 "gcn_model.conv1.lin.weight", "gcn_model.conv2.bias", "gcn_model.conv2.lin.weight", "sumW")
+
+
+def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc, ts, inject) -> _Ctx:
+    dev, d, T = x0.device, model.hidden, diff.steps
+    inject = inject or {}
+    p = model.drop.p if model.training else 0.0
+    c = _Ctx()
+    c.B, c.I, c.x0, c.ts, c.idx32 = B, I, x0, ts, idx32
+    # noising + dropout + operand cast, one pass each (gaussian_diffusion.py:849-870, DNN.py:1232-1233)
+    c.A1 = Bf16Mat.empty(B, I, dev, model._lo, zero=False)
+    keep = inject.get("keep_x")
+    K.qsample_dropout(x0, B, I, c.A1, row_t=ts, sqrt_ab=diff._f32["sqrt_alphas_cumprod"],
+                      sqrt_1mab=diff._f32["sqrt_one_minus_alphas_cumprod"], noise=inject.get("noise"),
+                      keep=keep.to(torch.uint8).contiguous() if keep is not None else None, dropout_p=p, seed=diff.seed,
+                      offset=diff._offset())
+    c.A2 = torch.empty(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)
+    kxu = inject.get("keep_xU")
+    K.onehot_noise(x0, B, I, c.A2, ts=ts_disc, discrete=float(diff.discrete), dropout_p=p, u_keep=inject.get("u_keep"),
+                   u_drop=kxu.float().contiguous() if kxu is not None else None, seed=diff.seed, offset=diff._offset())
+    # user tower buffers: always with lo parts (nt_xent needs split precision)
+    c.hc_f32 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
+    c.hc = Bf16Mat.empty(B, 3 * d, dev, True)
+    bufs = dict(hc_f32=c.hc_f32, hc=c.hc, S=None)
+    model._encode_x(bufs, c.A1, B, ts, 0, T)
+    model._encode_onehot_dense(bufs, c.A2, B, ts, 0, T, to_S=False)
+    f32, hi, lo = model._seg(bufs, 2)
+    K.gather_rows(model.embedding_user.weight.detach(), idx32, B, d, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+    # nt_xent logits (DNN.py:488): S_raw = h h_U^T, split precision
+    h_op = Bf16Mat(c.hc.hi[:, :d], c.hc.lo[:, :d], B, d)
+    hu_op = Bf16Mat(c.hc.hi[:, d:2 * d], c.hc.lo[:, d:2 * d], B, d)
+    c.S = torch.empty(B, K.round_up(B, 4), dtype=torch.float32, device=dev)
+    _mm3(h_op, hu_op, B, B, d, out_f32=c.S)
+    c.closs_rows = torch.empty(B, dtype=torch.float32, device=dev)
+    K.ntxent_rows(c.S, B, loss_rows=c.closs_rows)
+    # GCN on user rows, mix, norms (DNN.py:1274-1288)
+    g = model.gcn_model
+    wc1 = model._weight_operand("gcn1", g.conv1.lin.weight)
+    wc2 = model._weight_operand("gcn2", g.conv2.lin.weight)
+    c.g1_f32 = torch.empty(B, 512, dtype=torch.float32, device=dev)
+    c.g1 = Bf16Mat.empty(B, 512, dev, model._lo)
+    hc_in = c.hc if model._lo else Bf16Mat(c.hc.hi, None, B, 3 * d)
+    _mm_auto(model, hc_in, wc1, B, 512, 3 * d, act=K.ACT_RELU, bias=g.conv1.bias.detach(), out_f32=c.g1_f32,
+             out_bf16=c.g1.hi, out_bf16_lo=c.g1.lo)
+    c.g2 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
+    _mm_auto(model, c.g1, wc2, B, 3 * d, 512, bias=g.conv2.bias.detach(), out_f32=c.g2)
+    c.hcp_f32 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
+    c.hcp = Bf16Mat.empty(B, 3 * d, dev, model._lo)
+    c.inv_u = torch.empty(B, dtype=torch.float32, device=dev)
+    K.mix_rownorm(c.hc_f32, B, 3 * d, g=c.g2, sumw=model.sumW.detach(), out_f32=c.hcp_f32, out=c.hcp, inv_norm=c.inv_u)
+    # cosine scorer (DNN.py:1304-1327) and per-row MSE (gaussian_diffusion.py:902)
+    e_op, c.inv_i = model._item_operands()
+    c.out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
+    _mm_auto(model, c.hcp, e_op, B, I, 3 * d, row_scale=c.inv_u, col_scale=c.inv_i, out_f32=c.out)
+    c.mse = K.mse_rows(c.out, x0, B, I)
+    return c
+
+
+def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Tensor, g_closs: torch.Tensor):
+    B, I, d, dev, T = c.B, c.I, model.hidden, c.x0.device, diff.steps
+    d3, e = 3 * d, model.time_emb_dim
+    lo = model._lo
+    P = dict(model.named_parameters())
+    grads: Dict[str, torch.Tensor] = {}
+    ones1 = _ones(model, 1, dev)
+    Bp = K.round_up(B, 64)
+    # ---- dL/d out, fused with operand production and the norm-term reductions
+    Gs = torch.zeros(B, K.round_up(I, 64), dtype=torch.bfloat16, device=dev)
+    GsT = torch.empty(I, Bp, dtype=torch.bfloat16, device=dev)
+    n_cb = (I + 31) // 32
+    colsum = torch.empty(I, dtype=torch.float32, device=dev)
+    rowpart = torch.empty(n_cb, B, dtype=torch.float32, device=dev)
+    K.loss_grad(c.out, c.x0, g_mse.float().contiguous(), B, I, Gs, GT=GsT, row_scale=c.inv_u, col_scale=c.inv_i,
+                with_out=True, colsum=colsum, rowpart=rowpart)
+    r_b = K.colsum_f32(rowpart, n_cb, B)
+    # ---- cosine backward w.r.t. the user tower: d hc' = Gs E - hc' * ru^2 * r_b
+    eT = model._weight_operand("E", model.embedding_item.weight, transpose=True)  # [3d, I]
+    d_hcp = torch.empty(B, d3, dtype=torch.float32, device=dev)
+    coef_u = -(c.inv_u * c.inv_u) * r_b
+    _mm_auto(model, Bf16Mat(Gs, None, B, I), eT, B, d3, I, out_f32=d_hcp, row_t=_arange32(model, B, dev),
+             c1=_ones(model, B, dev), c2=coef_u, xt=c.hcp_f32)
+    # ---- d E = Gs^T hc' - E * ri^2 * c_i   (written straight into the parameter's gradient)
+    hcpT = K.cast_bf16_transpose(c.hcp_f32, with_lo=lo)  # [3d, B]
+    gE = torch.empty_like(P["embedding_item.weight"])
+    coef_i = -(c.inv_i * c.inv_i) * colsum
+    _mm_auto(model, Bf16Mat(GsT, None, I, B), hcpT, I, d3, B, out_f32=gE, row_t=_arange32(model, I, dev),
+             c1=_ones(model, I, dev), c2=coef_i, xt=P["embedding_item.weight"].detach())
+    grads["embedding_item.weight"] = gE
+    # ---- sumW mix backward
+    d_hc = torch.empty(B, d3, dtype=torch.float32, device=dev)
+    d_g2 = torch.empty(B, d3, dtype=torch.float32, device=dev)
+    dw_rows = torch.empty(B, dtype=torch.float32, device=dev)
+    K.mix_backward(d_hcp, c.hc_f32, c.g2, model.sumW.detach(), d_hc, d_g2, dw_rows, B, d3)
+    grads["sumW"] = dw_rows.sum()
+    # ---- GCN (user rows) backward
+    g = model.gcn_model
+    d_g2_op = K.cast_bf16(d_g2, with_lo=lo)
+    d_g2T = K.cast_bf16_transpose(d_g2, with_lo=lo)      # [3d, B]
+    g1T = K.cast_bf16_transpose(c.g1_f32, with_lo=lo)    # [512, B]
+    gW2 = torch.empty_like(P["gcn_model.conv2.lin.weight"])
+    _mm_auto(model, d_g2T, g1T, d3, 512, B, out_f32=gW2)
+    grads["gcn_model.conv2.lin.weight"] = gW2
+    grads["gcn_model.conv2.bias"] = K.colsum_f32(d_g2, B, d3)
+    wc2T = model._weight_operand("gcn2", g.conv2.lin.weight, transpose=True)  # [512, 3d]
+    d_g1 = torch.empty(B, 512, dtype=torch.float32, device=dev)
+    _mm_auto(model, d_g2_op, wc2T, B, 512, d3, out_f32=d_g1)
+    d_pre1 = torch.empty(B, 512, dtype=torch.float32, device=dev)
+    d_pre1_op = Bf16Mat.empty(B, 512, dev, lo, zero=True)
+    K.ew_binary(K.EW_RELU_BWD, d_g1, c.g1_f32, B, 512, out_f32=d_pre1, out_bf16=d_pre1_op.hi, out_bf16_lo=d_pre1_op.lo)
+    d_pre1T = K.cast_bf16_transpose(d_pre1, with_lo=lo)  # [512, B]
+    hcT = K.cast_bf16_transpose(c.hc_f32, with_lo=lo)    # [3d, B]
+    gW1 = torch.empty_like(P["gcn_model.conv1.lin.weight"])
+    _mm_auto(model, d_pre1T, hcT, 512, d3, B, out_f32=gW1)
+    grads["gcn_model.conv1.lin.weight"] = gW1
+    grads["gcn_model.conv1.bias"] = K.colsum_f32(d_pre1, B, 512)
+    wc1T = model._weight_operand("gcn1", g.conv1.lin.weight, transpose=True)  # [3d, 512]
+    d_hc_tot = torch.empty(B, d3, dtype=torch.float32, device=dev)
+    _mm_auto(model, d_pre1_op, wc1T, B, d3, 512, out_f32=d_hc_tot, c1=ones1, c2=ones1, xt=d_hc, t_const=0)
+    # ---- user embedding rows
+    gU = torch.zeros_like(P["embedding_user.weight"])
+    K.scatter_rows_add(d_hc_tot[:, 2 * d:], c.idx32, gU, B, d)
+    grads["embedding_user.weight"] = gU
+    # ---- nt_xent backward (DNN.py:479-508) into h and h_U
+    dS = torch.empty(B, K.round_up(B, 4), dtype=torch.float32, device=dev)
+    K.ntxent_rows(c.S, B, dscale=g_closs.float().reshape(1), dS=dS)
+    dS_op = K.cast_bf16(dS[:, :B], with_lo=True)
+    dST_op = K.cast_bf16_transpose(dS[:, :B], with_lo=True)
+    hT = K.cast_bf16_transpose(c.hc_f32[:, :d], with_lo=True)          # [d, B]
+    hUT = K.cast_bf16_transpose(c.hc_f32[:, d:2 * d], with_lo=True)    # [d, B]
+    dh_tot = torch.empty(B, d, dtype=torch.float32, device=dev)
+    dhU_tot = torch.empty(B, d, dtype=torch.float32, device=dev)
+    _mm3(dS_op, hUT, B, d, B, out_f32=dh_tot, c1=ones1, c2=ones1, xt=d_hc_tot[:, :d], t_const=0)
+    _mm3(dST_op, hT, B, d, B, out_f32=dhU_tot, c1=ones1, c2=ones1, xt=d_hc_tot[:, d:2 * d], t_const=0)
+    # ---- tanh backward, first-layer weight gradients
+    dh_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
+    dhU_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
+    K.ew_binary(K.EW_TANH_BWD, dh_tot, c.hc_f32[:, :d], B, d, out_f32=dh_pre)
+    K.ew_binary(K.EW_TANH_BWD, dhU_tot, c.hc_f32[:, d:2 * d], B, d, out_f32=dhU_pre)
+    dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)     # [d, B]
+    dhU_preT = K.cast_bf16_transpose(dhU_pre, with_lo=lo)
+    A1T = _bf16_T(c.A1, B, I, dev)                          # [I, B]
+    A2T = _bf16_T(Bf16Mat(c.A2, None, B, 2 * I), B, 2 * I, dev)
+    emb_table = K.time_bias_table(model.emb_layer.weight.detach(), model.emb_layer.bias.detach(),
+                                  model.in_layers[0].weight.detach(), I, None, T)[1]   # [T, e]
+    emb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
+    temb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
+    K.gather_rows(emb_table, c.ts, B, e, out_f32=emb_rows)
+    K.gather_rows(_temb_table(model, T, dev), c.ts, B, e, out_f32=temb_rows)
+    d_emb = torch.empty(B, e, dtype=torch.float32, device=dev)
+    for name, dpre, dpreT, AT, n_in, first in (("in_layers.0", dh_pre, dh_preT, A1T, I, True),
+                                              ("in_layers2.0", dhU_pre, dhU_preT, A2T, 2 * I, False)):
+        W = P[name + ".weight"]
+        gW = torch.empty_like(W)
+        _mm_auto(model, dpreT, AT, d, n_in, B, out_f32=gW)                                   # columns [0, n_in)
+        K.sgemm_small(dpre, emb_rows, gW[:, n_in:], d, e, B, trans_a=True)                   # time-embedding columns
+        grads[name + ".weight"] = gW
+        grads[name + ".bias"] = K.colsum_f32(dpre, B, d)
+        K.sgemm_small(dpre, W.detach()[:, n_in:], d_emb, B, e, d, beta=0.0 if first else 1.0)
+    gWe = torch.empty_like(P["emb_layer.weight"])
+    K.sgemm_small(d_emb, temb_rows, gWe, e, e, B, trans_a=True)
+    grads["emb_layer.weight"] = gWe
+    grads["emb_layer.bias"] = K.colsum_f32(d_emb, B, e)
+    return grads
+
+
+class _GdmcfTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, diff, x0, B, I, idx32, ts_disc, ts, inject, *params):
+        c = _gdmcf_forward(model, diff, x0, B, I, idx32, ts_disc, ts, inject)
+        ctx.c, ctx.model, ctx.diff = c, model, diff
+        closs = c.closs_rows.mean()
+        ctx.mark_non_differentiable(c.out)
+        return c.mse, closs, c.out
+
+    @staticmethod
+    def backward(ctx, g_mse, g_closs, g_out):
+        grads = _gdmcf_backward(ctx.model, ctx.diff, ctx.c, g_mse, g_closs)
+        ctx.c = None
+        return (None,) * 9 + tuple(grads[n] for n in _GDMCF_PARAMS)
+
+
+# ======================================================================================================
+# DNN backbone
+# ======================================================================================================
+_DNN_PARAMS = ("emb_layer.weight", "emb_layer.bias", "in_layers.0.weight", "in_layers.0.bias", "out_layers.0.weight",
+               "out_layers.0.bias")
+
+
+def _dnn_forward(model: DNN, diff, x0, B, I, ts, inject) -> _Ctx:
+    dev, d, T = x0.device, model.hidden, diff.steps
+    inject = inject or {}
+    p = model.drop.p if model.training else 0.0
+    c = _Ctx()
+    c.B, c.I, c.x0, c.ts = B, I, x0, ts
+    c.A1 = Bf16Mat.empty(B, I, dev, model._lo, zero=False)
+    keep = inject.get("keep_x")
+    K.qsample_dropout(x0, B, I, c.A1, row_t=ts, sqrt_ab=diff._f32["sqrt_alphas_cumprod"],
+                      sqrt_1mab=diff._f32["sqrt_one_minus_alphas_cumprod"], noise=inject.get("noise"),
+                      keep=keep.to(torch.uint8).contiguous() if keep is not None else None, dropout_p=p, seed=diff.seed,
+                      offset=diff._offset())
+    c.h_f32 = torch.empty(B, d, dtype=torch.float32, device=dev)
+    c.h = Bf16Mat.empty(B, d, dev, model._lo)
+    model._encode(c.A1, B, ts, 0, T, c.h, h_f32=c.h_f32)
+    c.out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
+    model._decode(c.h, B, c.out)
+    c.mse = K.mse_rows(c.out, x0, B, I)
+    return c
+
+
+def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
+    B, I, d, dev, T, e = c.B, c.I, model.hidden, c.x0.device, diff.steps, model.time_emb_dim
+    lo = model._lo
+    P = dict(model.named_parameters())
+    grads: Dict[str, torch.Tensor] = {}
+    Bp = K.round_up(B, 64)
+    G = torch.zeros(B, K.round_up(I, 64), dtype=torch.bfloat16, device=dev)
+    GT = torch.empty(I, Bp, dtype=torch.bfloat16, device=dev)
+    colsum = torch.empty(I, dtype=torch.float32, device=dev)
+    K.loss_grad(c.out, c.x0, g_mse.float().contiguous(), B, I, G, GT=GT, with_out=False, colsum=colsum)
+    grads["out_layers.0.bias"] = colsum
+    # d W_out [I, d] = G^T h
+    hT = K.cast_bf16_transpose(c.h_f32, with_lo=lo)  # [d, B]
+    gWo = torch.empty_like(P["out_layers.0.weight"])
+    _mm_auto(model, Bf16Mat(GT, None, I, B), hT, I, d, B, out_f32=gWo)
+    grads["out_layers.0.weight"] = gWo
+    # d h = G W_out  (B operand = W_out^T [d, I])
+    woT = model._weight_operand("out0", model.out_layers[0].weight, transpose=True)
+    dh = torch.empty(B, d, dtype=torch.float32, device=dev)
+    _mm_auto(model, Bf16Mat(G, None, B, I), woT, B, d, I, out_f32=dh)
+    dh_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
+    K.ew_binary(K.EW_TANH_BWD, dh, c.h_f32, B, d, out_f32=dh_pre)
+    dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)
+    A1T = _bf16_T(c.A1, B, I, dev)
+    W = P["in_layers.0.weight"]
+    gW = torch.empty_like(W)
+    _mm_auto(model, dh_preT, A1T, d, I, B, out_f32=gW)
+    emb_table = K.time_bias_table(model.emb_layer.weight.detach(), model.emb_layer.bias.detach(), W.detach(), I, None, T)[1]
+    emb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
+    temb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
+    K.gather_rows(emb_table, c.ts, B, e, out_f32=emb_rows)
+    K.gather_rows(_temb_table(model, T, dev), c.ts, B, e, out_f32=temb_rows)
+    K.sgemm_small(dh_pre, emb_rows, gW[:, I:], d, e, B, trans_a=True)
+    grads["in_layers.0.weight"] = gW
+    grads["in_layers.0.bias"] = K.colsum_f32(dh_pre, B, d)
+    d_emb = torch.empty(B, e, dtype=torch.float32, device=dev)
+    K.sgemm_small(dh_pre, W.detach()[:, I:], d_emb, B, e, d)
+    gWe = torch.empty_like(P["emb_layer.weight"])
+    K.sgemm_small(d_emb, temb_rows, gWe, e, e, B, trans_a=True)
+    grads["emb_layer.weight"] = gWe
+    grads["emb_layer.bias"] = K.colsum_f32(d_emb, B, e)
+    return grads
+
+
+class _DnnTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, diff, x0, B, I, ts, inject, *params):
+        c = _dnn_forward(model, diff, x0, B, I, ts, inject)
+        ctx.c, ctx.model, ctx.diff = c, model, diff
+        ctx.mark_non_differentiable(c.out)
+        return c.mse, c.out
+
+    @staticmethod
+    def backward(ctx, g_mse, g_out):
+        grads = _dnn_backward(ctx.model, ctx.diff, ctx.c, g_mse)
+        ctx.c = None
+        return (None,) * 7 + tuple(grads[n] for n in _DNN_PARAMS)
+
+
+# ======================================================================================================
+# training_losses
+# ======================================================================================================
+def training_losses(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None):
+    """GaussianDiffusionDiscrete.training_losses (models/gaussian_diffusion.py:834-957). Returns {"loss": [B] f64}
+    (+ "model_output", "mse", "closs" for tests). `inject` may carry ts_discrete / ts / noise / u_keep / keep_x /
+    keep_xU to replace the in-kernel Philox draws."""
+    from .models.gaussian_diffusion import CsrBatch
+    inject = inject or {}
+    x0, _, _, users, B, I = diff._dense_start(x_start, want_op=False, lo=False)
+    dev = x0.device
+    if index is None and users is not None:
+        index = users
+    if diff.noise_scale == 0.0:
+        raise NotImplementedError("noise_scale == 0 (no diffusion) is outside the hot path")
+    gdmcf = isinstance(model, DNNOneHotEmbeddingGCN)
+    if not gdmcf and not isinstance(model, DNN):
+        raise TypeError("training_losses needs a gdmcf_b200 denoiser (DNN / DNNOneHotEmbeddingGCN)")
+    if gdmcf != bool(diff.CatOneHot and diff.indexIn):
+        raise ValueError("diffusion flags (CatOneHot/indexIn) do not match the backbone")
+    # two timestep draws like the reference (:845 shapes the discrete noise, :865 feeds the model and the weights)
+    if gdmcf:
+        ts_disc = inject["ts_discrete"] if "ts_discrete" in inject else diff.sample_timesteps(B, dev, "importance")[0]
+    if "ts" in inject:
+        ts = inject["ts"].to(dev).long()
+        pt = diff._pt_for(ts)
+    else:
+        ts, pt = diff.sample_timesteps(B, dev, "importance")
+    ts32 = ts.to(torch.int32)
+    if gdmcf:
+        assert index is not None, "DNNOneHotEmbeddingGCN needs the user index of every row"
+        idx32 = index.to(dev).to(torch.int32)
+        params = dict(model.named_parameters())
+        mse, closs, out = _GdmcfTrainFn.apply(model, diff, x0, B, I, idx32, ts_disc.to(dev).to(torch.int32), ts32, inject,
+                                              *[params[n] for n in _GDMCF_PARAMS])
+    else:
+        params = dict(model.named_parameters())
+        mse, out = _DnnTrainFn.apply(model, diff, x0, B, I, ts32, inject, *[params[n] for n in _DNN_PARAMS])
+        closs = None
+    terms = {}
+    if reweight:
+        weight = diff.SNR(ts - 1) - diff.SNR(ts)
+        weight = torch.where((ts == 0), 1.0, weight)
+    else:
+        weight = torch.ones(B, device=dev)
+    terms["loss"] = weight * mse
+    diff._update_history(ts, terms["loss"])
+    terms["loss"] = terms["loss"] / pt
+    if closs is not None:
+        terms["loss"] = terms["loss"] + closs * 0.1
+    terms["model_output"], terms["mse"], terms["closs"] = out.detach()[:, :I], mse.detach(), closs.detach() if closs is not None else None
+    return terms

@@ -93,12 +93,16 @@ typedef struct {
   int32_t m, n;
 } gdmcf_gemm_desc;
 
-#define GDMCF_EPI_STORE 0    /* out = alpha*acc                                         */
-#define GDMCF_EPI_BIAS_ACT 1 /* out = act(alpha*acc + bias[t(m)*ld_bias + n])            */
-#define GDMCF_EPI_COSINE 2   /* s = alpha*acc*row_scale[m]*col_scale[n];
-                                out = c1 ? c1[t(m)]*s + c2[t(m)]*xt[m,n] : s
-                                (cosine scorer DNN.py:1304-1327 + posterior mean
-                                 gaussian_diffusion.py:1041-1050)                        */
+/* Fused epilogue, one formula (absent pointers drop their factor/term):
+ *   s   = act(alpha * acc * row_scale[m] * col_scale[n] + bias[t(m)*ld_bias + n])
+ *   out = c1 ? c1[t(m)] * s + c2[t(m)] * xt[m,n] : s            t(m) = row_t ? row_t[m] : t_const
+ * - bias + tanh/relu: nn.Linear + activation (models/DNN.py:79-86, :1240-1252, GCNConv bias :1082-1100);
+ * - row_scale/col_scale: the cosine scorer's 1/(|u| |e_i|) (models/DNN.py:1304-1327);
+ * - c1/c2/xt: posterior mean coef1*pred_xstart + coef2*x_t (models/gaussian_diffusion.py:1041-1050).
+ * `mode` is informational (kept for ABI stability): */
+#define GDMCF_EPI_STORE 0
+#define GDMCF_EPI_BIAS_ACT 1
+#define GDMCF_EPI_COSINE 2
 #define GDMCF_ACT_NONE 0
 #define GDMCF_ACT_TANH 1
 #define GDMCF_ACT_RELU 2
@@ -178,6 +182,26 @@ int gdmcf_encode_onehot_gather(const int32_t* rowptr, const int32_t* col, const 
 int gdmcf_onehot_tables(const float* w2, int64_t ld_w, int d, int n_items, float* base, float* delta,
                         int64_t ld_delta, gdmcf_stream_t stream);
 
+/* Per-timestep first-layer bias (the `cat([x, emb])` columns, models/DNN.py:72-80, :1227-1241): for every
+ * t < T: emb_table[t,:] = emb_layer(timestep_embedding(t, e)) and out[t,k] = b[k] + sum_j w_time[k,j]*emb_table[t,j],
+ * where w_time = &W[0, n_in] (the last e columns of the layer's weight, leading dim ld_w). b may be NULL. */
+int gdmcf_time_bias_table(const float* w_emb, const float* b_emb, const float* w_time, int64_t ld_w,
+                          const float* b, int T, int e, int d, float* emb_table, float* out, int64_t ld_out,
+                          gdmcf_stream_t stream);
+/* out[r,c] = act(in[r,c] + bias[t(r)*ld_bias + c]) as fp32 and/or bf16 hi(+lo). */
+int gdmcf_bias_act_rows(const float* in, int64_t ld_in, const float* bias, int64_t ld_bias, const int32_t* row_t,
+                        int t_const, int act, float* out_f32, int64_t ld_of, void* out_bf16, void* out_lo,
+                        int64_t ld_ob, int rows, int cols, gdmcf_stream_t stream);
+/* out[r,:] = table[idx[r],:] (nn.Embedding lookup, models/DNN.py:1265) as fp32 and/or bf16 hi(+lo). */
+int gdmcf_gather_rows(const float* table, int64_t ld_t, const int32_t* idx, float* out_f32, int64_t ld_of,
+                      void* out_bf16, void* out_lo, int64_t ld_ob, int rows, int cols, gdmcf_stream_t stream);
+/* Small fp32 CUDA-core GEMM for the tiny contractions (time-embedding columns, nt_xent logits):
+ * C = alpha * op(A) op(B) + beta * C; trans_a: A stored [k,m]; trans_b: B stored [n,k]. */
+int gdmcf_sgemm_small(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b, float* C,
+                      int64_t ldc, int m, int n, int k, float alpha, float beta, gdmcf_stream_t stream);
+/* out[c] = sum_r x[r,c] in row order (bias gradients). */
+int gdmcf_colsum_f32(const float* x, int64_t ld, int rows, int cols, float* out, gdmcf_stream_t stream);
+
 /* Row-wise finish of the user tower (models/DNN.py:1288, :1320-1321):
  * hc'[r,:] = sumW*hc[r,:] + (1-sumW)*g[r,:]; inv_norm[r] = 1/||hc'[r,:]||_2; hc' written as bf16
  * hi (+ optional lo) for the scorer GEMM and optionally as fp32. g may be NULL (sumW treated as 1). */
@@ -228,6 +252,37 @@ int gdmcf_mse_rows(const float* out, int64_t ld_out, const float* x0, int64_t ld
 int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int step, float grad_scale,
                       gdmcf_stream_t stream);
+
+/* Backward of the weighted MSE (models/gaussian_diffusion.py:902,932,951) in one pass over out [rows, cols]:
+ *   g[b,i] = gs[b] * 2*(out[b,i] - x0[b,i]) / cols          (gs[b] = dL/dloss[b] * weight[b] / pt[b])
+ *   g_bf16[b,i]  = bf16(g * row_scale[b] * col_scale[i])     A operand of the dgrad contraction
+ *   gt_bf16[i,b] = its transpose (optional)                  A operand of the wgrad contraction
+ *   colsum[i]      = sum_b (with_out ? g*out : g)            (optional)
+ *   rowpart[cb, b] = the same quantity summed over the 32 columns of block cb (optional; [ceil(cols/32), rows]);
+ * with_out = 1 yields the sums the cosine scorer's norm terms need (models/DNN.py:1320-1325). */
+int gdmcf_loss_grad(const float* out, int64_t ld_out, const float* x0, int64_t ld_x0, const float* gs,
+                    const float* row_scale, const float* col_scale, int with_out, void* g_bf16, int64_t ld_g,
+                    void* gt_bf16, int64_t ld_gt, float* colsum, float* rowpart, int rows, int cols,
+                    gdmcf_stream_t stream);
+/* bf16 [rows, cols] -> bf16 [cols, rows] (wgrad operands need the batch dimension contiguous). */
+int gdmcf_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols,
+                         gdmcf_stream_t stream);
+/* out = op(a, b): 0: a*(b>0) (relu backward)  1: a*(1-b*b) (tanh backward)  2: alpha*a + beta*b. */
+int gdmcf_ew_binary(int op, const float* a, int64_t ld_a, const float* b, int64_t ld_b, float alpha, float beta,
+                    float* out_f32, int64_t ld_of, void* out_bf16, void* out_lo, int64_t ld_ob, int rows, int cols,
+                    gdmcf_stream_t stream);
+/* Backward of hc' = sumW*hc + (1-sumW)*g2 (models/DNN.py:1288): d_hc = sumW*d, d_g2 = (1-sumW)*d,
+ * dw_rows[r] = sum_c d[r,c]*(hc[r,c]-g2[r,c]). */
+int gdmcf_mix_backward(const float* d_hcp, int64_t ld_d, const float* hc, int64_t ld_hc, const float* g2,
+                       int64_t ld_g, const float* sumw, float* d_hc, int64_t ld_dh, float* d_g2, int64_t ld_dg,
+                       float* dw_rows, int rows, int cols, gdmcf_stream_t stream);
+/* nt_xent_loss rows (models/DNN.py:479-508) from the raw logits S = h h_U^T [n,n]: loss_rows[i] =
+ * -log((p_ii+eps)/sum_{j!=i} p_ij) with p = softmax(S/tau) (closs = mean(loss_rows)); dS = dscale[0] * d closs/dS. */
+int gdmcf_ntxent_rows(const float* S, int64_t ld_s, int n, float tau, float eps, const float* dscale,
+                      float* loss_rows, float* dS, int64_t ld_ds, gdmcf_stream_t stream);
+/* grad[idx[r],:] += v[r,:] (dense nn.Embedding gradient rows, models/DNN.py:1265). */
+int gdmcf_scatter_rows_add(const float* v, int64_t ld_v, const int32_t* idx, float* grad, int64_t ld_g, int rows,
+                           int cols, gdmcf_stream_t stream);
 
 #ifdef __cplusplus
 }
