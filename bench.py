@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — users/sec through GDMCF's train + denoise + rank hot path (BASELINE.json metric) on B200.
+
+  python bench.py --gpus N --steps K --warmup W                 engine arm (this repo's CUDA path)
+  python bench.py --impl reference --gpus N --steps K --warmup W  reference arm: the CPU restatement of the
+                                                                  reference path (oracle/, kind "port") on host cores
+
+Workload (config.workload): synthetic Yelp-shape interactions (54 574 users x 34 395 items, 1 402 736 pairs, 7:1:2
+split), GDMCF backbone DNNOneHotEmbeddingGCN dims=[1000] steps=5 noise_scale=0.01 batch_size=400, reweight, lr=1e-5.
+One step = one logical batch of 400 users per GPU through (a) a full training step (training_losses -> backward ->
+AdamW, + gradient all-reduce when N > 1) and (b) denoise + rank (p_sample over 5 reverse steps -> history mask ->
+top-20 -> Recall/NDCG sums). value = N*400*K / max-over-ranks CUDA-event time with inputs resident in HBM;
+e2e = the same through the public API with the step's inputs in pinned host memory and results read back.
+Model weights + optimizer state (~4 GB) dwarf the 126 MB L2, so no explicit L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # name: (n_user, n_item, n_pairs, seed)
+    "yelp": (54574, 34395, 1402736, 0),
+    "amazon": (108822, 94949, 3146256, 1),
+    "tiny": (2000, 1500, 40000, 3),
+}
+METRIC = "users/sec train+denoise+rank (Yelp shape)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="yelp", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=400)
+    ap.add_argument("--dims", type=int, default=1000)
+    ap.add_argument("--diff_steps", type=int, default=5)
+    ap.add_argument("--topk", type=int, default=20)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--cpu_sample_users", type=int, default=200)
+    return ap.parse_args()
+
+
+def config_of(args, n_gpus):
+    U, I, P, _ = WORKLOADS[args.workload]
+    return {"workload": f"{args.workload}-shape synthetic GDMCF train+denoise+rank", "n_user": U, "n_item": I,
+            "interactions": P, "backbone": "DNNOneHotEmbeddingGCN", "dims": [args.dims], "steps": args.diff_steps,
+            "noise_scale": 0.01, "batch_size": args.batch, "top_k": args.topk, "users_per_step": args.batch * n_gpus,
+            "parallelism": f"dp{n_gpus} (user batches; grad all-reduce)", "l2": "inputs larger than L2 (weights+state ~4 GB)",
+            "precision": args.precision}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the benchmark runs (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc, self.t0, self.t1 = [], None, None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append((time.time(), parts))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        win = [p for (t, p) in self.samples if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30)]
+        use = win if len(win) >= 3 else [p for _, p in self.samples]
+        sm = sorted(int(p[0]) for p in use if p[0].isdigit())
+        mx = [int(p[1]) for p in use if p[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for p in use for i in range(4) if p[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(use), "in_timed_region": len(win)}
+
+
+# ======================================================================================================
+# CPU arm (oracle/ restatement of the reference path) — used for cpu_baseline and --impl reference
+# ======================================================================================================
+class CpuArm:
+    def __init__(self, args, state_dict=None):
+        import numpy as np
+        import torch
+        from gdmcf_b200 import data_utils
+        from oracle import gdmcf_oracle as O
+        self.torch, self.np, self.O = torch, np, O
+        self.cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(self.cores)
+        U, I, P, seed = WORKLOADS[args.workload]
+        tr, va, te = data_utils.synthetic_interactions(U, I, P, seed)
+        import scipy.sparse as sp
+        self.n_user, self.n_item = int(tr[:, 0].max()) + 1, int(tr[:, 1].max()) + 1
+        mk = lambda p: sp.csr_matrix((np.ones(len(p), dtype=np.float32), (p[:, 0], p[:, 1])), shape=(self.n_user, self.n_item))  # noqa: E731
+        self.train, self.test = mk(tr), mk(te)
+        torch.manual_seed(0)
+        self.model = O.OracleGDMCF([self.n_item, args.dims], [args.dims, self.n_item], 10, item_num=self.n_item, user_num=self.n_user)
+        if state_dict is not None:
+            self.model.load_state_dict(state_dict)
+        self.diff = O.OracleDiffusion(steps=args.diff_steps, noise_scale=0.01)
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=1e-5, weight_decay=0.0)
+        self.args = args
+        self.cursor = 0
+
+    def step(self, n_users):
+        """Train + denoise + rank on the next n_users users; returns seconds."""
+        torch, np, O, a = self.torch, self.np, self.O, self.args
+        users = np.arange(self.cursor, self.cursor + n_users) % self.n_user
+        self.cursor += n_users
+        x0 = torch.from_numpy(np.asarray(self.train[users].todense(), dtype=np.float32))
+        index = torch.from_numpy(users).long()
+        T = a.diff_steps
+        t0 = time.perf_counter()
+        self.model.train()
+        ts1, ts = torch.randint(0, T, (n_users,)), torch.randint(0, T, (n_users,))
+        noise, u_keep = torch.randn_like(x0), torch.rand_like(x0)
+        kx, kxu = torch.rand_like(x0) >= 0.5, torch.rand(n_users, 2 * self.n_item) >= 0.5
+        self.opt.zero_grad()
+        terms = self.diff.training_losses(self.model, x0, index, ts1, ts, noise, u_keep, kx, kxu, reweight=True)
+        terms["loss"].mean().backward()
+        self.opt.step()
+        self.model.eval()
+        with torch.no_grad():
+            pred = self.diff.p_sample(self.model, x0, 0, index=index)
+            hist = [self.train.indices[self.train.indptr[u]:self.train.indptr[u + 1]] for u in users]
+            _, idx = O.mask_topk(pred, hist, a.topk)
+        target = [self.test.indices[self.test.indptr[u]:self.test.indptr[u + 1]].tolist() for u in users]
+        O.computeTopNAccuracy(target, idx.tolist(), [10, a.topk] if a.topk > 10 else [a.topk])
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # only rank 0 runs the CPU arm
+    arm = CpuArm(args)
+    t_cal = arm.step(16)  # calibration (also first-touch of the weights)
+    rate = 16 / t_cal
+    total = args.steps + args.warmup
+    n = int(max(8, min(args.batch, 150.0 * rate / max(total, 1))))
+    for _ in range(args.warmup):
+        arm.step(n)
+    t = sum(arm.step(n) for _ in range(args.steps))
+    value = n * args.steps / t
+    sample = f"{n} users per step x {args.steps} steps (1 train step + {args.diff_steps}-step p_sample + mask + top-{args.topk} + metrics)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "users/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(args, 1),
+            "cpu_baseline": {"value": value, "unit": "users/s", "cores": arm.cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================
+# engine arm
+# ======================================================================================================
+def run_engine(args):
+    import numpy as np
+    import scipy.sparse as sp
+    import torch
+    from gdmcf_b200 import _lib, data_utils, dist_utils, evaluate_utils
+    from gdmcf_b200 import kernels as K
+    from gdmcf_b200.lightGCN import LightGCN
+    from gdmcf_b200.models import gaussian_diffusion as gd
+    from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    from gdmcf_b200.optim import FusedAdamW
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (engine arm) needs a CUDA device; there is no CPU fallback")
+    dist = dist_utils.init("nccl")
+    G, rank = dist.world_size, dist.rank
+    assert G == max(args.gpus, 1) or G == 1, f"--gpus {args.gpus} but WORLD_SIZE={G}"
+    dev = torch.device(f"cuda:{dist.local_rank}")
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    _lib.check(lib.gdmcf_device_check(), "device_check")
+    sampler = ClockSampler(dist.local_rank) if rank == 0 else None
+
+    U, I, P, seed = WORKLOADS[args.workload]
+    tr, va, te = data_utils.synthetic_interactions(U, I, P, seed)
+    n_user, n_item = int(tr[:, 0].max()) + 1, int(tr[:, 1].max()) + 1
+    mk = lambda p: sp.csr_matrix((np.ones(len(p), dtype=np.float32), (p[:, 0], p[:, 1])), shape=(n_user, n_item))  # noqa: E731
+    train_sp, test_sp = mk(tr), mk(te)
+    train_dev = data_utils.DeviceInteractions(train_sp, dev)
+    test_dev = data_utils.DeviceInteractions(test_sp, dev)
+    B, k, T = args.batch, args.topk, args.diff_steps
+    topN = [10, k] if k > 10 else [k]
+
+    torch.manual_seed(0)
+    diffusion = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, T, dev,
+                                             discrete=0.9995, CatOneHot=True)
+    diffusion.indexIn = True
+    model = DNNOneHotEmbeddingGCN([n_item, args.dims], [args.dims, n_item], 10, item_num=n_item, user_num=n_user,
+                                  precision=args.precision).to(dev)
+    dist.broadcast_parameters(model)
+    diffusion.seed = model.seed = 1234 + rank
+    opt = FusedAdamW(model.parameters(), lr=1e-5, weight_decay=0.0, modules=[model])
+    n_batches = n_user // B
+
+    def users_of(step):
+        b = (step * G + rank) % n_batches
+        return b * B, (b + 1) * B
+
+    def one_step(batch, users_global, hist, gt):
+        model.train()
+        opt.zero_grad()
+        losses = diffusion.training_losses(model, batch, True, index=users_global)
+        loss = losses["loss"].mean()
+        loss.backward()
+        dist.all_reduce_gradients(model)
+        opt.step(grad_scale=1.0 / G)
+        model.eval()
+        idx = diffusion.rank(model, batch, k, hist=hist, index=users_global)
+        sums = evaluate_utils.metrics_from_device(idx, batch.users, gt[0], gt[1], topN)
+        return loss.detach(), idx, sums
+
+    def resident_step(step):
+        lo, hi = users_of(step)
+        users = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+        return one_step(train_dev.batch(users), users, train_dev.csr, test_dev.csr)
+
+    # ---- e2e inputs: the step's rows in pinned host memory (CSR of train rows + ground-truth rows + user ids)
+    def host_batch(step):
+        lo, hi = users_of(step)
+        out = {}
+        for name, m in (("tr", train_sp), ("te", test_sp)):
+            rp = (m.indptr[lo:hi + 1] - m.indptr[lo]).astype(np.int32)
+            cl = m.indices[m.indptr[lo]:m.indptr[hi]].astype(np.int32)
+            if cl.size == 0:
+                cl = np.zeros(1, np.int32)
+            out[name] = (torch.from_numpy(rp).pin_memory(), torch.from_numpy(cl).pin_memory())
+        out["users"] = torch.arange(lo, hi, dtype=torch.int32).pin_memory()
+        return out
+
+    local_ids = torch.arange(B, dtype=torch.int32, device=dev)
+
+    def e2e_step(hb):
+        nb = lambda t: t.to(dev, non_blocking=True)  # noqa: E731
+        tr_rp, tr_cl, te_rp, te_cl, users = nb(hb["tr"][0]), nb(hb["tr"][1]), nb(hb["te"][0]), nb(hb["te"][1]), nb(hb["users"])
+        batch = gd.CsrBatch(tr_rp, tr_cl, local_ids, n_item)
+        loss, idx, sums = one_step(batch, users, (tr_rp, tr_cl), (te_rp, te_cl))
+        return loss.cpu(), idx.cpu(), sums.cpu()  # device -> host read of the step's results
+
+    def timed(fn, n_warm, n_steps, offset=0):
+        for s in range(n_warm):
+            fn(offset + s)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.gdmcf_launch_count()
+        t_wall0 = time.time()
+        e0.record()
+        for s in range(n_steps):
+            fn(offset + n_warm + s)
+        e1.record()
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if G > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item(), lib.gdmcf_launch_count() - launches0, (t_wall0, t_wall1)
+
+    Kst, W = args.steps, max(args.warmup, 3)
+    ms, launches, window = timed(resident_step, W, Kst)
+    if sampler is not None:
+        sampler.t0, sampler.t1 = window
+    value = G * B * Kst / (ms * 1e-3)
+
+    hbs = [host_batch(W + Kst + s) for s in range(W + Kst)]
+    ms_e2e, _, _ = timed(lambda s: e2e_step(hbs[s]), W, Kst)
+    e2e_value = G * B * Kst / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for key in ("tr", "te") for t in hbs[W][key]) + hbs[W]["users"].numel() * 4
+    d2h = 8 + B * k * 4 + len(topN) * 4 * 8
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch of a few more steps
+    records = []
+    orig_gemm = K.gemm
+
+    def timed_gemm(a, b, m, n, ks, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_gemm(a, b, m, n, ks, **kw)
+        e1.record()
+        records.append((e0, e1, 2.0 * m * n * float(sum(ks))))
+
+    K.gemm = timed_gemm
+    n_prof = 3
+    for s in range(n_prof):
+        resident_step(2 * (W + Kst) + s)
+    torch.cuda.synchronize()
+    K.gemm = orig_gemm
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
+    gemm_flops = sum(f for _, _, f in records)
+    pk = peaks()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (+ splitk_reduce_kernel)", "achieved": achieved,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak_source": f"{pk['src']} (sustained bf16)", "launches_per_step": len(records) / n_prof,
+                "gemm_ms_per_step": gemm_ms / n_prof, "gemm_share_of_step": (gemm_ms / n_prof) / (ms / Kst),
+                "flops_per_step": gemm_flops / n_prof}
+
+    # ---- SpMM (lightGCN propagation, K=3, d=64) on the same interaction graph, HBM roofline
+    spmm = None
+    if rank == 0:
+        lg = LightGCN({"user_id_idx": tr[:, 0], "item_id_idx": tr[:, 1]}, n_user, n_item, 3, 64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        _, col, val = lg.norm_adj_csr
+        E0 = lg.E0.weight.detach()
+        out = torch.empty_like(E0)
+        work = (torch.empty_like(E0), torch.empty_like(E0), torch.empty(max(lg.plan.n_slots, 1), 64, device=dev))
+        ts = []
+        for it in range(13):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            K.lightgcn_propagate(lg.plan, col, val, E0, 3, out=out, work=work)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ts.append(e0.elapsed_time(e1))
+        N, nnz = n_user + n_item, col.numel()
+        bytes_alg = 3 * (nnz * 8 + (N + 1) * 4 + 2 * N * 64 * 4)
+        t_med = sorted(ts)[len(ts) // 2]
+        gbs = bytes_alg / (t_med * 1e-3) / 1e9
+        spmm = {"bound": "hbm", "kernel": "spmm_items_kernel x3 (lightgcn_propagate, K=3, d=64, fp32)", "achieved": gbs,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "ms": t_med, "algorithmic_bytes": bytes_alg,
+                "N": N, "nnz": nnz, "l2": "flushed between iterations (256 MiB write)"}
+        del lg, flush
+
+    clocks = sampler.stop() if sampler is not None else None
+
+    cpu = None
+    if rank == 0 and G == 1 and not args.no_cpu_baseline:
+        sd = {kk: v.detach().cpu() for kk, v in model.state_dict().items()}
+        arm = CpuArm(args, sd)
+        n = args.cpu_sample_users
+        arm.step(8)  # first-touch
+        t = arm.step(n)
+        cpu = {"value": n / t, "unit": "users/s", "cores": arm.cores, "kind": "port",
+               "sample": f"{n} users: 1 train step (fwd+bwd+AdamW) + {T}-step p_sample + mask + top-{k} + metrics, {t:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "users/s", "n_gpus": G, "steps": Kst, "warmup": W,
+                "ms_per_step": ms / Kst, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-mode)", "data": "synthetic",
+                "config": config_of(args, G), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": ms_e2e / Kst},
+                "gpu_launches": int(launches), "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    dist.shutdown()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)

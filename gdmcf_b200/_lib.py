@@ -66,6 +66,7 @@ SIGNATURES = {
     "gdmcf_abi_version": (_I, []),
     "gdmcf_device_check": (_I, []),
     "gdmcf_num_sms": (_I, []),
+    "gdmcf_launch_count": (C.c_ulonglong, []),
     "gdmcf_spmm_plan": (_I, [_P, _I, _I, _P, _I, _P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "gdmcf_spmm_csr_f32": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _F, _F, _P]),
     "gdmcf_lightgcn_propagate_f32": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
@@ -92,7 +93,7 @@ SIGNATURES = {
     "gdmcf_colsum_f64": (_I, [_P, _I, _I, _P, _P]),
     "gdmcf_mse_rows": (_I, [_P, _L, _P, _L, _I, _I, _P, _P]),
     "gdmcf_adamw_fused": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
-    "gdmcf_loss_grad": (_I, [_P, _L, _P, _L, _P, _P, _P, _I, _P, _L, _P, _L, _P, _P, _I, _I, _P]),
+    "gdmcf_loss_grad": (_I, [_P, _L, _P, _L, _P, _P, _P, _I, _P, _P, _L, _P, _P, _L, _P, _P, _I, _I, _P]),
     "gdmcf_transpose_bf16": (_I, [_P, _L, _P, _L, _I, _I, _P]),
     "gdmcf_ew_binary": (_I, [_I, _P, _L, _P, _L, _F, _F, _P, _L, _P, _P, _L, _I, _I, _P]),
     "gdmcf_mix_backward": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _I, _I, _P]),

@@ -17,7 +17,10 @@ int cuda_fail(cudaError_t err, const char* what) {
   return GDMCF_ECUDA;
 }
 
+static unsigned long long g_launches = 0;
+
 int cuda_check_launch(const char* kernel) {
+  ++g_launches;  // every kernel launch of the library is followed by exactly one cuda_check_launch
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cuda_fail(err, kernel);
   return GDMCF_OK;
@@ -26,6 +29,8 @@ int cuda_check_launch(const char* kernel) {
 }  // namespace gd
 
 extern "C" const char* gdmcf_last_error(void) { return gd::g_err; }
+
+extern "C" unsigned long long gdmcf_launch_count(void) { return gd::g_launches; }
 
 extern "C" int gdmcf_abi_version(void) { return GDMCF_ABI_VERSION; }
 

@@ -33,7 +33,8 @@ GD_DEV void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
 __global__ void __launch_bounds__(256)
 loss_grad_kernel(const float* __restrict__ out, long long ld_out, const float* __restrict__ x0, long long ld_x0,
                  const float* __restrict__ gs, const float* __restrict__ rs, const float* __restrict__ cs, int with_out,
-                 __nv_bfloat16* __restrict__ G, long long ld_g, __nv_bfloat16* __restrict__ GT, long long ld_gt,
+                 __nv_bfloat16* __restrict__ G, __nv_bfloat16* __restrict__ G_lo, long long ld_g,
+                 __nv_bfloat16* __restrict__ GT, __nv_bfloat16* __restrict__ GT_lo, long long ld_gt,
                  float* __restrict__ colsum, float* __restrict__ rowpart, int B, int I) {
   __shared__ float tile[32][33];
   __shared__ float colred[8][32];
@@ -54,7 +55,10 @@ loss_grad_kernel(const float* __restrict__ out, long long ld_out, const float* _
           const float g = gs[r] * ((o - x0[(long long)r * ld_x0 + c]) * inv_i2);
           red = with_out ? g * o : g;
           gsv = g * (rs ? rs[r] : 1.0f) * csc;
-          G[(long long)r * ld_g + c] = __float2bfloat16_rn(gsv);
+          __nv_bfloat16 hi, lo;
+          split_bf16(gsv, hi, lo);
+          G[(long long)r * ld_g + c] = hi;
+          if (G_lo) G_lo[(long long)r * ld_g + c] = lo;
         }
         colacc += red;
         const float rsum = warp_sum(red);
@@ -66,7 +70,12 @@ loss_grad_kernel(const float* __restrict__ out, long long ld_out, const float* _
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int cc = cb * 32 + ty + 8 * q, rr = r0 + tx;
-          if (cc < I && rr < B) GT[(long long)cc * ld_gt + rr] = __float2bfloat16_rn(tile[tx][ty + 8 * q]);
+          if (cc < I && rr < B) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(tile[tx][ty + 8 * q], hi, lo);
+            GT[(long long)cc * ld_gt + rr] = hi;
+            if (GT_lo) GT_lo[(long long)cc * ld_gt + rr] = lo;
+          }
         }
       }
       __syncthreads();
@@ -231,18 +240,19 @@ using namespace gd::train;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" int gdmcf_loss_grad(const float* out, int64_t ld_out, const float* x0, int64_t ld_x0, const float* gs,
-                               const float* row_scale, const float* col_scale, int with_out, void* g_bf16, int64_t ld_g,
-                               void* gt_bf16, int64_t ld_gt, float* colsum, float* rowpart, int rows, int cols,
-                               gdmcf_stream_t stream) {
+                               const float* row_scale, const float* col_scale, int with_out, void* g_bf16, void* g_lo,
+                               int64_t ld_g, void* gt_bf16, void* gt_lo, int64_t ld_gt, float* colsum, float* rowpart,
+                               int rows, int cols, gdmcf_stream_t stream) {
   if (!out || !x0 || !gs || !g_bf16 || rows <= 0 || cols <= 0 || ld_out < cols || ld_x0 < cols || ld_g < cols ||
-      (gt_bf16 && ld_gt < rows)) {
+      (gt_bf16 && ld_gt < rows) || (gt_lo && !gt_bf16)) {
     set_error("loss_grad: bad arguments");
     return GDMCF_EBADARG;
   }
   GD_PRE();
   const int n_cb = (cols + 31) / 32;
   loss_grad_kernel<<<std::min(n_cb, sm_count() * 8), 256, 0, st>>>(out, ld_out, x0, ld_x0, gs, row_scale, col_scale, with_out,
-                                                                   (__nv_bfloat16*)g_bf16, ld_g, (__nv_bfloat16*)gt_bf16, ld_gt,
+                                                                   (__nv_bfloat16*)g_bf16, (__nv_bfloat16*)g_lo, ld_g,
+                                                                   (__nv_bfloat16*)gt_bf16, (__nv_bfloat16*)gt_lo, ld_gt,
                                                                    colsum, rowpart, rows, cols);
   return cuda_check_launch("loss_grad_kernel");
 }

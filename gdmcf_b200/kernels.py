@@ -374,11 +374,12 @@ def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.9
                                    grad_scale, stream()), "adamw_fused")
 
 
-def loss_grad(out, x0, gs, rows: int, cols: int, G: torch.Tensor, *, GT=None, row_scale=None, col_scale=None,
-              with_out: bool = False, colsum=None, rowpart=None) -> None:
-    require_cuda(out, x0, gs, G, GT, row_scale, col_scale, colsum, rowpart)
+def loss_grad(out, x0, gs, rows: int, cols: int, G: Bf16Mat, *, GT: Optional[Bf16Mat] = None, row_scale=None,
+              col_scale=None, with_out: bool = False, colsum=None, rowpart=None) -> None:
+    require_cuda(out, x0, gs, G.hi, row_scale, col_scale, colsum, rowpart)
     check(load().gdmcf_loss_grad(ptr(out), out.stride(0), ptr(x0), x0.stride(0), ptr(gs), ptr(row_scale), ptr(col_scale),
-                                 int(with_out), ptr(G), G.stride(0), ptr(GT), GT.stride(0) if GT is not None else 0,
+                                 int(with_out), ptr(G.hi), ptr(G.lo), G.ld, ptr(GT.hi) if GT is not None else None,
+                                 ptr(GT.lo) if GT is not None else None, GT.ld if GT is not None else 0,
                                  ptr(colsum), ptr(rowpart), rows, cols, stream()), "loss_grad")
 
 

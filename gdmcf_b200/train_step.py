@@ -137,8 +137,8 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
     ones1 = _ones(model, 1, dev)
     Bp = K.round_up(B, 64)
     # ---- dL/d out, fused with operand production and the norm-term reductions
-    Gs = torch.zeros(B, K.round_up(I, 64), dtype=torch.bfloat16, device=dev)
-    GsT = torch.empty(I, Bp, dtype=torch.bfloat16, device=dev)
+    Gs = Bf16Mat.empty(B, I, dev, lo, zero=True)
+    GsT = Bf16Mat.empty(I, B, dev, lo, zero=False)
     n_cb = (I + 31) // 32
     colsum = torch.empty(I, dtype=torch.float32, device=dev)
     rowpart = torch.empty(n_cb, B, dtype=torch.float32, device=dev)
@@ -149,13 +149,13 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
     eT = model._weight_operand("E", model.embedding_item.weight, transpose=True)  # [3d, I]
     d_hcp = torch.empty(B, d3, dtype=torch.float32, device=dev)
     coef_u = -(c.inv_u * c.inv_u) * r_b
-    _mm_auto(model, Bf16Mat(Gs, None, B, I), eT, B, d3, I, out_f32=d_hcp, row_t=_arange32(model, B, dev),
+    _mm_auto(model, Gs, eT, B, d3, I, out_f32=d_hcp, row_t=_arange32(model, B, dev),
              c1=_ones(model, B, dev), c2=coef_u, xt=c.hcp_f32)
     # ---- d E = Gs^T hc' - E * ri^2 * c_i   (written straight into the parameter's gradient)
     hcpT = K.cast_bf16_transpose(c.hcp_f32, with_lo=lo)  # [3d, B]
     gE = torch.empty_like(P["embedding_item.weight"])
     coef_i = -(c.inv_i * c.inv_i) * colsum
-    _mm_auto(model, Bf16Mat(GsT, None, I, B), hcpT, I, d3, B, out_f32=gE, row_t=_arange32(model, I, dev),
+    _mm_auto(model, GsT, hcpT, I, d3, B, out_f32=gE, row_t=_arange32(model, I, dev),
              c1=_ones(model, I, dev), c2=coef_i, xt=P["embedding_item.weight"].detach())
     grads["embedding_item.weight"] = gE
     # ---- sumW mix backward
@@ -285,20 +285,20 @@ def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
     P = dict(model.named_parameters())
     grads: Dict[str, torch.Tensor] = {}
     Bp = K.round_up(B, 64)
-    G = torch.zeros(B, K.round_up(I, 64), dtype=torch.bfloat16, device=dev)
-    GT = torch.empty(I, Bp, dtype=torch.bfloat16, device=dev)
+    G = Bf16Mat.empty(B, I, dev, lo, zero=True)
+    GT = Bf16Mat.empty(I, B, dev, lo, zero=False)
     colsum = torch.empty(I, dtype=torch.float32, device=dev)
     K.loss_grad(c.out, c.x0, g_mse.float().contiguous(), B, I, G, GT=GT, with_out=False, colsum=colsum)
     grads["out_layers.0.bias"] = colsum
     # d W_out [I, d] = G^T h
     hT = K.cast_bf16_transpose(c.h_f32, with_lo=lo)  # [d, B]
     gWo = torch.empty_like(P["out_layers.0.weight"])
-    _mm_auto(model, Bf16Mat(GT, None, I, B), hT, I, d, B, out_f32=gWo)
+    _mm_auto(model, GT, hT, I, d, B, out_f32=gWo)
     grads["out_layers.0.weight"] = gWo
     # d h = G W_out  (B operand = W_out^T [d, I])
     woT = model._weight_operand("out0", model.out_layers[0].weight, transpose=True)
     dh = torch.empty(B, d, dtype=torch.float32, device=dev)
-    _mm_auto(model, Bf16Mat(G, None, B, I), woT, B, d, I, out_f32=dh)
+    _mm_auto(model, G, woT, B, d, I, out_f32=dh)
     dh_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
     K.ew_binary(K.EW_TANH_BWD, dh, c.h_f32, B, d, out_f32=dh_pre)
     dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)

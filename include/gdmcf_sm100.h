@@ -39,6 +39,8 @@ int gdmcf_abi_version(void);
 /* 0 if the current device is compute capability 10.x, GDMCF_EARCH otherwise. */
 int gdmcf_device_check(void);
 int gdmcf_num_sms(void);
+/* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+unsigned long long gdmcf_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K1 — normalized-adjacency propagation (CSR SpMM).
@@ -257,13 +259,14 @@ int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, f
  *   g[b,i] = gs[b] * 2*(out[b,i] - x0[b,i]) / cols          (gs[b] = dL/dloss[b] * weight[b] / pt[b])
  *   g_bf16[b,i]  = bf16(g * row_scale[b] * col_scale[i])     A operand of the dgrad contraction
  *   gt_bf16[i,b] = its transpose (optional)                  A operand of the wgrad contraction
+ *   g_lo / gt_lo = optional bf16 residuals of the two (fp32 mode)
  *   colsum[i]      = sum_b (with_out ? g*out : g)            (optional)
  *   rowpart[cb, b] = the same quantity summed over the 32 columns of block cb (optional; [ceil(cols/32), rows]);
  * with_out = 1 yields the sums the cosine scorer's norm terms need (models/DNN.py:1320-1325). */
 int gdmcf_loss_grad(const float* out, int64_t ld_out, const float* x0, int64_t ld_x0, const float* gs,
-                    const float* row_scale, const float* col_scale, int with_out, void* g_bf16, int64_t ld_g,
-                    void* gt_bf16, int64_t ld_gt, float* colsum, float* rowpart, int rows, int cols,
-                    gdmcf_stream_t stream);
+                    const float* row_scale, const float* col_scale, int with_out, void* g_bf16, void* g_lo,
+                    int64_t ld_g, void* gt_bf16, void* gt_lo, int64_t ld_gt, float* colsum, float* rowpart,
+                    int rows, int cols, gdmcf_stream_t stream);
 /* bf16 [rows, cols] -> bf16 [cols, rows] (wgrad operands need the batch dimension contiguous). */
 int gdmcf_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols,
                          gdmcf_stream_t stream);
