@@ -99,6 +99,7 @@ SIGNATURES = {
     "gdmcf_mix_backward": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _I, _I, _P]),
     "gdmcf_ntxent_rows": (_I, [_P, _L, _I, _F, _F, _P, _P, _P, _L, _P]),
     "gdmcf_scatter_rows_add": (_I, [_P, _L, _P, _P, _L, _I, _I, _P]),
+    "gdmcf_lt_history_update": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -28,15 +28,28 @@ GD_DEV void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, long long ld_out, int rows, int cols) {
-  const long long total = (long long)rows * ld_out;
+  // one thread per 8 output columns: eight coalesced scalar loads (the fp32 rows of nn.Linear weights are not
+  // 16 B aligned: ld_in = n_item + emb_size), one 16 B store per output
+  const int groups = (int)(ld_out >> 3);  // ld_out % 8 == 0 (checked on the host)
+  const long long total = (long long)rows * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / ld_out);
-    const int c = (int)(i % ld_out);
-    const float v = (c < cols) ? in[(long long)r * ld_in + c] : 0.f;
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    const int r = (int)(i / groups);
+    const int c0 = (int)(i % groups) << 3;
+    const float* src = in + (long long)r * ld_in + c0;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cols) ? src[j] : 0.f;
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * j], h0, l0);
+      split_bf16(v[2 * j + 1], h1, l1);
+      ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + (long long)r * ld_out + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + (long long)r * ld_out + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 
@@ -352,17 +365,34 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
                              float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
   const float step_size = lr / bc1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float grad = g[i] * grad_scale;
-    float param = p[i];
-    param *= 1.0f - lr * weight_decay;
-    const float mi = m[i] + (grad - m[i]) * (1.0f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * beta2 + (1.0f - beta2) * grad * grad;      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+  const float decay = 1.0f - lr * weight_decay;
+  auto update = [&](float& param, float gr, float& mi, float& vi) {
+    const float grad = gr * grad_scale;
+    param *= decay;
+    mi = mi + (grad - mi) * (1.0f - beta1);                // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * beta2 + (1.0f - beta2) * grad * grad;        // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     param -= step_size * (mi / denom);
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = param;
+  };
+  // 128-bit streams (all four tensors are 16 B aligned: checked on the host), scalar tail
+  const long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    update(pp.x, gg.x, mm.x, vv.x);
+    update(pp.y, gg.y, mm.y, vv.y);
+    update(pp.z, gg.z, mm.z, vv.z);
+    update(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    update(pp, g[i], mm, vv);
+    p[i] = pp; m[i] = mm; v[i] = vv;
   }
 }
 
@@ -379,9 +409,13 @@ using namespace gd::ew;
 
 extern "C" int gdmcf_cast_bf16(const float* in, int64_t ld_in, void* out_hi, void* out_lo, int64_t ld_out, int rows,
                                int cols, gdmcf_stream_t stream) {
-  if (!in || !out_hi || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols) { set_error("cast_bf16: bad arguments"); return GDMCF_EBADARG; }
+  if (!in || !out_hi || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols || (ld_out & 7) || ((uintptr_t)out_hi & 15) ||
+      ((uintptr_t)out_lo & 15)) {
+    set_error("cast_bf16: bad arguments (ld_out %% 8 == 0, 16 B aligned outputs)");
+    return GDMCF_EBADARG;
+  }
   GD_PRE();
-  cast_bf16_kernel<<<grid_1d((long long)rows * ld_out), TPB, 0, st>>>(in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
+  cast_bf16_kernel<<<grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st>>>(in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
   return cuda_check_launch("cast_bf16_kernel");
 }
 
@@ -499,6 +533,10 @@ extern "C" int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, i
                                  float beta2, float eps, float weight_decay, int step, float grad_scale,
                                  gdmcf_stream_t stream) {
   if (!p || !g || !m || !v || n <= 0 || step < 1) { set_error("adamw_fused: bad arguments (step counts from 1)"); return GDMCF_EBADARG; }
+  if (n >= 4 && (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15)) {
+    set_error("adamw_fused: p/g/m/v must be 16 B aligned");
+    return GDMCF_EBADARG;
+  }
   GD_PRE();
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);

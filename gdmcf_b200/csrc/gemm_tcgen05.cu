@@ -36,7 +36,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // power of two: 256 or 512
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for alignment slack
+  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // one 32x33 fp32 transpose tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;  // +1024 alignment slack
 };
 
 struct TmaMaps {
@@ -164,6 +165,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, con
   uint64_t* tfull_bar = bars + 2 * C::STAGES;    // [2]
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -257,32 +259,63 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, con
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = u.m_blk * BM + ew * 32 + lane;
+      // tcgen05.ld hands lane i the 32 columns of row i; a 32x33 smem transpose per warp turns that into
+      // lane = column, so every global access below is a contiguous 128 B (fp32) / 64 B (bf16) row segment.
+      const int m_warp0 = u.m_blk * BM + ew * 32;
+      const int rows_here = min(32, shape.m - m_warp0);  // warp-uniform; <= 0 for fully out-of-range warps
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
       const int n_tile0 = u.n_blk * BN;
+      float* st = stage + ew * (32 * 33);
+      // per-row epilogue context, owned by lane = row and broadcast by shuffle
+      const int m_l = m_warp0 + lane;
+      const bool row_ok = lane < rows_here;
+      const float rs_l = epi.alpha * ((epi.row_scale && row_ok) ? epi.row_scale[m_l] : 1.0f);
+      const int t_l = (epi.row_t && row_ok) ? epi.row_t[m_l] : epi.t_const;
+      const float c1_l = epi.c1 ? epi.c1[t_l] : 1.0f;
+      const float c2_l = epi.c1 ? epi.c2[t_l] : 0.0f;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         if (n_tile0 + c >= shape.n) break;  // warp-uniform
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c, v);
         tmem_ld_wait();
-        if (m < shape.m) {
+        if (rows_here > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[lane * 33 + j] = v[j];
+          __syncwarp();
+          const int n = n_tile0 + c + lane;
           if (shape.ws) {
-            float* dst = shape.ws + (long long)u.split * shape.slab_stride + (long long)m * shape.ld_ws + n_tile0 + c;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (n_tile0 + c + q * 4 < shape.ld_ws)
-                reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
+            // split-K partial slab (ld_ws is a multiple of 32, so the whole chunk is in range)
+            float* dst = shape.ws + (long long)u.split * shape.slab_stride + (long long)m_warp0 * shape.ld_ws + n;
+            for (int r = 0; r < rows_here; ++r) dst[(long long)r * shape.ld_ws] = st[r * 33 + lane];
           } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float a8[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) a8[j] = v[q * 8 + j];
-              epilogue8(epi, m, n_tile0 + c + q * 8, shape.n, a8);
+            const bool col_ok = n < shape.n;
+            const float cs = (epi.col_scale && col_ok) ? epi.col_scale[n] : 1.0f;
+            const float bias0 = (epi.bias && epi.ld_bias == 0 && col_ok) ? epi.bias[n] : 0.0f;
+            for (int r = 0; r < rows_here; ++r) {
+              const float rs = __shfl_sync(0xffffffffu, rs_l, r);
+              const int t = __shfl_sync(0xffffffffu, t_l, r);
+              const float c1 = __shfl_sync(0xffffffffu, c1_l, r);
+              const float c2 = __shfl_sync(0xffffffffu, c2_l, r);
+              if (col_ok) {
+                const long long m = m_warp0 + r;
+                float val = st[r * 33 + lane] * rs * cs;
+                if (epi.bias) val += epi.ld_bias ? epi.bias[(long long)t * epi.ld_bias + n] : bias0;
+                if (epi.act == GDMCF_ACT_TANH) val = tanhf(val);
+                else if (epi.act == GDMCF_ACT_RELU) val = fmaxf(val, 0.f);
+                if (epi.c1) val = c1 * val + c2 * epi.xt[m * epi.ld_xt + n];
+                if (epi.out_f32) epi.out_f32[m * epi.ld_f32 + n] = val;
+                if (epi.out_bf16) {
+                  const __nv_bfloat16 h = __float2bfloat16_rn(val);
+                  reinterpret_cast<__nv_bfloat16*>(epi.out_bf16)[m * epi.ld_bf16 + n] = h;
+                  if (epi.out_bf16_lo)
+                    reinterpret_cast<__nv_bfloat16*>(epi.out_bf16_lo)[m * epi.ld_bf16 + n] =
+                        __float2bfloat16_rn(val - __bfloat162float(h));
+                }
+              }
             }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();

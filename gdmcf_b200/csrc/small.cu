@@ -134,12 +134,90 @@ __global__ void sgemm_small_kernel(const float* __restrict__ A, long long lda, i
   }
 }
 
-// out[c] = sum_r x[r, c] (fp32 in, fp32 accumulate in fixed order per column; deterministic)
-__global__ void colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+// out[c] = sum_r x[r, c]: 32 columns x 8 row-slices per CTA, fixed summation order (deterministic).
+__global__ void __launch_bounds__(256)
+colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c0 = blockIdx.x * 32; c0 < cols; c0 += gridDim.x * 32) {
+    const int c = c0 + tx;
     float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += x[(long long)r * ld + c];
-    out[c] = s;
+    if (c < cols)
+      for (int r = ty; r < rows; r += 8) s += x[(long long)r * ld + c];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += red[j][tx];
+      out[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// Skinny contractions (n <= 16): C[m, 0..n) = alpha * sum_k A[m,k] * B[k, 0..n) + beta * C.
+// NN form (A is [M,K]): one warp per output row, lanes split K, warp-reduce.
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+skinny_nn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, int tb,
+                 float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, float beta) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int m = warp0; m < M; m += nwarps) {
+    float acc[NMAX];
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float a = A[(long long)m * lda + k];
+#pragma unroll
+      for (int j = 0; j < NMAX; ++j)
+        if (j < N) acc[j] = fmaf(a, tb ? B[(long long)j * ldb + k] : B[(long long)k * ldb + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+      for (int j = 0; j < N; ++j) {
+        float* c = C + (long long)m * ldc + j;
+        *c = alpha * acc[j] + (beta != 0.f ? beta * (*c) : 0.f);
+      }
+    }
+  }
+}
+// TN form (A stored [K,M]): 32 output rows x 8 K-slices per CTA (coalesced over m), smem reduce in fixed order.
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+skinny_tn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, int tb,
+                 float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, float beta) {
+  __shared__ float red[8][NMAX][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int m0 = blockIdx.x * 32; m0 < M; m0 += gridDim.x * 32) {
+    const int m = m0 + tx;
+    float acc[NMAX];
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) acc[j] = 0.f;
+    if (m < M) {
+      for (int k = ty; k < K; k += 8) {
+        const float a = A[(long long)k * lda + m];
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j)
+          if (j < N) acc[j] = fmaf(a, tb ? B[(long long)j * ldb + k] : B[(long long)k * ldb + j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) red[ty][j][tx] = acc[j];
+    __syncthreads();
+    if (ty == 0 && m < M) {
+      for (int j = 0; j < N; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][j][tx];
+        float* c = C + (long long)m * ldc + j;
+        *c = alpha * t + (beta != 0.f ? beta * (*c) : 0.f);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -199,6 +277,14 @@ extern "C" int gdmcf_sgemm_small(const float* A, int64_t lda, int trans_a, const
                                  int64_t ldc, int m, int n, int k, float alpha, float beta, gdmcf_stream_t stream) {
   if (!A || !B || !C || m <= 0 || n <= 0 || k <= 0 || ldc < n) { set_error("sgemm_small: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
+  if (n <= 16) {  // time-embedding columns: a 32x32 tile would be mostly padding and the K loop would be serial
+    if (trans_a) {
+      skinny_tn_kernel<16><<<grid_1d((m + 31) / 32, 1), 256, 0, st>>>(A, lda, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
+      return cuda_check_launch("skinny_tn_kernel");
+    }
+    skinny_nn_kernel<16><<<grid_1d((long long)m * 32), 256, 0, st>>>(A, lda, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
+    return cuda_check_launch("skinny_nn_kernel");
+  }
   const int ntiles = ((m + 31) / 32) * ((n + 31) / 32);
   sgemm_small_kernel<<<grid_1d(ntiles, 1), TPB, 0, st>>>(A, lda, trans_a, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
   return cuda_check_launch("sgemm_small_kernel");
@@ -207,6 +293,6 @@ extern "C" int gdmcf_sgemm_small(const float* A, int64_t lda, int trans_a, const
 extern "C" int gdmcf_colsum_f32(const float* x, int64_t ld, int rows, int cols, float* out, gdmcf_stream_t stream) {
   if (!x || !out || rows <= 0 || cols <= 0 || ld < cols) { set_error("colsum_f32: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
-  colsum_f32_kernel<<<grid_1d(cols), TPB, 0, st>>>(x, ld, rows, cols, out);
+  colsum_f32_kernel<<<grid_1d((cols + 31) / 32, 1), 256, 0, st>>>(x, ld, rows, cols, out);
   return cuda_check_launch("colsum_f32_kernel");
 }

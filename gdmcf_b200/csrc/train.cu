@@ -228,11 +228,42 @@ __global__ void scatter_rows_add_kernel(const float* __restrict__ v, long long l
   }
 }
 
+// Lt_history / Lt_count update of training_losses (models/gaussian_diffusion.py:935-949) with the reference's
+// sequential semantics: thread t replays the batch in order and touches only its own row of the history.
+__global__ void lt_history_kernel(const long long* __restrict__ ts, const double* __restrict__ loss, double* __restrict__ hist,
+                                  long long* __restrict__ count, int B, int T, int H) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double* row = hist + (long long)t * H;
+  long long cnt = count[t];
+  for (int b = 0; b < B; ++b) {
+    if (ts[b] != t) continue;
+    if (cnt == H) {
+      for (int j = 0; j + 1 < H; ++j) row[j] = row[j + 1];
+      row[H - 1] = loss[b];
+    } else {
+      row[cnt] = loss[b];
+      ++cnt;
+    }
+  }
+  count[t] = cnt;
+}
+
 }  // namespace train
 }  // namespace gd
 
 using namespace gd;
 using namespace gd::train;
+
+extern "C" int gdmcf_lt_history_update(const int64_t* ts, const double* loss, double* lt_history, int64_t* lt_count, int batch,
+                                       int steps, int history, gdmcf_stream_t stream) {
+  if (!ts || !loss || !lt_history || !lt_count || batch <= 0 || steps <= 0 || history <= 0) { set_error("lt_history_update: bad arguments"); return GDMCF_EBADARG; }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  lt_history_kernel<<<(steps + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ts), loss, lt_history, reinterpret_cast<long long*>(lt_count), batch, steps, history);
+  return cuda_check_launch("lt_history_kernel");
+}
 
 #define GD_PRE()                 \
   int rc = gdmcf_device_check(); \

@@ -417,3 +417,12 @@ def scatter_rows_add(v, idx, grad, rows: int, cols: int) -> None:
     assert idx.dtype == torch.int32
     check(load().gdmcf_scatter_rows_add(ptr(v), v.stride(0), ptr(idx), ptr(grad), grad.stride(0), rows, cols, stream()),
           "scatter_rows_add")
+
+
+def lt_history_update(ts, loss, lt_history, lt_count) -> None:
+    """In-place Lt_history/Lt_count update (gaussian_diffusion.py:935-949). ts int64 [B], loss fp64 [B]."""
+    require_cuda(ts, loss, lt_history, lt_count)
+    assert ts.dtype == torch.int64 and loss.dtype == torch.float64 and lt_history.dtype == torch.float64 and lt_count.dtype == torch.int64
+    assert ts.is_contiguous() and loss.is_contiguous() and lt_history.is_contiguous() and lt_count.is_contiguous()
+    check(load().gdmcf_lt_history_update(ptr(ts), ptr(loss), ptr(lt_history), ptr(lt_count), ts.numel(), lt_history.shape[0],
+                                         lt_history.shape[1], stream()), "lt_history_update")

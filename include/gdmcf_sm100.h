@@ -283,6 +283,10 @@ int gdmcf_mix_backward(const float* d_hcp, int64_t ld_d, const float* hc, int64_
  * -log((p_ii+eps)/sum_{j!=i} p_ij) with p = softmax(S/tau) (closs = mean(loss_rows)); dS = dscale[0] * d closs/dS. */
 int gdmcf_ntxent_rows(const float* S, int64_t ld_s, int n, float tau, float eps, const float* dscale,
                       float* loss_rows, float* dS, int64_t ld_ds, gdmcf_stream_t stream);
+/* Lt_history / Lt_count update (models/gaussian_diffusion.py:935-949), sequential semantics per timestep:
+ * ts int64 [batch], loss fp64 [batch], lt_history fp64 [steps, history], lt_count int64 [steps]. */
+int gdmcf_lt_history_update(const int64_t* ts, const double* loss, double* lt_history, int64_t* lt_count, int batch,
+                            int steps, int history, gdmcf_stream_t stream);
 /* grad[idx[r],:] += v[r,:] (dense nn.Embedding gradient rows, models/DNN.py:1265). */
 int gdmcf_scatter_rows_add(const float* v, int64_t ld_v, const int32_t* idx, float* grad, int64_t ld_g, int rows,
                            int cols, gdmcf_stream_t stream);
