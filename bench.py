@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--topk", type=int, default=20)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--kernel_times", action="store_true", help="print a per-kernel device-time table (torch.profiler) to stderr")
     ap.add_argument("--cpu_sample_users", type=int, default=200)
     return ap.parse_args()
 
@@ -310,7 +311,7 @@ def run_engine(args):
         e0.record()
         orig_gemm(a, b, m, n, ks, **kw)
         e1.record()
-        records.append((e0, e1, 2.0 * m * n * float(sum(ks))))
+        records.append((e0, e1, 2.0 * m * n * float(sum(ks)), (m, n, tuple(ks))))
 
     K.gemm = timed_gemm
     n_prof = 3
@@ -318,15 +319,21 @@ def run_engine(args):
         resident_step(2 * (W + Kst) + s)
     torch.cuda.synchronize()
     K.gemm = orig_gemm
-    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
-    gemm_flops = sum(f for _, _, f in records)
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in records)
+    gemm_flops = sum(f for _, _, f, _ in records)
+    by_shape = {}
+    for e0, e1, f, shp in records:
+        a_ = by_shape.setdefault(str(shp), [0, 0.0, 0.0])
+        a_[0] += 1; a_[1] += e0.elapsed_time(e1); a_[2] += f
+    breakdown = [{"mnk": kk, "launches_per_step": v_[0] / n_prof, "ms_per_step": v_[1] / n_prof,
+                  "tflops": v_[2] / (v_[1] * 1e-3) / 1e12} for kk, v_ in sorted(by_shape.items(), key=lambda kv: -kv[1][1])]
     pk = peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (+ splitk_reduce_kernel)", "achieved": achieved,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
                 "peak_source": f"{pk['src']} (sustained bf16)", "launches_per_step": len(records) / n_prof,
                 "gemm_ms_per_step": gemm_ms / n_prof, "gemm_share_of_step": (gemm_ms / n_prof) / (ms / Kst),
-                "flops_per_step": gemm_flops / n_prof}
+                "flops_per_step": gemm_flops / n_prof, "by_shape": breakdown}
 
     # ---- SpMM (lightGCN propagation, K=3, d=64) on the same interaction graph, HBM roofline
     spmm = None
@@ -357,6 +364,19 @@ def run_engine(args):
         del lg, flush
 
     clocks = sampler.stop() if sampler is not None else None
+
+    if args.kernel_times and rank == 0:
+        # per-kernel device times of 3 steps (CUPTI through torch.profiler) -> stderr table; not part of the JSON line
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for s in range(3):
+                resident_step(3 * (W + Kst) + s)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        print(f"kernel times over 3 steps: total {tot / 3e3:.3f} ms/step", file=sys.stderr)
+        for e in rows[:45]:
+            print(f"{e.device_time_total / 3e3:9.3f} ms/step  x{e.count / 3:6.1f}  {e.key[:100]}", file=sys.stderr)
 
     cpu = None
     if rank == 0 and G == 1 and not args.no_cpu_baseline:

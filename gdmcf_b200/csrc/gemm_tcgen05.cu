@@ -27,6 +27,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARP_FLOATS = 32 * 65 + 32 * 4;
 
 template <int BN>
 struct Cfg {
@@ -36,8 +37,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // power of two: 256 or 512
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // one 32x33 fp32 transpose tile per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;  // +1024 alignment slack
+  // per epilogue warp: a [32][65] fp32 transpose tile + 32 float4 row contexts
+  static constexpr int EPI_STAGE_BYTES = 4 * EPI_WARP_FLOATS * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES;  // base is 1024 B aligned (checked)
 };
 
 struct TmaMaps {
@@ -155,9 +157,10 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, const gdmcf_epilogue epi) {
   using C = Cfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* tiles = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
@@ -265,52 +268,99 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, con
       const int rows_here = min(32, shape.m - m_warp0);  // warp-uniform; <= 0 for fully out-of-range warps
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
       const int n_tile0 = u.n_blk * BN;
-      float* st = stage + ew * (32 * 33);
-      // per-row epilogue context, owned by lane = row and broadcast by shuffle
-      const int m_l = m_warp0 + lane;
-      const bool row_ok = lane < rows_here;
-      const float rs_l = epi.alpha * ((epi.row_scale && row_ok) ? epi.row_scale[m_l] : 1.0f);
-      const int t_l = (epi.row_t && row_ok) ? epi.row_t[m_l] : epi.t_const;
-      const float c1_l = epi.c1 ? epi.c1[t_l] : 1.0f;
-      const float c2_l = epi.c1 ? epi.c2[t_l] : 0.0f;
+      float* st = stage + ew * EPI_WARP_FLOATS;                       // [32][65] transpose tile
+      float4* rowctx = reinterpret_cast<float4*>(st + 32 * 65);       // [32] {alpha*row_scale, c1, c2, t}; 16 B aligned
+      {  // per-row epilogue context: lane = row writes it once per tile, rows read it back as a broadcast LDS.128
+        const int m_l = m_warp0 + lane;
+        const bool row_ok = lane < rows_here;
+        const float rs_l = epi.alpha * ((epi.row_scale && row_ok) ? epi.row_scale[m_l] : 1.0f);
+        const int t_l = (epi.row_t && row_ok) ? epi.row_t[m_l] : epi.t_const;
+        rowctx[lane] = make_float4(rs_l, epi.c1 ? epi.c1[t_l] : 1.0f, epi.c1 ? epi.c2[t_l] : 0.0f, __int_as_float(t_l));
+      }
+      // loop-invariant (warp-uniform) switches hoisted out of the per-row code
+      const bool has_xt = epi.c1 != nullptr, has_tab = epi.bias && epi.ld_bias != 0, has_vec = epi.bias && epi.ld_bias == 0;
+      const bool w32 = epi.out_f32 != nullptr, w16 = epi.out_bf16 != nullptr, wlo = epi.out_bf16_lo != nullptr;
+      const int act = epi.act;
+      const float* __restrict__ xt = epi.xt;
+      const float* __restrict__ bias = epi.bias;
+      float* __restrict__ o32 = epi.out_f32;
+      __nv_bfloat16* __restrict__ o16 = reinterpret_cast<__nv_bfloat16*>(epi.out_bf16);
+      __nv_bfloat16* __restrict__ olo = reinterpret_cast<__nv_bfloat16*>(epi.out_bf16_lo);
+      const long long ld_xt = epi.ld_xt, ld_f32 = epi.ld_f32, ld_b16 = epi.ld_bf16, ld_bias = epi.ld_bias;
+      __syncwarp();
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = 0; c < BN; c += 64) {
         if (n_tile0 + c >= shape.n) break;  // warp-uniform
-        float v[32];
-        tmem_ld_32x32(t_row + (uint32_t)c, v);
+        float v[64];
+        tmem_ld_32x32(t_row + (uint32_t)c, *reinterpret_cast<float(*)[32]>(v));
+        tmem_ld_32x32(t_row + (uint32_t)(c + 32), *reinterpret_cast<float(*)[32]>(v + 32));
         tmem_ld_wait();
         if (rows_here > 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) st[lane * 33 + j] = v[j];
+          for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j];  // bank (lane + j) % 32: conflict-free
           __syncwarp();
-          const int n = n_tile0 + c + lane;
+          // lane now owns columns n0 and n1 = n0 + 32 of every row: two fully coalesced 128 B segments per row
+          const int n0 = n_tile0 + c + lane, n1 = n0 + 32;
           if (shape.ws) {
-            // split-K partial slab (ld_ws is a multiple of 32, so the whole chunk is in range)
-            float* dst = shape.ws + (long long)u.split * shape.slab_stride + (long long)m_warp0 * shape.ld_ws + n;
-            for (int r = 0; r < rows_here; ++r) dst[(long long)r * shape.ld_ws] = st[r * 33 + lane];
-          } else {
-            const bool col_ok = n < shape.n;
-            const float cs = (epi.col_scale && col_ok) ? epi.col_scale[n] : 1.0f;
-            const float bias0 = (epi.bias && epi.ld_bias == 0 && col_ok) ? epi.bias[n] : 0.0f;
+            float* dst = shape.ws + (long long)u.split * shape.slab_stride + (long long)m_warp0 * shape.ld_ws;
+            const bool k0 = n0 < shape.ld_ws, k1 = n1 < shape.ld_ws;
             for (int r = 0; r < rows_here; ++r) {
-              const float rs = __shfl_sync(0xffffffffu, rs_l, r);
-              const int t = __shfl_sync(0xffffffffu, t_l, r);
-              const float c1 = __shfl_sync(0xffffffffu, c1_l, r);
-              const float c2 = __shfl_sync(0xffffffffu, c2_l, r);
-              if (col_ok) {
+              if (k0) dst[(long long)r * shape.ld_ws + n0] = st[r * 65 + lane];
+              if (k1) dst[(long long)r * shape.ld_ws + n1] = st[r * 65 + 32 + lane];
+            }
+          } else {
+            const bool ok0 = n0 < shape.n, ok1 = n1 < shape.n;
+            const float cs0 = (epi.col_scale && ok0) ? epi.col_scale[n0] : 1.0f;
+            const float cs1 = (epi.col_scale && ok1) ? epi.col_scale[n1] : 1.0f;
+            const float bv0 = (has_vec && ok0) ? bias[n0] : 0.0f, bv1 = (has_vec && ok1) ? bias[n1] : 0.0f;
+            // The row loop is deliberately NOT fully unrolled: the unrolled form was ~117 KB of SASS and the
+            // epilogue warps stalled on instruction fetch (ncu: stall_no_inst on every line). Rows go in groups of
+            // RG with all global reads of a group issued before the first use (2*RG independent loads per lane).
+            constexpr int RG = 8;
+#pragma unroll 1
+            for (int r0 = 0; r0 < rows_here; r0 += RG) {
+              float x0[RG], x1[RG], a0[RG], a1[RG];
+#pragma unroll
+              for (int q = 0; q < RG; ++q) {
+                const int r = r0 + q;
+                const bool rok = r < rows_here;
                 const long long m = m_warp0 + r;
-                float val = st[r * 33 + lane] * rs * cs;
-                if (epi.bias) val += epi.ld_bias ? epi.bias[(long long)t * epi.ld_bias + n] : bias0;
-                if (epi.act == GDMCF_ACT_TANH) val = tanhf(val);
-                else if (epi.act == GDMCF_ACT_RELU) val = fmaxf(val, 0.f);
-                if (epi.c1) val = c1 * val + c2 * epi.xt[m * epi.ld_xt + n];
-                if (epi.out_f32) epi.out_f32[m * epi.ld_f32 + n] = val;
-                if (epi.out_bf16) {
-                  const __nv_bfloat16 h = __float2bfloat16_rn(val);
-                  reinterpret_cast<__nv_bfloat16*>(epi.out_bf16)[m * epi.ld_bf16 + n] = h;
-                  if (epi.out_bf16_lo)
-                    reinterpret_cast<__nv_bfloat16*>(epi.out_bf16_lo)[m * epi.ld_bf16 + n] =
-                        __float2bfloat16_rn(val - __bfloat162float(h));
+                x0[q] = (has_xt && rok && ok0) ? xt[m * ld_xt + n0] : 0.f;
+                x1[q] = (has_xt && rok && ok1) ? xt[m * ld_xt + n1] : 0.f;
+                a0[q] = bv0;
+                a1[q] = bv1;
+                if (has_tab) {
+                  const long long t = __float_as_int(rowctx[r].w);
+                  a0[q] = (rok && ok0) ? bias[t * ld_bias + n0] : 0.f;
+                  a1[q] = (rok && ok1) ? bias[t * ld_bias + n1] : 0.f;
+                }
+              }
+#pragma unroll
+              for (int q = 0; q < RG; ++q) {
+                const int r = r0 + q;
+                if (r < rows_here) {  // warp-uniform
+                  const float4 rc = rowctx[r];
+                  const long long m = m_warp0 + r;
+                  float y0 = st[r * 65 + lane] * rc.x * cs0 + a0[q];
+                  float y1 = st[r * 65 + 32 + lane] * rc.x * cs1 + a1[q];
+                  if (act == GDMCF_ACT_TANH) { y0 = tanhf(y0); y1 = tanhf(y1); }
+                  else if (act == GDMCF_ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                  // coef1 * pred_xstart + coef2 * x_t (gaussian_diffusion.py:1047-1050); c1 = 1, c2 = 0 when absent
+                  y0 = rc.y * y0 + rc.z * x0[q];
+                  y1 = rc.y * y1 + rc.z * x1[q];
+                  if (w32) {
+                    if (ok0) o32[m * ld_f32 + n0] = y0;
+                    if (ok1) o32[m * ld_f32 + n1] = y1;
+                  }
+                  if (w16) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+                    if (ok0) o16[m * ld_b16 + n0] = h0;
+                    if (ok1) o16[m * ld_b16 + n1] = h1;
+                    if (wlo) {
+                      if (ok0) olo[m * ld_b16 + n0] = __float2bfloat16_rn(y0 - __bfloat162float(h0));
+                      if (ok1) olo[m * ld_b16 + n1] = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+                    }
+                  }
                 }
               }
             }
