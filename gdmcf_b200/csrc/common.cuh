@@ -84,6 +84,21 @@ GD_DEV void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c_i
       : "memory");
 }
 
+// 2-D tiled bulk tensor store smem -> global (bulk async-group completion). Out-of-bounds parts of the box are
+// clipped by the hardware, so M/N tails need no masking.
+GD_DEV void tma_store_2d(const void* tmap, const void* smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)tmap),
+               "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+GD_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest 0 groups have finished READING their shared-memory source (staging can be overwritten)
+GD_DEV void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+GD_DEV void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) that will read them
+GD_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+GD_DEV void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: tensor memory + 5th-gen tensor-core MMA (single-CTA group)
 // ----------------------------------------------------------------------------------------------

@@ -4,13 +4,19 @@
 //
 // One persistent CTA per SM walks work units (m-block fastest so that the CTAs running side by side
 // share the weight tile in L2). Per CTA, warp-specialised:
-//   warp 0     TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 4-stage smem ring
+//   warp 0     TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 3/5-stage smem ring
 //   warp 1     MMA issuer     : one elected lane issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
 //   warp 2     TMEM allocator : 2 accumulator stages (double-buffered against the epilogue)
-//   warps 4-7  epilogue       : tcgen05.ld 32x32b -> fused epilogue (bias/tanh/relu, cosine scale +
-//                               posterior mean) -> vectorised global stores (fp32 and/or bf16 hi/lo)
-// Split-K units write fp32 partial slabs; splitk_reduce_kernel sums them in fixed order
-// (deterministic) and applies the same epilogue.
+//   warps 4-7  epilogue       : tcgen05.ld 32x32b -> fused epilogue -> global memory, two forms:
+//     (a) TMA-store form (all outputs 16 B-strided): every lane keeps its own row, applies scale / bias /
+//         activation / posterior mean in registers (x_t read as 16 independent 16 B loads per lane), writes
+//         the row into a 128B-swizzled staging tile (conflict-free STS.128) and one lane issues
+//         cp.async.bulk.tensor stores. ~0.15 instructions per output element per warp — the epilogue warps are
+//         single-warp-per-scheduler, so instruction count, not bandwidth, is what bounds them (ncu, round 1).
+//     (b) transposed form (odd leading dimensions, per-timestep bias tables, split-K partial slabs): a
+//         32x65 smem transpose per warp turns lane = row into lane = column so that plain stores coalesce.
+// Split-K units write fp32 partial slabs; splitk_reduce_kernel sums them in fixed order (deterministic)
+// and applies the same epilogue formula.
 //
 // Reference call sites replaced: nn.Linear at models/DNN.py:79-86, :1240-1252, GCNConv linears on the
 // user rows :1082-1100, torch.mm + norm division :1320-1325, posterior mean
@@ -27,24 +33,25 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_WARP_FLOATS = 32 * 65 + 32 * 4;
+constexpr int EPI_WARP_BYTES = 16384;  // per epilogue warp: fp32 [32x64] (8 KB) + bf16 hi (4 KB) + bf16 lo (4 KB)
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  // bytes in flight needed per SM = L2 bandwidth share (~12 TB/s / 148) x ~1 us latency ~ 81 KB: 3 x 48 KB is enough
+  static constexpr int STAGES = (BN == 256) ? 3 : 5;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // power of two: 256 or 512
-  static constexpr int BAR_BYTES = 256;
-  // per epilogue warp: a [32][65] fp32 transpose tile + 32 float4 row contexts
-  static constexpr int EPI_STAGE_BYTES = 4 * EPI_WARP_FLOATS * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES;  // base is 1024 B aligned (checked)
+  static constexpr int BAR_BYTES = 1024;    // barriers + tmem slot, keeps the staging tiles 1024 B aligned
+  static constexpr int COLVEC_BYTES = 2 * BN * 4;  // col_scale / bias of the current tile
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + COLVEC_BYTES;
 };
 
 struct TmaMaps {
   CUtensorMap a[GDMCF_MAX_SEG];
   CUtensorMap b[GDMCF_MAX_SEG];
+  CUtensorMap o32, o16, olo;  // outputs (TMA-store epilogue only)
 };
 
 struct Shape {
@@ -57,10 +64,11 @@ struct Shape {
   long long slab_stride;  // elements between split slabs (fp32)
   int ld_ws;              // leading dim of a slab
   float* ws;              // split-K workspace (NULL when splits == 1)
+  int tma_store;          // 1: epilogue form (a)
 };
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue on 8 consecutive columns of one row (shared by the GEMM and the split-K reducer).
+// Epilogue on 8 consecutive columns of one row (split-K reducer).
 // ---------------------------------------------------------------------------------------------
 GD_DEV void store8_f32(float* dst, const float (&o)[8], int valid, bool vec_ok) {
   if (valid == 8 && vec_ok) {
@@ -71,6 +79,9 @@ GD_DEV void store8_f32(float* dst, const float (&o)[8], int valid, bool vec_ok) 
     for (int j = 0; j < 8; ++j)
       if (j < valid) dst[j] = o[j];
   }
+}
+GD_DEV uint32_t pack_bf16x2(float a, float b) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
 }
 GD_DEV void store8_bf16(__nv_bfloat16* dst, const __nv_bfloat16 (&h)[8], int valid) {
   if (valid == 8) {
@@ -85,6 +96,11 @@ GD_DEV void store8_bf16(__nv_bfloat16* dst, const __nv_bfloat16 (&h)[8], int val
     for (int j = 0; j < 8; ++j)
       if (j < valid) dst[j] = h[j];
   }
+}
+
+// Kept out of line: the activation is only used by the small encoder / GCN contractions.
+__device__ __noinline__ float apply_act(float v, int act) {
+  return act == GDMCF_ACT_TANH ? tanhf(v) : fmaxf(v, 0.f);
 }
 
 // acc: 8 accumulator values of row m, columns n0..n0+7 (n0 % 8 == 0); N = logical column count.
@@ -111,8 +127,7 @@ GD_DEV void epilogue8(const gdmcf_epilogue& e, int m, int n0, int N, const float
       v = acc[j] * rs;
       if (e.col_scale) v *= e.col_scale[n0 + j];
       if (bias) v += bias[j];
-      if (e.act == GDMCF_ACT_TANH) v = tanhf(v);
-      else if (e.act == GDMCF_ACT_RELU) v = fmaxf(v, 0.f);
+      if (e.act != GDMCF_ACT_NONE) v = apply_act(v, e.act);
       // same association as the reference: coef1 * pred_xstart + coef2 * x_t (gaussian_diffusion.py:1047-1050)
       if (xt) v = c1 * v + c2 * xt[j];
     }
@@ -136,9 +151,6 @@ GD_DEV void epilogue8(const gdmcf_epilogue& e, int m, int n0, int N, const float
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Main kernel
-// ---------------------------------------------------------------------------------------------
 struct UnitCoord {
   int m_blk, n_blk, split, kb_begin, kb_end;
 };
@@ -153,22 +165,234 @@ GD_DEV UnitCoord unit_coord(const Shape& s, int unit) {
   return u;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Epilogue form (a): row per lane, registers -> swizzled staging -> TMA store. One call per tile per warp.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+GD_DEV void epilogue_tile_tma(const TmaMaps& maps, const Shape& shape, const gdmcf_epilogue& epi, uint8_t* stg,
+                              const float* colvec, uint32_t t_row, int m_warp0, int n_tile0, int lane) {
+  const int rows_here = min(32, shape.m - m_warp0);
+  const int m_l = m_warp0 + lane;
+  const bool row_ok = lane < rows_here;
+  const float rs = epi.alpha * ((epi.row_scale && row_ok) ? epi.row_scale[m_l] : 1.0f);
+  const int t = (epi.row_t && row_ok) ? epi.row_t[m_l] : epi.t_const;
+  const bool has_xt = epi.c1 != nullptr, has_cs = epi.col_scale != nullptr, has_b = epi.bias != nullptr;
+  const float c1 = has_xt ? epi.c1[t] : 1.0f, c2 = has_xt ? epi.c2[t] : 0.0f;
+  const bool w32 = epi.out_f32 != nullptr, w16 = epi.out_bf16 != nullptr, wlo = epi.out_bf16_lo != nullptr;
+  const int act = epi.act;
+  const float* xrow = epi.xt + (long long)m_l * epi.ld_xt;  // only dereferenced when has_xt && row_ok
+  const uint32_t sw = (uint32_t)(lane & 7);                 // 128B swizzle: 16 B chunk index ^= row % 8
+  uint8_t* s32 = stg;                // two [32 rows x 128 B] boxes (columns 0-31, 32-63 of the chunk)
+  uint8_t* s16 = stg + 8192;         // [32 rows x 128 B] bf16
+  uint8_t* slo = stg + 12288;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 64) {
+    const int n_c = n_tile0 + c;
+    if (n_c >= shape.n || rows_here <= 0) break;  // warp-uniform
+    float v[64];
+    tmem_ld_32x32(t_row + (uint32_t)c, *reinterpret_cast<float(*)[32]>(v));
+    tmem_ld_32x32(t_row + (uint32_t)(c + 32), *reinterpret_cast<float(*)[32]>(v + 32));
+    // x_t row segment: 16 independent 16 B loads per lane, issued before the TMEM wait
+    float4 x[16];
+    if (has_xt) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        x[q] = (row_ok && n_c + 4 * q < shape.n) ? __ldg(reinterpret_cast<const float4*>(xrow + n_c + 4 * q))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tmem_ld_wait();
+    // s = act(alpha*acc*row_scale*col_scale + bias); out = c1*s + c2*x_t      (column vectors: broadcast LDS.128)
+    const float4* cs4 = reinterpret_cast<const float4*>(colvec + c);
+    const float4* b4 = reinterpret_cast<const float4*>(colvec + BN + c);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      float4 y = make_float4(v[4 * q] * rs, v[4 * q + 1] * rs, v[4 * q + 2] * rs, v[4 * q + 3] * rs);
+      if (has_cs) { const float4 s = cs4[q]; y.x *= s.x; y.y *= s.y; y.z *= s.z; y.w *= s.w; }
+      if (has_b) { const float4 b = b4[q]; y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w; }
+      if (act != GDMCF_ACT_NONE) { y.x = apply_act(y.x, act); y.y = apply_act(y.y, act); y.z = apply_act(y.z, act); y.w = apply_act(y.w, act); }
+      if (has_xt) {
+        y.x = c1 * y.x + c2 * x[q].x; y.y = c1 * y.y + c2 * x[q].y;
+        y.z = c1 * y.z + c2 * x[q].z; y.w = c1 * y.w + c2 * x[q].w;
+      }
+      v[4 * q] = y.x; v[4 * q + 1] = y.y; v[4 * q + 2] = y.z; v[4 * q + 3] = y.w;
+    }
+    // staging is free once the previous chunk's bulk stores have been read out of shared memory
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    if (w32) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const uint32_t box = (uint32_t)(q >> 3), ch = (uint32_t)(q & 7) ^ sw;
+        *reinterpret_cast<float4*>(s32 + box * 4096 + lane * 128 + ch * 16) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+    if (w16) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t ch = (uint32_t)q ^ sw;
+        uint4 hi;
+        hi.x = pack_bf16x2(v[8 * q], v[8 * q + 1]); hi.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+        hi.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); hi.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+        *reinterpret_cast<uint4*>(s16 + lane * 128 + ch * 16) = hi;
+        if (wlo) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = v[8 * q + j] - __bfloat162float(__float2bfloat16_rn(v[8 * q + j]));
+          uint4 lo;
+          lo.x = pack_bf16x2(r[0], r[1]); lo.y = pack_bf16x2(r[2], r[3]);
+          lo.z = pack_bf16x2(r[4], r[5]); lo.w = pack_bf16x2(r[6], r[7]);
+          *reinterpret_cast<uint4*>(slo + lane * 128 + ch * 16) = lo;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && epi.mode != 101) {
+      if (w32) {
+        tma_store_2d(&maps.o32, s32, n_c, m_warp0);
+        if (n_c + 32 < shape.n) tma_store_2d(&maps.o32, s32 + 4096, n_c + 32, m_warp0);
+      }
+      if (w16) tma_store_2d(&maps.o16, s16, n_c, m_warp0);
+      if (wlo) tma_store_2d(&maps.olo, slo, n_c, m_warp0);
+      bulk_commit();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue form (b): smem transpose (lane = row -> lane = column), plain coalesced stores.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+GD_DEV void epilogue_tile_transposed(const Shape& shape, const gdmcf_epilogue& epi, const UnitCoord& u, float* st,
+                                     uint32_t t_row, int m_warp0, int n_tile0, int lane) {
+  const int rows_here = min(32, shape.m - m_warp0);  // warp-uniform; <= 0 for fully out-of-range warps
+  float4* rowctx = reinterpret_cast<float4*>(st + 32 * 65);  // [32] {alpha*row_scale, c1, c2, t}; 16 B aligned
+  {
+    const int m_l = m_warp0 + lane;
+    const bool row_ok = lane < rows_here;
+    const float rs_l = epi.alpha * ((epi.row_scale && row_ok) ? epi.row_scale[m_l] : 1.0f);
+    const int t_l = (epi.row_t && row_ok) ? epi.row_t[m_l] : epi.t_const;
+    rowctx[lane] = make_float4(rs_l, epi.c1 ? epi.c1[t_l] : 1.0f, epi.c1 ? epi.c2[t_l] : 0.0f, __int_as_float(t_l));
+  }
+  const bool has_xt = epi.c1 != nullptr, has_tab = epi.bias && epi.ld_bias != 0, has_vec = epi.bias && epi.ld_bias == 0;
+  const bool w32 = epi.out_f32 != nullptr, w16 = epi.out_bf16 != nullptr, wlo = epi.out_bf16_lo != nullptr;
+  const int act = epi.act;
+  const float* __restrict__ bias = epi.bias;
+  float* __restrict__ o32 = epi.out_f32;
+  __nv_bfloat16* __restrict__ o16 = reinterpret_cast<__nv_bfloat16*>(epi.out_bf16);
+  __nv_bfloat16* __restrict__ olo = reinterpret_cast<__nv_bfloat16*>(epi.out_bf16_lo);
+  const long long ld_xt = epi.ld_xt, ld_f32 = epi.ld_f32, ld_b16 = epi.ld_bf16, ld_bias = epi.ld_bias;
+  __syncwarp();
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 64) {
+    if (n_tile0 + c >= shape.n) break;  // warp-uniform
+    float v[64];
+    tmem_ld_32x32(t_row + (uint32_t)c, *reinterpret_cast<float(*)[32]>(v));
+    tmem_ld_32x32(t_row + (uint32_t)(c + 32), *reinterpret_cast<float(*)[32]>(v + 32));
+    tmem_ld_wait();
+    if (rows_here > 0 && epi.mode != 100) {  // mode 100/101: timing probes (tools/gemm_case.py), never used by the engine
+#pragma unroll
+      for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j];  // bank (lane + j) % 32: conflict-free
+      __syncwarp();
+      // lane now owns columns n0 and n1 = n0 + 32 of every row: two fully coalesced 128 B segments per row
+      const int n0 = n_tile0 + c + lane, n1 = n0 + 32;
+      if (shape.ws) {
+        float* dst = shape.ws + (long long)u.split * shape.slab_stride + (long long)m_warp0 * shape.ld_ws;
+        const bool k0 = n0 < shape.ld_ws, k1 = n1 < shape.ld_ws;
+        for (int r = 0; r < rows_here; ++r) {
+          if (k0) dst[(long long)r * shape.ld_ws + n0] = st[r * 65 + lane];
+          if (k1) dst[(long long)r * shape.ld_ws + n1] = st[r * 65 + 32 + lane];
+        }
+      } else {
+        const bool ok0 = n0 < shape.n, ok1 = n1 < shape.n;
+        const float cs0 = (epi.col_scale && ok0) ? epi.col_scale[n0] : 1.0f;
+        const float cs1 = (epi.col_scale && ok1) ? epi.col_scale[n1] : 1.0f;
+        const float bv0 = (has_vec && ok0) ? bias[n0] : 0.0f, bv1 = (has_vec && ok1) ? bias[n1] : 0.0f;
+        // Rows go in groups of RG (not fully unrolled: the unrolled form did not fit the instruction cache);
+        // addresses advance by one leading dimension per row.
+        constexpr int RG = 8;
+        const float* px = epi.xt + (long long)m_warp0 * ld_xt + n0;
+        float* p32 = o32 + (long long)m_warp0 * ld_f32 + n0;
+        __nv_bfloat16* p16 = o16 + (long long)m_warp0 * ld_b16 + n0;
+        __nv_bfloat16* plo = olo + (long long)m_warp0 * ld_b16 + n0;
+        const float* stp = st + lane;
+        const bool store_ok = epi.mode != 101;
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_here; r0 += RG) {
+          float x0[RG], x1[RG];
+          if (has_xt) {  // warp-uniform: all reads of the group in flight before the first use
+#pragma unroll
+            for (int q = 0; q < RG; ++q) {
+              const bool rok = r0 + q < rows_here;
+              x0[q] = (rok && ok0) ? px[q * ld_xt] : 0.f;
+              x1[q] = (rok && ok1) ? px[q * ld_xt + 32] : 0.f;
+            }
+            px += RG * ld_xt;
+          } else {
+#pragma unroll
+            for (int q = 0; q < RG; ++q) x0[q] = x1[q] = 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < RG; ++q) {
+            const int r = r0 + q;
+            if (r < rows_here) {  // warp-uniform
+              const float4 rc = rowctx[r];
+              float y0 = stp[r * 65] * rc.x * cs0 + bv0;
+              float y1 = stp[r * 65 + 32] * rc.x * cs1 + bv1;
+              if (has_tab) {
+                const float* bt = bias + (long long)__float_as_int(rc.w) * ld_bias;
+                if (ok0) y0 += bt[n0];
+                if (ok1) y1 += bt[n1];
+              }
+              if (act != GDMCF_ACT_NONE) { y0 = apply_act(y0, act); y1 = apply_act(y1, act); }
+              // coef1 * pred_xstart + coef2 * x_t (gaussian_diffusion.py:1047-1050); c1 = 1, c2 = 0 when absent
+              y0 = rc.y * y0 + rc.z * x0[q];
+              y1 = rc.y * y1 + rc.z * x1[q];
+              if (store_ok) {
+                if (w32) {
+                  if (ok0) p32[q * ld_f32] = y0;
+                  if (ok1) p32[q * ld_f32 + 32] = y1;
+                }
+                if (w16) {
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+                  if (ok0) p16[q * ld_b16] = h0;
+                  if (ok1) p16[q * ld_b16 + 32] = h1;
+                  if (wlo) {
+                    if (ok0) plo[q * ld_b16] = __float2bfloat16_rn(y0 - __bfloat162float(h0));
+                    if (ok1) plo[q * ld_b16 + 32] = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+                  }
+                }
+              }
+            }
+          }
+          p32 += RG * ld_f32;
+          p16 += RG * ld_b16;
+          plo += RG * ld_b16;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Main kernel
+// ---------------------------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, const gdmcf_epilogue epi) {
   using C = Cfg<BN>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024 B alignment.
-  uint8_t* smem = smem_raw;
+  extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* tiles = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = bars;                     // [STAGES]
-  uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * C::STAGES;    // [2]
+  uint64_t* full_bar = bars;                        // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;           // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2]
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  float* stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+  uint8_t* epi_stage = smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;  // 4 x 16 KB, 1024 B aligned
+  float* colvec = reinterpret_cast<float*>(epi_stage + 4 * EPI_WARP_BYTES);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -255,123 +479,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, con
   } else if (warp >= EPI_WARP0) {
     // ================= epilogue =================
     const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127 among the epilogue threads
+    uint8_t* stg = epi_stage + ew * EPI_WARP_BYTES;
     int local = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++local) {
       const UnitCoord u = unit_coord(shape, unit);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      // tcgen05.ld hands lane i the 32 columns of row i; a 32x33 smem transpose per warp turns that into
-      // lane = column, so every global access below is a contiguous 128 B (fp32) / 64 B (bf16) row segment.
       const int m_warp0 = u.m_blk * BM + ew * 32;
-      const int rows_here = min(32, shape.m - m_warp0);  // warp-uniform; <= 0 for fully out-of-range warps
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
       const int n_tile0 = u.n_blk * BN;
-      float* st = stage + ew * EPI_WARP_FLOATS;                       // [32][65] transpose tile
-      float4* rowctx = reinterpret_cast<float4*>(st + 32 * 65);       // [32] {alpha*row_scale, c1, c2, t}; 16 B aligned
-      {  // per-row epilogue context: lane = row writes it once per tile, rows read it back as a broadcast LDS.128
-        const int m_l = m_warp0 + lane;
-        const bool row_ok = lane < rows_here;
-        const float rs_l = epi.alpha * ((epi.row_scale && row_ok) ? epi.row_scale[m_l] : 1.0f);
-        const int t_l = (epi.row_t && row_ok) ? epi.row_t[m_l] : epi.t_const;
-        rowctx[lane] = make_float4(rs_l, epi.c1 ? epi.c1[t_l] : 1.0f, epi.c1 ? epi.c2[t_l] : 0.0f, __int_as_float(t_l));
-      }
-      // loop-invariant (warp-uniform) switches hoisted out of the per-row code
-      const bool has_xt = epi.c1 != nullptr, has_tab = epi.bias && epi.ld_bias != 0, has_vec = epi.bias && epi.ld_bias == 0;
-      const bool w32 = epi.out_f32 != nullptr, w16 = epi.out_bf16 != nullptr, wlo = epi.out_bf16_lo != nullptr;
-      const int act = epi.act;
-      const float* __restrict__ xt = epi.xt;
-      const float* __restrict__ bias = epi.bias;
-      float* __restrict__ o32 = epi.out_f32;
-      __nv_bfloat16* __restrict__ o16 = reinterpret_cast<__nv_bfloat16*>(epi.out_bf16);
-      __nv_bfloat16* __restrict__ olo = reinterpret_cast<__nv_bfloat16*>(epi.out_bf16_lo);
-      const long long ld_xt = epi.ld_xt, ld_f32 = epi.ld_f32, ld_b16 = epi.ld_bf16, ld_bias = epi.ld_bias;
-      __syncwarp();
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 64) {
-        if (n_tile0 + c >= shape.n) break;  // warp-uniform
-        float v[64];
-        tmem_ld_32x32(t_row + (uint32_t)c, *reinterpret_cast<float(*)[32]>(v));
-        tmem_ld_32x32(t_row + (uint32_t)(c + 32), *reinterpret_cast<float(*)[32]>(v + 32));
-        tmem_ld_wait();
-        if (rows_here > 0) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) st[lane * 65 + j] = v[j];  // bank (lane + j) % 32: conflict-free
-          __syncwarp();
-          // lane now owns columns n0 and n1 = n0 + 32 of every row: two fully coalesced 128 B segments per row
-          const int n0 = n_tile0 + c + lane, n1 = n0 + 32;
-          if (shape.ws) {
-            float* dst = shape.ws + (long long)u.split * shape.slab_stride + (long long)m_warp0 * shape.ld_ws;
-            const bool k0 = n0 < shape.ld_ws, k1 = n1 < shape.ld_ws;
-            for (int r = 0; r < rows_here; ++r) {
-              if (k0) dst[(long long)r * shape.ld_ws + n0] = st[r * 65 + lane];
-              if (k1) dst[(long long)r * shape.ld_ws + n1] = st[r * 65 + 32 + lane];
-            }
-          } else {
-            const bool ok0 = n0 < shape.n, ok1 = n1 < shape.n;
-            const float cs0 = (epi.col_scale && ok0) ? epi.col_scale[n0] : 1.0f;
-            const float cs1 = (epi.col_scale && ok1) ? epi.col_scale[n1] : 1.0f;
-            const float bv0 = (has_vec && ok0) ? bias[n0] : 0.0f, bv1 = (has_vec && ok1) ? bias[n1] : 0.0f;
-            // The row loop is deliberately NOT fully unrolled: the unrolled form was ~117 KB of SASS and the
-            // epilogue warps stalled on instruction fetch (ncu: stall_no_inst on every line). Rows go in groups of
-            // RG with all global reads of a group issued before the first use (2*RG independent loads per lane).
-            constexpr int RG = 8;
-#pragma unroll 1
-            for (int r0 = 0; r0 < rows_here; r0 += RG) {
-              float x0[RG], x1[RG], a0[RG], a1[RG];
-#pragma unroll
-              for (int q = 0; q < RG; ++q) {
-                const int r = r0 + q;
-                const bool rok = r < rows_here;
-                const long long m = m_warp0 + r;
-                x0[q] = (has_xt && rok && ok0) ? xt[m * ld_xt + n0] : 0.f;
-                x1[q] = (has_xt && rok && ok1) ? xt[m * ld_xt + n1] : 0.f;
-                a0[q] = bv0;
-                a1[q] = bv1;
-                if (has_tab) {
-                  const long long t = __float_as_int(rowctx[r].w);
-                  a0[q] = (rok && ok0) ? bias[t * ld_bias + n0] : 0.f;
-                  a1[q] = (rok && ok1) ? bias[t * ld_bias + n1] : 0.f;
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < RG; ++q) {
-                const int r = r0 + q;
-                if (r < rows_here) {  // warp-uniform
-                  const float4 rc = rowctx[r];
-                  const long long m = m_warp0 + r;
-                  float y0 = st[r * 65 + lane] * rc.x * cs0 + a0[q];
-                  float y1 = st[r * 65 + 32 + lane] * rc.x * cs1 + a1[q];
-                  if (act == GDMCF_ACT_TANH) { y0 = tanhf(y0); y1 = tanhf(y1); }
-                  else if (act == GDMCF_ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-                  // coef1 * pred_xstart + coef2 * x_t (gaussian_diffusion.py:1047-1050); c1 = 1, c2 = 0 when absent
-                  y0 = rc.y * y0 + rc.z * x0[q];
-                  y1 = rc.y * y1 + rc.z * x1[q];
-                  if (w32) {
-                    if (ok0) o32[m * ld_f32 + n0] = y0;
-                    if (ok1) o32[m * ld_f32 + n1] = y1;
-                  }
-                  if (w16) {
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-                    if (ok0) o16[m * ld_b16 + n0] = h0;
-                    if (ok1) o16[m * ld_b16 + n1] = h1;
-                    if (wlo) {
-                      if (ok0) olo[m * ld_b16 + n0] = __float2bfloat16_rn(y0 - __bfloat162float(h0));
-                      if (ok1) olo[m * ld_b16 + n1] = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-                    }
-                  }
-                }
-              }
-            }
-          }
-          __syncwarp();
+      if (shape.tma_store) {
+        // column vectors of this tile -> smem (the 4 epilogue warps only: named barrier 1, 128 threads)
+        named_bar_sync(1, 128);  // previous tile's readers are done
+        for (int j = et; j < BN; j += 128) {
+          const int n = n_tile0 + j;
+          colvec[j] = (epi.col_scale && n < shape.n) ? epi.col_scale[n] : 1.0f;
+          colvec[BN + j] = (epi.bias && n < shape.n) ? epi.bias[n] : 0.0f;
         }
+        named_bar_sync(1, 128);
       }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (shape.tma_store)
+        epilogue_tile_tma<BN>(maps, shape, epi, stg, colvec, t_row, m_warp0, n_tile0, lane);
+      else
+        epilogue_tile_transposed<BN>(shape, epi, u, reinterpret_cast<float*>(stg), t_row, m_warp0, n_tile0, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (shape.tma_store && lane == 0) bulk_wait_all();  // bulk stores must have landed before the CTA retires
   }
 
   tc_fence_before();
@@ -422,18 +560,19 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dim ld; box = [box_rows, 64 cols], 128B swizzle,
-// out-of-bounds elements are zero-filled (K tails and M/N tails need no special casing).
-static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, long long ld, int box_rows) {
+// 2-D row-major [rows, cols] tensor with leading dim ld (elements of `esize` bytes); box = [box_rows, box_cols]
+// with box_cols * esize == 128 B, 128B swizzle. Loads zero-fill out-of-bounds elements, stores clip them
+// (K tails and M/N tails need no special casing).
+static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* ptr, int rows, int cols, long long ld,
+                    int box_rows, int box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return GDMCF_ECUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (rows=%d cols=%d ld=%lld ptr=%p) -> %d", rows, cols, ld, ptr, (int)r);
     return GDMCF_EBADARG;
@@ -508,16 +647,16 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
     }
     shape.kb[s] = (g->k[s] + BK - 1) / BK;
     shape.total_kb += shape.kb[s];
-    if ((rc = make_map(&maps.a[s], g->a[s], g->m, g->k[s], g->lda[s], BM))) return rc;
-    if ((rc = make_map(&maps.b[s], g->b[s], g->n, g->k[s], g->ldb[s], bn))) return rc;
+    if ((rc = make_map(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->a[s], g->m, g->k[s], g->lda[s], BM, BK))) return rc;
+    if ((rc = make_map(&maps.b[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->b[s], g->n, g->k[s], g->ldb[s], bn, BK))) return rc;
   }
-  if (e->mode < 0 || e->mode > GDMCF_EPI_COSINE) { set_error("gemm: bad epilogue mode %d", e->mode); return GDMCF_EBADARG; }
+  if (e->mode < 0 || (e->mode > GDMCF_EPI_COSINE && e->mode != 100 && e->mode != 101)) { set_error("gemm: bad epilogue mode %d", e->mode); return GDMCF_EBADARG; }
   if (e->c1 && (!e->c2 || !e->xt)) {
     set_error("gemm: the posterior-mean epilogue needs c1, c2 and xt together");
     return GDMCF_EBADARG;
   }
-  if ((e->out_bf16 && ((e->ld_bf16 & 7) || ((uintptr_t)e->out_bf16 & 15))) ||
-      (e->out_f32 && ((uintptr_t)e->out_f32 & 15)) || (!e->out_f32 && !e->out_bf16)) {
+  if ((e->out_bf16 && ((e->ld_bf16 & 7) || ((uintptr_t)e->out_bf16 & 15))) || (e->out_bf16_lo && ((uintptr_t)e->out_bf16_lo & 15)) ||
+      (e->out_f32 && ((uintptr_t)e->out_f32 & 15)) || (!e->out_f32 && !e->out_bf16) || (e->out_bf16_lo && !e->out_bf16)) {
     set_error("gemm: epilogue outputs need 16B alignment, ld_bf16%%8==0, and at least one output");
     return GDMCF_EBADARG;
   }
@@ -536,6 +675,19 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
     shape.ws = reinterpret_cast<float*>(workspace);
     shape.ld_ws = (g->n + 31) / 32 * 32;
     shape.slab_stride = (long long)g->m * shape.ld_ws;
+  }
+  // Epilogue form (a) needs 16 B global strides on every output and on x_t, a plain (or no) bias vector, and no split-K.
+  // The bulk tensor store clips at 16 B granularity (measured: with n = 1111 fp32 columns, column 1111 is written too),
+  // so the columns [n, round_up(n, 4 | 8)) of every output row must be inside its leading dimension; they receive the
+  // epilogue of a zero accumulator.
+  const long long n4 = ((long long)g->n + 3) / 4 * 4, n8 = ((long long)g->n + 7) / 8 * 8;
+  shape.tma_store = shape.splits == 1 && e->mode != 100 && (!e->bias || e->ld_bias == 0) &&
+                    (!e->out_f32 || ((e->ld_f32 & 3) == 0 && e->ld_f32 >= n4)) && (!e->out_bf16 || e->ld_bf16 >= n8) &&
+                    (!e->c1 || ((e->ld_xt & 3) == 0 && e->ld_xt >= n4 && ((uintptr_t)e->xt & 15) == 0));
+  if (shape.tma_store) {
+    if (e->out_f32 && (rc = make_map(&maps.o32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e->out_f32, g->m, g->n, e->ld_f32, 32, 32))) return rc;
+    if (e->out_bf16 && (rc = make_map(&maps.o16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->out_bf16, g->m, g->n, e->ld_bf16, 32, 64))) return rc;
+    if (e->out_bf16_lo && (rc = make_map(&maps.olo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->out_bf16_lo, g->m, g->n, e->ld_bf16, 32, 64))) return rc;
   }
   const int num_units = shape.tiles_m * shape.tiles_n * shape.splits;
   const int sms = gdmcf_num_sms();

@@ -232,21 +232,42 @@ __global__ void scatter_rows_add_kernel(const float* __restrict__ v, long long l
 // sequential semantics: thread t replays the batch in order and touches only its own row of the history.
 __global__ void lt_history_kernel(const long long* __restrict__ ts, const double* __restrict__ loss, double* __restrict__ hist,
                                   long long* __restrict__ count, int B, int T, int H) {
+  // the batch is staged through shared memory in slabs (a serial walk over global memory costs ~0.6 us per row)
+  constexpr int SLAB = 1024;
+  __shared__ int s_ts[SLAB];
+  __shared__ double s_loss[SLAB];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  double* row = hist + (long long)t * H;
-  long long cnt = count[t];
-  for (int b = 0; b < B; ++b) {
-    if (ts[b] != t) continue;
-    if (cnt == H) {
-      for (int j = 0; j + 1 < H; ++j) row[j] = row[j + 1];
-      row[H - 1] = loss[b];
-    } else {
-      row[cnt] = loss[b];
-      ++cnt;
+  double* grow = hist + (long long)min(t, T - 1) * H;
+  double lrow[32];  // the row is edited in thread-local storage (H <= 32, checked on the host) and written back once
+  if (t < T)
+    for (int j = 0; j < H; ++j) lrow[j] = grow[j];
+  double* row = lrow;
+  long long cnt = t < T ? count[t] : 0;
+  for (int b0 = 0; b0 < B; b0 += SLAB) {
+    const int nb = min(SLAB, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      s_ts[i] = (int)ts[b0 + i];
+      s_loss[i] = loss[b0 + i];
+    }
+    __syncthreads();
+    if (t < T) {
+      for (int b = 0; b < nb; ++b) {
+        if (s_ts[b] != t) continue;
+        if (cnt == H) {
+          for (int j = 0; j + 1 < H; ++j) row[j] = row[j + 1];
+          row[H - 1] = s_loss[b];
+        } else {
+          row[cnt] = s_loss[b];
+          ++cnt;
+        }
+      }
     }
   }
-  count[t] = cnt;
+  if (t < T) {
+    count[t] = cnt;
+    for (int j = 0; j < H; ++j) grow[j] = lrow[j];
+  }
 }
 
 }  // namespace train
@@ -257,7 +278,10 @@ using namespace gd::train;
 
 extern "C" int gdmcf_lt_history_update(const int64_t* ts, const double* loss, double* lt_history, int64_t* lt_count, int batch,
                                        int steps, int history, gdmcf_stream_t stream) {
-  if (!ts || !loss || !lt_history || !lt_count || batch <= 0 || steps <= 0 || history <= 0) { set_error("lt_history_update: bad arguments"); return GDMCF_EBADARG; }
+  if (!ts || !loss || !lt_history || !lt_count || batch <= 0 || steps <= 0 || history <= 0 || history > 32) {
+    set_error("lt_history_update: bad arguments (history_num_per_term <= 32)");
+    return GDMCF_EBADARG;
+  }
   int rc = gdmcf_device_check();
   if (rc) return rc;
   lt_history_kernel<<<(steps + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

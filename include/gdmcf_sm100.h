@@ -101,6 +101,9 @@ typedef struct {
  * - bias + tanh/relu: nn.Linear + activation (models/DNN.py:79-86, :1240-1252, GCNConv bias :1082-1100);
  * - row_scale/col_scale: the cosine scorer's 1/(|u| |e_i|) (models/DNN.py:1304-1327);
  * - c1/c2/xt: posterior mean coef1*pred_xstart + coef2*x_t (models/gaussian_diffusion.py:1041-1050).
+ * Padding rule: when an output's leading dimension is a multiple of 4 (fp32) / 8 (bf16) elements, the columns
+ * [n, round_up(n, 4 | 8)) of each row may be overwritten (bulk tensor stores clip at 16 B granularity); columns
+ * beyond that are never touched. Outputs with other leading dimensions are written exactly.
  * `mode` is informational (kept for ABI stability): */
 #define GDMCF_EPI_STORE 0
 #define GDMCF_EPI_BIAS_ACT 1

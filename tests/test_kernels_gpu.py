@@ -52,6 +52,35 @@ def test_gemm_store(K, m, n, k, splits):
     assert err <= 2e-5 * scale * math.sqrt(k / 64 + 1), f"max err {err} vs scale {scale}"
 
 
+def test_gemm_odd_leading_dimension_and_tails(K):
+    """fp32 output whose row stride is not a multiple of 16 B (nn.Linear weight gradients: ld = n_item + emb_size)
+    takes the transposed-store epilogue; the 16 B-strided case takes the TMA-store epilogue. Both with M/N tails,
+    x_t mixing and a bf16 copy; untouched padding must stay untouched."""
+    m, n, k = 333, 1111, 200
+    a, b = _bf16_operand(m, k, 11), _bf16_operand(n, k, 12)
+    ref = _ref_mm(a, b, k)
+    for ld in (n + 10, K.round_up(n, 4) + 8):
+        out = torch.full((m, ld), 7.0, device="cuda")
+        K.gemm([a], [b], m, n, [k], out_f32=out, splits=1)
+        torch.cuda.synchronize()
+        assert (out[:, :n] - ref).abs().max().item() < 1e-4 * ref.abs().max().item()
+        first_untouched = n if ld % 4 else K.round_up(n, 4)  # header: 16 B clipping granularity of bulk stores
+        assert (out[:, first_untouched:] == 7.0).all()
+    xt = torch.randn(m, K.round_up(n, 4), device="cuda")
+    c1 = torch.rand(m, device="cuda")
+    c2 = torch.rand(m, device="cuda")
+    rt = torch.arange(m, dtype=torch.int32, device="cuda")
+    out = torch.full((m, K.round_up(n, 4) + 4), 7.0, device="cuda")
+    ob = K.Bf16Mat.empty(m, n, "cuda", with_lo=True)
+    K.gemm([a], [b], m, n, [k], out_f32=out, out_bf16=ob.hi, out_bf16_lo=ob.lo, row_t=rt, c1=c1, c2=c2, xt=xt, splits=1)
+    want = c1[:, None] * ref + c2[:, None] * xt[:, :n]
+    torch.cuda.synchronize()
+    assert (out[:, :n] - want).abs().max().item() < 1e-4 * want.abs().max().item()
+    assert (out[:, K.round_up(n, 4):] == 7.0).all()
+    assert torch.equal(ob.hi[:, :n], out[:, :n].to(torch.bfloat16)) and ob.hi[:, K.round_up(n, 8):].abs().max().item() == 0
+    assert (ob.float() - out[:, :n]).abs().max().item() < 2 ** -15 * want.abs().max().item()
+
+
 def test_gemm_multi_segment_bias_tanh(K):
     m, n = 400, 512
     ks = [1000, 1000, 1000]

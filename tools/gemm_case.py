@@ -20,6 +20,7 @@ def op(rows, cols, seed, scale=0.05):
 def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "scorer_post"
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     B, I, d = 400, 34395, 1000
     kw = {}
     if case.startswith("scorer"):
@@ -56,13 +57,13 @@ def main():
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        K.gemm([a], [b], m, n, [k], **kw)
+        K.gemm([a], [b], m, n, [k], mode=mode, **kw)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     flops = 2.0 * m * n * k
     best = min(ts[1:]) if len(ts) > 1 else ts[0]
-    print(f"{case}: m={m} n={n} k={k} ms={['%.3f' % t for t in ts]} best {flops / best / 1e9:.1f} TFLOP/s")
+    print(f"{case} mode={mode}: m={m} n={n} k={k} ms={['%.3f' % t for t in ts]} best {flops / best / 1e9:.1f} TFLOP/s")
 
 
 if __name__ == "__main__":
