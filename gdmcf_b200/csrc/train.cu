@@ -242,6 +242,7 @@ __global__ void lt_history_kernel(const long long* __restrict__ ts, const double
   if (t < T)
     for (int j = 0; j < H; ++j) lrow[j] = grow[j];
   double* row = lrow;
+  int start = 0;
   long long cnt = t < T ? count[t] : 0;
   for (int b0 = 0; b0 < B; b0 += SLAB) {
     const int nb = min(SLAB, B - b0);
@@ -254,11 +255,11 @@ __global__ void lt_history_kernel(const long long* __restrict__ ts, const double
     if (t < T) {
       for (int b = 0; b < nb; ++b) {
         if (s_ts[b] != t) continue;
-        if (cnt == H) {
-          for (int j = 0; j + 1 < H; ++j) row[j] = row[j + 1];
-          row[H - 1] = s_loss[b];
+        if (cnt == H) {  // shift-left-and-append == overwrite the oldest slot of a ring
+          row[start] = s_loss[b];
+          start = (start + 1 == H) ? 0 : start + 1;
         } else {
-          row[cnt] = s_loss[b];
+          row[cnt] = s_loss[b];  // start is still 0 while the row is filling up
           ++cnt;
         }
       }
@@ -266,7 +267,10 @@ __global__ void lt_history_kernel(const long long* __restrict__ ts, const double
   }
   if (t < T) {
     count[t] = cnt;
-    for (int j = 0; j < H; ++j) grow[j] = lrow[j];
+    for (int j = 0; j < H; ++j) {
+      const int src = start + j;
+      grow[j] = lrow[src >= H ? src - H : src];
+    }
   }
 }
 
