@@ -282,14 +282,17 @@ def run_engine(args):
         for s in range(n_steps):
             fn(offset + n_warm + s)
         e1.record()
+        t_enq = time.time()  # host finished enqueueing (it may run ahead of the device)
         torch.cuda.synchronize()
         t_wall1 = time.time()
         dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if G > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        host_ms.append(1e3 * (t_enq - t_wall0) / n_steps)
         return ms.item(), lib.gdmcf_launch_count() - launches0, (t_wall0, t_wall1)
 
+    host_ms = []
     Kst, W = args.steps, max(args.warmup, 3)
     ms, launches, window = timed(resident_step, W, Kst)
     if sampler is not None:
@@ -395,7 +398,7 @@ def run_engine(args):
                 "config": config_of(args, G), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": ms_e2e / Kst},
-                "gpu_launches": int(launches), "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms[0], "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     dist.shutdown()
 

@@ -77,8 +77,8 @@ SIGNATURES = {
     "gdmcf_cast_bf16": (_I, [_P, _L, _P, _P, _L, _I, _I, _P]),
     "gdmcf_cast_bf16_transpose": (_I, [_P, _L, _P, _P, _L, _I, _I, _P]),
     "gdmcf_densify_rows": (_I, [_P, _P, _P, _I, _I, _P, _L, _P, _L, _P]),
-    "gdmcf_qsample_dropout": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _F, _U64, _U64, _P, _L, _P, _P, _L, _I, _I, _P]),
-    "gdmcf_onehot_noise": (_I, [_P, _L, _P, _F, _F, _P, _P, _U64, _U64, _P, _L, _I, _I, _P]),
+    "gdmcf_qsample_dropout": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _F, _U64, _U64, _P, _P, _L, _P, _P, _L, _I, _I, _P]),
+    "gdmcf_onehot_noise": (_I, [_P, _L, _P, _F, _F, _P, _P, _U64, _U64, _P, _P, _L, _I, _I, _P]),
     "gdmcf_encode_onehot_gather": (_I, [_P, _P, _P, _I, _P, _P, _L, _I, _P, _L, _P]),
     "gdmcf_onehot_tables": (_I, [_P, _L, _I, _I, _P, _P, _L, _P]),
     "gdmcf_time_bias_table": (_I, [_P, _P, _P, _L, _P, _I, _I, _I, _P, _P, _L, _P]),
@@ -92,7 +92,8 @@ SIGNATURES = {
     "gdmcf_topn_metrics": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "gdmcf_colsum_f64": (_I, [_P, _I, _I, _P, _P]),
     "gdmcf_mse_rows": (_I, [_P, _L, _P, _L, _I, _I, _P, _P]),
-    "gdmcf_adamw_fused": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "gdmcf_adamw_fused": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
+    "gdmcf_counter_add": (_I, [_P, _U64, _P]),
     "gdmcf_loss_grad": (_I, [_P, _L, _P, _L, _P, _P, _P, _I, _P, _P, _L, _P, _P, _L, _P, _P, _I, _I, _P]),
     "gdmcf_transpose_bf16": (_I, [_P, _L, _P, _L, _I, _I, _P]),
     "gdmcf_ew_binary": (_I, [_I, _P, _L, _P, _L, _F, _F, _P, _L, _P, _P, _L, _I, _I, _P]),

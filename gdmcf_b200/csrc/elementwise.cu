@@ -116,9 +116,13 @@ __global__ void densify_rows_kernel(const int* __restrict__ rowptr, const int* _
 __global__ void qsample_dropout_kernel(const float* __restrict__ x0, long long ld_x0, const int* __restrict__ row_t,
                                        int t_const, const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab,
                                        const float* __restrict__ noise, const uint8_t* __restrict__ keep, float dropout_p,
-                                       uint64_t seed, uint64_t offset, float* __restrict__ xt_f32, long long ld_xt,
+                                       uint64_t seed, uint64_t offset0, const uint64_t* __restrict__ epoch,
+                                       float* __restrict__ xt_f32, long long ld_xt,
                                        __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, long long ld_a,
                                        int rows, int cols) {
+  // Philox counter = offset0 + (epoch << 44) + element group: `epoch` is a device-resident step counter, so a
+  // captured CUDA graph draws fresh numbers on every replay
+  const uint64_t offset = offset0 + (epoch ? (epoch[0] << 44) : 0ull);
   const int groups = (int)(ld_a / 4);  // ld_a % 8 == 0
   const long long total = (long long)rows * groups;
   const Philox rng(seed);
@@ -178,8 +182,10 @@ __global__ void qsample_dropout_kernel(const float* __restrict__ x0, long long l
 // ---------------------------------------------------------------------------------------------
 __global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x0, const int* __restrict__ ts,
                                     float discrete, float dropout_p, const float* __restrict__ u_keep,
-                                    const float* __restrict__ u_drop, uint64_t seed, uint64_t offset,
-                                    __nv_bfloat16* __restrict__ out, long long ld_out, int rows, int cols) {
+                                    const float* __restrict__ u_drop, uint64_t seed, uint64_t offset0,
+                                    const uint64_t* __restrict__ epoch, __nv_bfloat16* __restrict__ out, long long ld_out,
+                                    int rows, int cols) {
+  const uint64_t offset = offset0 + (epoch ? (epoch[0] << 44) : 0ull);
   const int groups = (int)(ld_out / 8);  // 8 outputs = 4 items per thread
   const long long total = (long long)rows * groups;
   const Philox rng(seed);
@@ -276,13 +282,44 @@ __global__ void encode_onehot_gather_kernel(const int* __restrict__ rowptr, cons
                                             const int* __restrict__ users, int n_rows, const float* __restrict__ base,
                                             const float* __restrict__ delta, long long ld_delta, int d,
                                             float* __restrict__ out, long long ld_out) {
+  // the row's item ids are staged in shared memory so that the delta-row gathers (coalesced over k) are independent
+  // loads, 8 in flight per thread, instead of a chain id -> gather -> id -> gather
+  constexpr int SLAB = 512;
+  __shared__ int s_col[SLAB];
   for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
     const int u = users ? users[r] : r;
     const int b = rowptr[u], e = rowptr[u + 1];
-    for (int k = threadIdx.x; k < d; k += blockDim.x) {
-      float s = base[k];
-      for (int j = b; j < e; ++j) s += __ldg(delta + (long long)__ldg(col + j) * ld_delta + k);
-      out[(long long)r * ld_out + k] = s;
+    float s[4];  // up to 4 output columns per thread (d <= 4 * blockDim.x, checked on the host)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = threadIdx.x + q * blockDim.x;
+      s[q] = k < d ? base[k] : 0.f;
+    }
+    for (int j0 = b; j0 < e; j0 += SLAB) {
+      const int n = min(SLAB, e - j0);
+      __syncthreads();
+      for (int j = threadIdx.x; j < n; j += blockDim.x) s_col[j] = col[j0 + j];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = threadIdx.x + q * blockDim.x;
+        if (k < d) {
+          int j = 0;
+          for (; j + 8 <= n; j += 8) {
+            float x[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) x[t] = __ldg(delta + (long long)s_col[j + t] * ld_delta + k);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) s[q] += x[t];
+          }
+          for (; j < n; ++j) s[q] += __ldg(delta + (long long)s_col[j] * ld_delta + k);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = threadIdx.x + q * blockDim.x;
+      if (k < d) out[(long long)r * ld_out + k] = s[q];
     }
   }
 }
@@ -363,7 +400,13 @@ __global__ void mse_rows_kernel(const float* __restrict__ out, long long ld_out,
 // ---------------------------------------------------------------------------------------------
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
+                             float weight_decay, float bc1, float bc2_sqrt, float grad_scale,
+                             const long long* __restrict__ step_dev) {
+  if (step_dev) {  // bias corrections from a device-resident step counter (CUDA-graph replays advance it on the device)
+    const double st = (double)step_dev[0];
+    bc1 = (float)(1.0 - pow((double)beta1, st));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, st));
+  }
   const float step_size = lr / bc1;
   const float decay = 1.0f - lr * weight_decay;
   auto update = [&](float& param, float gr, float& mi, float& vi) {
@@ -394,6 +437,10 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     update(pp, g[i], mm, vv);
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
+}
+
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctr[0] += inc;
 }
 
 }  // namespace ew
@@ -444,9 +491,9 @@ extern "C" int gdmcf_densify_rows(const int32_t* rowptr, const int32_t* col, con
 
 extern "C" int gdmcf_qsample_dropout(const float* x0, int64_t ld_x0, const int32_t* row_t, int t_const,
                                      const float* sqrt_ab, const float* sqrt_1mab, const float* noise,
-                                     const uint8_t* keep, float dropout_p, uint64_t seed, uint64_t offset, float* xt_f32,
-                                     int64_t ld_xt, void* a_bf16, void* a_lo, int64_t ld_a, int rows, int cols,
-                                     gdmcf_stream_t stream) {
+                                     const uint8_t* keep, float dropout_p, uint64_t seed, uint64_t offset,
+                                     const uint64_t* epoch_dev, float* xt_f32, int64_t ld_xt, void* a_bf16, void* a_lo,
+                                     int64_t ld_a, int rows, int cols, gdmcf_stream_t stream) {
   if (!x0 || !a_bf16 || rows <= 0 || cols <= 0 || (ld_a & 7) || ld_a < cols || ld_x0 < cols || ((uintptr_t)a_bf16 & 15) ||
       ((uintptr_t)a_lo & 15) || (xt_f32 && ld_xt < cols) || dropout_p < 0.f || dropout_p >= 1.f || ((sqrt_ab == nullptr) != (sqrt_1mab == nullptr))) {
     set_error("qsample_dropout: bad arguments (ld_a %% 8 == 0, 0 <= dropout_p < 1, both or neither coefficient tables)");
@@ -454,14 +501,15 @@ extern "C" int gdmcf_qsample_dropout(const float* x0, int64_t ld_x0, const int32
   }
   GD_PRE();
   qsample_dropout_kernel<<<grid_1d((long long)rows * (ld_a / 4)), TPB, 0, st>>>(
-      x0, ld_x0, row_t, t_const, sqrt_ab, sqrt_1mab, noise, keep, dropout_p, seed, offset, xt_f32, ld_xt,
+      x0, ld_x0, row_t, t_const, sqrt_ab, sqrt_1mab, noise, keep, dropout_p, seed, offset, epoch_dev, xt_f32, ld_xt,
       (__nv_bfloat16*)a_bf16, (__nv_bfloat16*)a_lo, ld_a, rows, cols);
   return cuda_check_launch("qsample_dropout_kernel");
 }
 
 extern "C" int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t* ts, float discrete, float dropout_p,
-                                  const float* u_keep, const float* u_drop, uint64_t seed, uint64_t offset, void* out_bf16,
-                                  int64_t ld_out, int rows, int cols, gdmcf_stream_t stream) {
+                                  const float* u_keep, const float* u_drop, uint64_t seed, uint64_t offset,
+                                  const uint64_t* epoch_dev, void* out_bf16, int64_t ld_out, int rows, int cols,
+                                  gdmcf_stream_t stream) {
   if (!x0 || !out_bf16 || rows <= 0 || cols <= 0 || (ld_out & 7) || ld_out < 2LL * cols || ld_x0 < cols ||
       ((uintptr_t)out_bf16 & 15) || dropout_p < 0.f || dropout_p >= 1.f) {
     set_error("onehot_noise: bad arguments (ld_out %% 8 == 0 and >= 2*cols)");
@@ -469,7 +517,7 @@ extern "C" int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t*
   }
   GD_PRE();
   onehot_noise_kernel<<<grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st>>>(
-      x0, ld_x0, ts, discrete, dropout_p, u_keep, u_drop, seed, offset, (__nv_bfloat16*)out_bf16, ld_out, rows, cols);
+      x0, ld_x0, ts, discrete, dropout_p, u_keep, u_drop, seed, offset, epoch_dev, (__nv_bfloat16*)out_bf16, ld_out, rows, cols);
   return cuda_check_launch("onehot_noise_kernel");
 }
 
@@ -490,8 +538,8 @@ extern "C" int gdmcf_onehot_tables(const float* w2, int64_t ld_w, int d, int n_i
 extern "C" int gdmcf_encode_onehot_gather(const int32_t* rowptr, const int32_t* col, const int32_t* users, int n_rows,
                                           const float* base, const float* delta, int64_t ld_delta, int d, float* out,
                                           int64_t ld_out, gdmcf_stream_t stream) {
-  if (!rowptr || !col || !base || !delta || !out || n_rows <= 0 || d <= 0 || ld_delta < d || ld_out < d) {
-    set_error("encode_onehot_gather: bad arguments");
+  if (!rowptr || !col || !base || !delta || !out || n_rows <= 0 || d <= 0 || d > 4 * TPB || ld_delta < d || ld_out < d) {
+    set_error("encode_onehot_gather: bad arguments (d <= 1024)");
     return GDMCF_EBADARG;
   }
   GD_PRE();
@@ -530,9 +578,9 @@ extern "C" int gdmcf_mse_rows(const float* out, int64_t ld_out, const float* x0,
 }
 
 extern "C" int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                                 float beta2, float eps, float weight_decay, int step, float grad_scale,
-                                 gdmcf_stream_t stream) {
-  if (!p || !g || !m || !v || n <= 0 || step < 1) { set_error("adamw_fused: bad arguments (step counts from 1)"); return GDMCF_EBADARG; }
+                                 float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
+                                 float grad_scale, gdmcf_stream_t stream) {
+  if (!p || !g || !m || !v || n <= 0 || (step < 1 && !step_dev)) { set_error("adamw_fused: bad arguments (step counts from 1)"); return GDMCF_EBADARG; }
   if (n >= 4 && (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15)) {
     set_error("adamw_fused: p/g/m/v must be 16 B aligned");
     return GDMCF_EBADARG;
@@ -540,6 +588,13 @@ extern "C" int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, i
   GD_PRE();
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adamw_kernel<<<grid_1d(n), TPB, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+  adamw_kernel<<<grid_1d(n), TPB, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, reinterpret_cast<const long long*>(step_dev));
   return cuda_check_launch("adamw_kernel");
+}
+
+extern "C" int gdmcf_counter_add(uint64_t* counter_dev, uint64_t inc, gdmcf_stream_t stream) {
+  if (!counter_dev) { set_error("counter_add: null pointer"); return GDMCF_EBADARG; }
+  GD_PRE();
+  counter_add_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long*>(counter_dev), inc);
+  return cuda_check_launch("counter_add_kernel");
 }

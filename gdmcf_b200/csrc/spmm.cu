@@ -38,20 +38,30 @@ GD_DEV float2 ld_stream_f32x2(const float* p) {
 constexpr int GATHER_UNROLL = 8;
 constexpr int WARPS_PER_CTA = 8;
 
+GD_DEV float4 ld_stream_f32x4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// One warp per (work item, 64-column slab). The two half-warps take alternate non-zeros of the item and each lane
+// gathers a float4 (16 lanes x 16 B = one 256 B embedding row), so every gather instruction moves two rows and
+// 16 rows (4 KB) are in flight per warp; control flow stays warp-uniform. The halves are combined by shuffle.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, const int4* __restrict__ items,
                   int n_items, const float* __restrict__ X, const float* __restrict__ Z, float* __restrict__ Y,
                   float* __restrict__ scratch, int d, float alpha, float beta) {
   const int lane = threadIdx.x & 31;
+  const int half = lane >> 4, hl = lane & 15;
   const int slabs = d >> 6;
   const long long total = (long long)n_items * slabs;
   const long long warp0 = (long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * WARPS_PER_CTA;
   for (long long w = warp0; w < total; w += nwarps) {
     const int item = (int)(w / slabs);
-    const int coff = (int)(w % slabs) * 64 + lane * 2;
+    const int coff = (int)(w % slabs) * 64 + hl * 4;
     const int4 it = __ldg(&items[item]);  // {row, begin, end, slot}
-    float2 acc = make_float2(0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = it.y; base < it.z; base += 32) {
       const int n = min(32, it.z - base);
       int my_c = 0;
@@ -60,35 +70,45 @@ spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, co
         my_c = ld_stream_i32(col + base + lane);
         my_v = ld_stream_f32(val + base + lane);
       }
-      for (int j0 = 0; j0 < n; j0 += GATHER_UNROLL) {
-        float2 x[GATHER_UNROLL];
+      for (int j0 = 0; j0 < n; j0 += 2 * GATHER_UNROLL) {
+        float4 x[GATHER_UNROLL];
         float v[GATHER_UNROLL];
 #pragma unroll
         for (int u = 0; u < GATHER_UNROLL; ++u) {
-          const int c = __shfl_sync(0xffffffffu, my_c, (j0 + u) & 31);
-          v[u] = __shfl_sync(0xffffffffu, my_v, (j0 + u) & 31);
-          x[u] = make_float2(0.f, 0.f);
-          if (j0 + u < n) x[u] = __ldg(reinterpret_cast<const float2*>(X + (long long)c * d + coff));
+          const int j = j0 + 2 * u + half;
+          const int c = __shfl_sync(0xffffffffu, my_c, j & 31);
+          const float vv = __shfl_sync(0xffffffffu, my_v, j & 31);
+          const bool ok = j < n;
+          v[u] = ok ? vv : 0.f;
+          x[u] = ok ? __ldg(reinterpret_cast<const float4*>(X + (long long)c * d + coff)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < GATHER_UNROLL; ++u) {
-          if (j0 + u < n) {  // warp-uniform; keeps the CSR summation order
-            acc.x = fmaf(v[u], x[u].x, acc.x);
-            acc.y = fmaf(v[u], x[u].y, acc.y);
-          }
+          acc.x = fmaf(v[u], x[u].x, acc.x);
+          acc.y = fmaf(v[u], x[u].y, acc.y);
+          acc.z = fmaf(v[u], x[u].z, acc.z);
+          acc.w = fmaf(v[u], x[u].w, acc.w);
         }
       }
     }
-    if (it.w < 0) {
-      float2 o = make_float2(alpha * acc.x, alpha * acc.y);
-      if (Z) {
-        const float2 z = ld_stream_f32x2(Z + (long long)it.x * d + coff);
-        o.x = fmaf(beta, z.x, o.x);
-        o.y = fmaf(beta, z.y, o.y);
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    if (half == 0) {
+      if (it.w < 0) {
+        float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+        if (Z) {
+          const float4 z = ld_stream_f32x4(Z + (long long)it.x * d + coff);
+          o.x = fmaf(beta, z.x, o.x);
+          o.y = fmaf(beta, z.y, o.y);
+          o.z = fmaf(beta, z.z, o.z);
+          o.w = fmaf(beta, z.w, o.w);
+        }
+        *reinterpret_cast<float4*>(Y + (long long)it.x * d + coff) = o;
+      } else {
+        *reinterpret_cast<float4*>(scratch + (long long)it.w * d + coff) = acc;
       }
-      *reinterpret_cast<float2*>(Y + (long long)it.x * d + coff) = o;
-    } else {
-      *reinterpret_cast<float2*>(scratch + (long long)it.w * d + coff) = acc;
     }
   }
 }

@@ -219,24 +219,24 @@ def densify_rows(rowptr, col, users, n_rows: int, n_items: int, out_f32=None, ou
 
 def qsample_dropout(x0, rows: int, cols: int, a_out: Bf16Mat, *, row_t=None, t_const: int = 0, sqrt_ab=None,
                     sqrt_1mab=None, noise=None, keep=None, dropout_p: float = 0.0, seed: int = 0, offset: int = 0,
-                    xt_out=None) -> None:
+                    epoch=None, xt_out=None) -> None:
     require_cuda(x0, a_out.hi, row_t, sqrt_ab, sqrt_1mab, noise, keep, xt_out)
     if noise is not None:
         assert noise.is_contiguous() and noise.shape == (rows, cols) and noise.dtype == torch.float32
     if keep is not None:
         assert keep.is_contiguous() and keep.shape == (rows, cols) and keep.dtype == torch.uint8
     check(load().gdmcf_qsample_dropout(ptr(x0), x0.stride(0), ptr(row_t), t_const, ptr(sqrt_ab), ptr(sqrt_1mab), ptr(noise),
-                                       ptr(keep), dropout_p, seed, offset, ptr(xt_out),
+                                       ptr(keep), dropout_p, seed, offset, ptr(epoch), ptr(xt_out),
                                        xt_out.stride(0) if xt_out is not None else 0, ptr(a_out.hi), ptr(a_out.lo),
                                        a_out.ld, rows, cols, stream()), "qsample_dropout")
 
 
 def onehot_noise(x0, rows: int, cols: int, out: torch.Tensor, *, ts=None, discrete: float = 0.9995,
-                 dropout_p: float = 0.0, u_keep=None, u_drop=None, seed: int = 0, offset: int = 0) -> None:
+                 dropout_p: float = 0.0, u_keep=None, u_drop=None, seed: int = 0, offset: int = 0, epoch=None) -> None:
     require_cuda(x0, out, ts, u_keep, u_drop)
     assert out.dtype == torch.bfloat16 and out.stride(1) == 1
     check(load().gdmcf_onehot_noise(ptr(x0), x0.stride(0), ptr(ts), discrete, dropout_p, ptr(u_keep), ptr(u_drop), seed,
-                                    offset, ptr(out), out.stride(0), rows, cols, stream()), "onehot_noise")
+                                    offset, ptr(epoch), ptr(out), out.stride(0), rows, cols, stream()), "onehot_noise")
 
 
 def onehot_tables(w2: torch.Tensor, d: int, n_items: int):
@@ -367,11 +367,11 @@ def mse_rows(out, x0, rows: int, cols: int) -> torch.Tensor:
 
 
 def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
-                weight_decay: float = 0.0, step: int = 1, grad_scale: float = 1.0) -> None:
+                weight_decay: float = 0.0, step: int = 1, step_dev=None, grad_scale: float = 1.0) -> None:
     require_cuda(p, g, m, v)
     assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
     check(load().gdmcf_adamw_fused(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
-                                   grad_scale, stream()), "adamw_fused")
+                                   ptr(step_dev), grad_scale, stream()), "adamw_fused")
 
 
 def loss_grad(out, x0, gs, rows: int, cols: int, G: Bf16Mat, *, GT: Optional[Bf16Mat] = None, row_scale=None,
@@ -426,3 +426,10 @@ def lt_history_update(ts, loss, lt_history, lt_count) -> None:
     assert ts.is_contiguous() and loss.is_contiguous() and lt_history.is_contiguous() and lt_count.is_contiguous()
     check(load().gdmcf_lt_history_update(ptr(ts), ptr(loss), ptr(lt_history), ptr(lt_count), ts.numel(), lt_history.shape[0],
                                          lt_history.shape[1], stream()), "lt_history_update")
+
+
+def counter_add(counter: torch.Tensor, inc: int = 1) -> None:
+    """counter[0] += inc on the stream (device-resident step / RNG-epoch counters; int64 or uint64 scalar tensor)."""
+    require_cuda(counter)
+    assert counter.element_size() == 8
+    check(load().gdmcf_counter_add(ptr(counter), inc, stream()), "counter_add")

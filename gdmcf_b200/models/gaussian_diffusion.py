@@ -86,6 +86,7 @@ class GaussianDiffusionDiscrete(nn.Module):
         self.indexIn = False
         self.seed = 0
         self._calls = 0
+        self._epoch = None
         self._importance_ready = False
         if mean_type != ModelMeanType.START_X:
             raise NotImplementedError("mean_type=eps is an ablation outside the hot path (SURVEY.md §8f)")
@@ -153,6 +154,15 @@ class GaussianDiffusionDiscrete(nn.Module):
             res = res[..., None]
         return res.expand(broadcast_shape)
 
+    def _begin_step(self, dev) -> None:
+        """Advance the device-resident RNG epoch (one per training_losses / p_sample call). The Philox counter of every
+        in-kernel draw is (call site << 40) + (epoch << 44) + element, so a captured CUDA graph draws fresh numbers on
+        each replay without any host-side state."""
+        if self._epoch is None or self._epoch.device != torch.device(dev):
+            self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        K.counter_add(self._epoch, 1)
+        self._calls = 0
+
     def _offset(self) -> int:
         self._calls += 1
         return (self._calls << 40) | (1 << 62)
@@ -184,9 +194,10 @@ class GaussianDiffusionDiscrete(nn.Module):
             noise = noise.float().contiguous()
         out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=x_start.device)
         scratch = Bf16Mat.empty(B, I, x_start.device, zero=False)
+        self._begin_step(x_start.device)
         K.qsample_dropout(x_start.float(), B, I, scratch, row_t=t.to(torch.int32), sqrt_ab=self._f32["sqrt_alphas_cumprod"],
                           sqrt_1mab=self._f32["sqrt_one_minus_alphas_cumprod"], noise=noise, seed=self.seed,
-                          offset=self._offset(), xt_out=out)
+                          offset=self._offset(), epoch=self._epoch, xt_out=out)
         return out[:, :I]
 
     def apply_noise(self, ts, x_start, x_base=None, u_keep=None):
@@ -195,8 +206,9 @@ class GaussianDiffusionDiscrete(nn.Module):
         B, I, _ = x_start.shape
         cls = x_start[..., 1].float().contiguous()  # class index as {0,1}
         out = torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=x_start.device)
+        self._begin_step(x_start.device)
         K.onehot_noise(cls, B, I, out, ts=ts.to(torch.int32), discrete=float(self.discrete), u_keep=u_keep, seed=self.seed,
-                       offset=self._offset())
+                       offset=self._offset(), epoch=self._epoch)
         kept = out[:, : 2 * I].reshape(B, I, 2) != 0
         # apply_noise itself returns one_hot(sample): the class flips when the true class was not kept
         onehot = x_start.bool()
@@ -280,6 +292,8 @@ class GaussianDiffusionDiscrete(nn.Module):
         lo = getattr(model, "_lo", False)
         x0, x0_op, csr, users, B, I = self._dense_start(x_start, want_op=(steps == 0), lo=lo)
         dev = x0.device
+        if steps != 0:
+            self._begin_step(dev)
         gdmcf = self.CatOneHot and self.indexIn
         if self.CatOneHot and not self.indexIn:
             raise NotImplementedError("CatOneHot without indexIn selects backbones outside the hot path")
@@ -298,12 +312,13 @@ class GaussianDiffusionDiscrete(nn.Module):
             x_op = Bf16Mat.empty(B, I, dev, lo, zero=False)
             K.qsample_dropout(x0, B, I, x_op, t_const=steps - 1, sqrt_ab=self._f32["sqrt_alphas_cumprod"],
                               sqrt_1mab=self._f32["sqrt_one_minus_alphas_cumprod"], noise=noise, seed=self.seed,
-                              offset=self._offset(), xt_out=x_t)
+                              offset=self._offset(), epoch=self._epoch, xt_out=x_t)
             if gdmcf:
                 xu_op = torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)
                 ts = torch.full((B,), steps - 1, dtype=torch.int32, device=dev)
                 K.onehot_noise(x0, B, I, xu_op, ts=ts, discrete=float(self.discrete),
-                               u_keep=inject.get("u_keep") if inject else None, seed=self.seed, offset=self._offset())
+                               u_keep=inject.get("u_keep") if inject else None, seed=self.seed, offset=self._offset(),
+                               epoch=self._epoch)
         elif gdmcf and csr is None:
             # dense input, x_tU = one_hot(x0): build the interleaved one-hot operand once
             xu_op = torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)

@@ -35,6 +35,12 @@ def _temb_table(model, T, dev):
     return _vec_cache(model, f"temb{T}", lambda: timestep_embedding(torch.arange(T), model.time_emb_dim).to(dev).contiguous())
 
 
+def _time_cols(model, name, W, n_in):
+    """Contiguous [d, e] copy of a first layer's time-embedding columns (cached per weight version): the strided
+    view W[:, n_in:] would make every lane of the skinny contraction touch a different 137 KB-apart row."""
+    return model._ops.get(name + ".tcols", [W], lambda: W.detach()[:, n_in:].contiguous())
+
+
 def _mm_auto(model, a: Bf16Mat, b: Bf16Mat, m, n, k, **epi):
     """Contraction in the model's precision; operands that carry no lo part fall back to their hi part only."""
     if model._lo and a.lo is not None and b.lo is not None:
@@ -85,11 +91,11 @@ def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc,
     K.qsample_dropout(x0, B, I, c.A1, row_t=ts, sqrt_ab=diff._f32["sqrt_alphas_cumprod"],
                       sqrt_1mab=diff._f32["sqrt_one_minus_alphas_cumprod"], noise=inject.get("noise"),
                       keep=keep.to(torch.uint8).contiguous() if keep is not None else None, dropout_p=p, seed=diff.seed,
-                      offset=diff._offset())
+                      offset=diff._offset(), epoch=diff._epoch)
     c.A2 = torch.empty(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)
     kxu = inject.get("keep_xU")
     K.onehot_noise(x0, B, I, c.A2, ts=ts_disc, discrete=float(diff.discrete), dropout_p=p, u_keep=inject.get("u_keep"),
-                   u_drop=kxu.float().contiguous() if kxu is not None else None, seed=diff.seed, offset=diff._offset())
+                   u_drop=kxu.float().contiguous() if kxu is not None else None, seed=diff.seed, offset=diff._offset(), epoch=diff._epoch)
     # user tower buffers: always with lo parts (nt_xent needs split precision)
     c.hc_f32 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
     c.hc = Bf16Mat.empty(B, 3 * d, dev, True)
@@ -227,7 +233,7 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
         K.sgemm_small(dpre, emb_rows, gW[:, n_in:], d, e, B, trans_a=True)                   # time-embedding columns
         grads[name + ".weight"] = gW
         grads[name + ".bias"] = K.colsum_f32(dpre, B, d)
-        K.sgemm_small(dpre, W.detach()[:, n_in:], d_emb, B, e, d, beta=0.0 if first else 1.0)
+        K.sgemm_small(dpre, _time_cols(model, name, W, n_in), d_emb, B, e, d, beta=0.0 if first else 1.0)
     gWe = torch.empty_like(P["emb_layer.weight"])
     K.sgemm_small(d_emb, temb_rows, gWe, e, e, B, trans_a=True)
     grads["emb_layer.weight"] = gWe
@@ -269,7 +275,7 @@ def _dnn_forward(model: DNN, diff, x0, B, I, ts, inject) -> _Ctx:
     K.qsample_dropout(x0, B, I, c.A1, row_t=ts, sqrt_ab=diff._f32["sqrt_alphas_cumprod"],
                       sqrt_1mab=diff._f32["sqrt_one_minus_alphas_cumprod"], noise=inject.get("noise"),
                       keep=keep.to(torch.uint8).contiguous() if keep is not None else None, dropout_p=p, seed=diff.seed,
-                      offset=diff._offset())
+                      offset=diff._offset(), epoch=diff._epoch)
     c.h_f32 = torch.empty(B, d, dtype=torch.float32, device=dev)
     c.h = Bf16Mat.empty(B, d, dev, model._lo)
     model._encode(c.A1, B, ts, 0, T, c.h, h_f32=c.h_f32)
@@ -315,7 +321,7 @@ def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
     grads["in_layers.0.weight"] = gW
     grads["in_layers.0.bias"] = K.colsum_f32(dh_pre, B, d)
     d_emb = torch.empty(B, e, dtype=torch.float32, device=dev)
-    K.sgemm_small(dh_pre, W.detach()[:, I:], d_emb, B, e, d)
+    K.sgemm_small(dh_pre, _time_cols(model, "in_layers.0", W, I), d_emb, B, e, d)
     gWe = torch.empty_like(P["emb_layer.weight"])
     K.sgemm_small(d_emb, temb_rows, gWe, e, e, B, trans_a=True)
     grads["emb_layer.weight"] = gWe
@@ -349,6 +355,7 @@ def training_losses(diff, model, x_start, reweight=False, index=None, inject: Op
     inject = inject or {}
     x0, _, _, users, B, I = diff._dense_start(x_start, want_op=False, lo=False)
     dev = x0.device
+    diff._begin_step(dev)
     if index is None and users is not None:
         index = users
     if diff.noise_scale == 0.0:

@@ -165,7 +165,7 @@ int gdmcf_densify_rows(const int32_t* rowptr, const int32_t* col, const int32_t*
 int gdmcf_qsample_dropout(const float* x0, int64_t ld_x0, const int32_t* row_t, int t_const,
                           const float* sqrt_ab, const float* sqrt_1mab, const float* noise,
                           const uint8_t* keep, float dropout_p, uint64_t seed, uint64_t offset,
-                          float* xt_f32, int64_t ld_xt, void* a_bf16, void* a_lo, int64_t ld_a, int rows,
+                          const uint64_t* epoch_dev, float* xt_f32, int64_t ld_xt, void* a_bf16, void* a_lo, int64_t ld_a, int rows,
                           int cols, gdmcf_stream_t stream);
 
 /* apply_noise + "& one_hot(x0)" + dropout on the one-hot branch (gaussian_diffusion.py:770-831,:851;
@@ -175,7 +175,7 @@ int gdmcf_qsample_dropout(const float* x0, int64_t ld_x0, const int32_t* row_t, 
  * u_keep / u_drop: optional injected uniforms [rows, cols] / [rows, 2*cols] (fp32 in [0,1)). */
 int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t* ts, float discrete, float dropout_p,
                        const float* u_keep, const float* u_drop, uint64_t seed, uint64_t offset,
-                       void* out_bf16, int64_t ld_out, int rows, int cols, gdmcf_stream_t stream);
+                       const uint64_t* epoch_dev, void* out_bf16, int64_t ld_out, int rows, int cols, gdmcf_stream_t stream);
 
 /* Inference form of the one-hot encoder (models/DNN.py:1249-1251 with x_tU = one_hot(x0)):
  * S[r,:] = base[:] + sum_{i in row users[r]} delta[i,:], where base = sum_i W2[:,2i] and
@@ -255,8 +255,11 @@ int gdmcf_mse_rows(const float* out, int64_t ld_out, const float* x0, int64_t ld
  * the gradient first (1/world_size after an allreduce-sum). Optionally refreshes the bf16 operand
  * copy (hi + lo) used by the contractions when the parameter is a [rows, cols] matrix. */
 int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                      float beta2, float eps, float weight_decay, int step, float grad_scale,
-                      gdmcf_stream_t stream);
+                      float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
+                      float grad_scale, gdmcf_stream_t stream);
+/* counter_dev[0] += inc on the stream: the device-resident step / RNG-epoch counters that keep captured CUDA graphs
+ * advancing (Philox counter = offset + (epoch << 44); AdamW bias corrections from *step_dev when non-NULL). */
+int gdmcf_counter_add(uint64_t* counter_dev, uint64_t inc, gdmcf_stream_t stream);
 
 /* Backward of the weighted MSE (models/gaussian_diffusion.py:902,932,951) in one pass over out [rows, cols]:
  *   g[b,i] = gs[b] * 2*(out[b,i] - x0[b,i]) / cols          (gs[b] = dL/dloss[b] * weight[b] / pt[b])
