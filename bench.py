@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--topk", type=int, default=20)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_graphs", action="store_true", help="launch the step kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--kernel_times", action="store_true", help="print a per-kernel device-time table (torch.profiler) to stderr")
     ap.add_argument("--cpu_sample_users", type=int, default=200)
     return ap.parse_args()
@@ -192,10 +193,12 @@ def run_engine(args):
     from gdmcf_b200.lightGCN import LightGCN
     from gdmcf_b200.models import gaussian_diffusion as gd
     from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    from gdmcf_b200.engine import StepEngine
     from gdmcf_b200.optim import FusedAdamW
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (engine arm) needs a CUDA device; there is no CPU fallback")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's banner off stdout (one JSON line only)
     dist = dist_utils.init("nccl")
     G, rank = dist.world_size, dist.rank
     assert G == max(args.gpus, 1) or G == 1, f"--gpus {args.gpus} but WORLD_SIZE={G}"
@@ -223,30 +226,29 @@ def run_engine(args):
                                   precision=args.precision).to(dev)
     dist.broadcast_parameters(model)
     diffusion.seed = model.seed = 1234 + rank
-    opt = FusedAdamW(model.parameters(), lr=1e-5, weight_decay=0.0, modules=[model])
+    opt = FusedAdamW(model.parameters(), lr=1e-5, weight_decay=0.0, modules=[model], capturable=True)
     n_batches = n_user // B
 
     def users_of(step):
         b = (step * G + rank) % n_batches
         return b * B, (b + 1) * B
 
-    def one_step(batch, users_global, hist, gt):
-        model.train()
-        opt.zero_grad()
-        losses = diffusion.training_losses(model, batch, True, index=users_global)
-        loss = losses["loss"].mean()
-        loss.backward()
-        dist.all_reduce_gradients(model)
-        opt.step(grad_scale=1.0 / G)
-        model.eval()
-        idx = diffusion.rank(model, batch, k, hist=hist, index=users_global)
-        sums = evaluate_utils.metrics_from_device(idx, batch.users, gt[0], gt[1], topN)
-        return loss.detach(), idx, sums
+    def window_nnz(m):  # largest number of interactions in any batch window
+        ends = m.indptr[np.arange(1, n_batches + 1) * B]
+        starts = m.indptr[np.arange(0, n_batches) * B]
+        return int((ends - starts).max())
+
+    # The public step API: gdmcf_b200.engine.StepEngine = diffusion.training_losses -> backward -> (all-reduce) ->
+    # FusedAdamW.step -> diffusion.rank -> metrics_from_device, captured once as CUDA graph(s) around static inputs.
+    eng = StepEngine(model, diffusion, opt, dist, batch_size=B, n_item=n_item, topk=k, topN=topN,
+                     cap_train_nnz=window_nnz(train_sp), cap_gt_nnz=window_nnz(test_sp), reweight=True,
+                     graphs=not args.no_graphs)
+    eng.load_resident(train_dev, test_dev, *users_of(0))
+    eng.capture(warmup=3)
 
     def resident_step(step):
-        lo, hi = users_of(step)
-        users = torch.arange(lo, hi, dtype=torch.int32, device=dev)
-        return one_step(train_dev.batch(users), users, train_dev.csr, test_dev.csr)
+        eng.load_resident(train_dev, test_dev, *users_of(step))  # device-to-device slices of the resident CSR
+        return eng.step()
 
     # ---- e2e inputs: the step's rows in pinned host memory (CSR of train rows + ground-truth rows + user ids)
     def host_batch(step):
@@ -255,19 +257,13 @@ def run_engine(args):
         for name, m in (("tr", train_sp), ("te", test_sp)):
             rp = (m.indptr[lo:hi + 1] - m.indptr[lo]).astype(np.int32)
             cl = m.indices[m.indptr[lo]:m.indptr[hi]].astype(np.int32)
-            if cl.size == 0:
-                cl = np.zeros(1, np.int32)
             out[name] = (torch.from_numpy(rp).pin_memory(), torch.from_numpy(cl).pin_memory())
         out["users"] = torch.arange(lo, hi, dtype=torch.int32).pin_memory()
         return out
 
-    local_ids = torch.arange(B, dtype=torch.int32, device=dev)
-
     def e2e_step(hb):
-        nb = lambda t: t.to(dev, non_blocking=True)  # noqa: E731
-        tr_rp, tr_cl, te_rp, te_cl, users = nb(hb["tr"][0]), nb(hb["tr"][1]), nb(hb["te"][0]), nb(hb["te"][1]), nb(hb["users"])
-        batch = gd.CsrBatch(tr_rp, tr_cl, local_ids, n_item)
-        loss, idx, sums = one_step(batch, users, (tr_rp, tr_cl), (te_rp, te_cl))
+        eng.load_host(hb["users"], hb["tr"], hb["te"])  # host -> device copies of this step's inputs
+        loss, idx, sums = eng.step()
         return loss.cpu(), idx.cpu(), sums.cpu()  # device -> host read of the step's results
 
     def timed(fn, n_warm, n_steps, offset=0):
@@ -290,7 +286,10 @@ def run_engine(args):
         if G > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         host_ms.append(1e3 * (t_enq - t_wall0) / n_steps)
-        return ms.item(), lib.gdmcf_launch_count() - launches0, (t_wall0, t_wall1)
+        counted = lib.gdmcf_launch_count() - launches0
+        if eng.launches_per_step:  # graph replays do not pass through the library's launch counter
+            counted += eng.launches_per_step * n_steps
+        return ms.item(), counted, (t_wall0, t_wall1)
 
     host_ms = []
     Kst, W = args.steps, max(args.warmup, 3)
@@ -319,8 +318,12 @@ def run_engine(args):
     K.gemm = timed_gemm
     n_prof = 3
     for s in range(n_prof):
-        resident_step(2 * (W + Kst) + s)
-    torch.cuda.synchronize()
+        # same step, launched kernel by kernel (no graph) so that events can bracket every GEMM; a device-side spin
+        # first lets the host queue the whole step ahead, otherwise the intervals would include host enqueue gaps
+        eng.load_resident(train_dev, test_dev, *users_of(2 * (W + Kst) + s))
+        torch.cuda._sleep(int(2.5e7))
+        eng._eager_step()
+        torch.cuda.synchronize()
     K.gemm = orig_gemm
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in records)
     gemm_flops = sum(f for _, _, f, _ in records)
@@ -373,7 +376,8 @@ def run_engine(args):
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for s in range(3):
-                resident_step(3 * (W + Kst) + s)
+                eng.load_resident(train_dev, test_dev, *users_of(3 * (W + Kst) + s))
+                eng._eager_step()
             torch.cuda.synchronize()
         rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
         tot = sum(e.device_time_total for e in rows)
@@ -398,7 +402,8 @@ def run_engine(args):
                 "config": config_of(args, G), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": ms_e2e / Kst},
-                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms[0], "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "launches_per_step": int(launches) // Kst, "cuda_graphs": bool(eng.launches_per_step),
+                "host_enqueue_ms_per_step": host_ms[0], "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     dist.shutdown()
 

@@ -35,8 +35,8 @@ GD_DEV float2 ld_stream_f32x2(const float* p) {
   return v;
 }
 
-constexpr int GATHER_UNROLL = 8;
 constexpr int WARPS_PER_CTA = 8;
+constexpr int CTAS_PER_SM = 5;  // 40 warps per SM: the kernel hides L2 latency with thread-level parallelism
 
 GD_DEV float4 ld_stream_f32x4(const float* p) {
   float4 v;
@@ -44,72 +44,109 @@ GD_DEV float4 ld_stream_f32x4(const float* p) {
   return v;
 }
 
-// One warp per (work item, 64-column slab). The two half-warps take alternate non-zeros of the item and each lane
-// gathers a float4 (16 lanes x 16 B = one 256 B embedding row), so every gather instruction moves two rows and
-// 16 rows (4 KB) are in flight per warp; control flow stays warp-uniform. The halves are combined by shuffle.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+GD_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// The 32 lanes take the (col,val) pairs [base, base+n) of an item. Lanes past n hold a duplicate of the last column
+// with value 0, so the gather loop below needs no predicates (the duplicate row is an L1 hit).
+GD_DEV void load_pairs(const int* __restrict__ col, const float* __restrict__ val, int base, int n, int lane, int& c, float& v) {
+  c = 0;
+  v = 0.f;
+  if (n > 0) c = ld_stream_i32(col + base + min(lane, n - 1));
+  if (lane < n) v = ld_stream_f32(val + base + lane);
+}
+
+// acc += sum_j v_j * X[c_j, coff..coff+3]: the two half-warps take alternate non-zeros; each lane gathers a float4
+// (16 lanes x 16 B = one 256 B embedding row), 4 independent gathers per lane per trip; 8 instructions per 2 nnz.
+GD_DEV void gather_pairs(const float* __restrict__ Xs, long long ldx, int cc, float vv, int n, int half, float4& acc) {
+  const int ng = (n + 7) & ~7;
+#pragma unroll 1
+  for (int j0 = 0; j0 < ng; j0 += 8) {
+    float4 x[4];
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 2 * u + half;  // <= 31
+      const int c = __shfl_sync(0xffffffffu, cc, j);
+      v[u] = __shfl_sync(0xffffffffu, vv, j);
+      x[u] = __ldg(reinterpret_cast<const float4*>(Xs + (long long)c * ldx));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc.x = fmaf(v[u], x[u].x, acc.x);
+      acc.y = fmaf(v[u], x[u].y, acc.y);
+      acc.z = fmaf(v[u], x[u].z, acc.z);
+      acc.w = fmaf(v[u], x[u].w, acc.w);
+    }
+  }
+}
+
+// One warp per work item, items dealt round-robin to the resident warps. The item descriptor two items ahead (L1 prefetch) and the
+// first 32 (col,val) pairs one item ahead are requested before the current item's gathers, so the dependent chain
+// descriptor -> pairs -> rows costs one L2 round trip per item instead of three.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, const int4* __restrict__ items,
                   int n_items, const float* __restrict__ X, const float* __restrict__ Z, float* __restrict__ Y,
                   float* __restrict__ scratch, int d, float alpha, float beta) {
   const int lane = threadIdx.x & 31;
   const int half = lane >> 4, hl = lane & 15;
   const int slabs = d >> 6;
-  const long long total = (long long)n_items * slabs;
-  const long long warp0 = (long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * WARPS_PER_CTA;
-  for (long long w = warp0; w < total; w += nwarps) {
-    const int item = (int)(w / slabs);
-    const int coff = (int)(w % slabs) * 64 + hl * 4;
-    const int4 it = __ldg(&items[item]);  // {row, begin, end, slot}
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = it.y; base < it.z; base += 32) {
-      const int n = min(32, it.z - base);
-      int my_c = 0;
-      float my_v = 0.f;
-      if (lane < n) {
-        my_c = ld_stream_i32(col + base + lane);
-        my_v = ld_stream_f32(val + base + lane);
+  const int nwarps = gridDim.x * WARPS_PER_CTA;
+  int item = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  int4 it = __ldg(&items[item]);  // {row, begin, end, slot}
+  if (item + nwarps < n_items) prefetch_l1(&items[item + nwarps]);
+  int my_c;
+  float my_v;
+  load_pairs(col, val, it.y, min(32, it.z - it.y), lane, my_c, my_v);
+  while (true) {
+    const int item_n = item + nwarps;
+    int c_n = 0;
+    float v_n = 0.f;
+    if (item_n < n_items) {
+      const int4 nx = __ldg(&items[item_n]);  // L1 hit: prefetched one trip ago
+      load_pairs(col, val, nx.y, min(32, nx.z - nx.y), lane, c_n, v_n);
+      if (item_n + nwarps < n_items) prefetch_l1(&items[item_n + nwarps]);
+    }
+
+#pragma unroll 1
+    for (int slab = 0; slab < slabs; ++slab) {
+      const int coff = slab * 64 + hl * 4;
+      const float* Xs = X + coff;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int base = it.y;
+      int cc = my_c;
+      float vv = my_v;
+      while (true) {
+        gather_pairs(Xs, d, cc, vv, min(32, it.z - base), half, acc);
+        base += 32;
+        if (base >= it.z) break;
+        load_pairs(col, val, base, min(32, it.z - base), lane, cc, vv);
       }
-      for (int j0 = 0; j0 < n; j0 += 2 * GATHER_UNROLL) {
-        float4 x[GATHER_UNROLL];
-        float v[GATHER_UNROLL];
-#pragma unroll
-        for (int u = 0; u < GATHER_UNROLL; ++u) {
-          const int j = j0 + 2 * u + half;
-          const int c = __shfl_sync(0xffffffffu, my_c, j & 31);
-          const float vv = __shfl_sync(0xffffffffu, my_v, j & 31);
-          const bool ok = j < n;
-          v[u] = ok ? vv : 0.f;
-          x[u] = ok ? __ldg(reinterpret_cast<const float4*>(X + (long long)c * d + coff)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < GATHER_UNROLL; ++u) {
-          acc.x = fmaf(v[u], x[u].x, acc.x);
-          acc.y = fmaf(v[u], x[u].y, acc.y);
-          acc.z = fmaf(v[u], x[u].z, acc.z);
-          acc.w = fmaf(v[u], x[u].w, acc.w);
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+      if (half == 0) {
+        if (it.w < 0) {
+          float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+          if (Z) {
+            const float4 z = ld_stream_f32x4(Z + (long long)it.x * d + coff);
+            o.x = fmaf(beta, z.x, o.x);
+            o.y = fmaf(beta, z.y, o.y);
+            o.z = fmaf(beta, z.z, o.z);
+            o.w = fmaf(beta, z.w, o.w);
+          }
+          *reinterpret_cast<float4*>(Y + (long long)it.x * d + coff) = o;
+        } else {
+          *reinterpret_cast<float4*>(scratch + (long long)it.w * d + coff) = acc;
         }
       }
     }
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-    if (half == 0) {
-      if (it.w < 0) {
-        float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
-        if (Z) {
-          const float4 z = ld_stream_f32x4(Z + (long long)it.x * d + coff);
-          o.x = fmaf(beta, z.x, o.x);
-          o.y = fmaf(beta, z.y, o.y);
-          o.z = fmaf(beta, z.z, o.z);
-          o.w = fmaf(beta, z.w, o.w);
-        }
-        *reinterpret_cast<float4*>(Y + (long long)it.x * d + coff) = o;
-      } else {
-        *reinterpret_cast<float4*>(scratch + (long long)it.w * d + coff) = acc;
-      }
-    }
+    if (item_n >= n_items) break;
+    item = item_n;
+    it = __ldg(&items[item]);
+    my_c = c_n;
+    my_v = v_n;
   }
 }
 
@@ -186,7 +223,7 @@ __global__ void norm_adj_fill_kernel(const int* __restrict__ r_rowptr, const int
 static int grid_for_warps(long long warps) {
   const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
   const long long ctas = (warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sms * 16));
+  return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sms * CTAS_PER_SM));
 }
 
 }  // namespace spmm

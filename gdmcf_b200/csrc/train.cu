@@ -274,6 +274,65 @@ __global__ void lt_history_kernel(const long long* __restrict__ ts, const double
   }
 }
 
+// sample_timesteps(method="importance") of models/gaussian_diffusion.py:959-986 without leaving the device: while any
+// Lt_count[t] < H the draw is uniform with pt = 1 (:961-962); afterwards p = sqrt(mean(Lt_history^2)) normalised,
+// mixed with uniform_prob, t ~ Categorical(p) by inverse CDF, pt = p[t] * T (:964-978). One CTA; thread 0 builds the
+// CDF in index order (T <= 1024). ts_in != NULL: no draw, only pt for the given timesteps (parity tests inject ts).
+__global__ void __launch_bounds__(256)
+sample_timesteps_kernel(const double* __restrict__ hist, const long long* __restrict__ count, int T, int H, int B,
+                        double uniform_prob, uint64_t seed, uint64_t offset0, const uint64_t* __restrict__ epoch,
+                        const long long* __restrict__ ts_in, long long* __restrict__ ts, double* __restrict__ pt) {
+  __shared__ double s_p[1024];
+  __shared__ double s_cdf[1024];
+  int full = 1;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    full &= (count[t] == (long long)H) ? 1 : 0;
+    double acc = 0.0;
+    for (int j = 0; j < H; ++j) {
+      const double x = hist[(long long)t * H + j];
+      acc += x * x;
+    }
+    s_p[t] = sqrt(acc / (double)H);
+  }
+  const int ready = __syncthreads_and(full);
+  if (threadIdx.x == 0 && ready) {
+    double tot = 0.0;
+    for (int t = 0; t < T; ++t) tot += s_p[t];
+    double run = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const double p = s_p[t] / tot * (1.0 - uniform_prob) + uniform_prob / (double)T;
+      s_p[t] = p;
+      run += p;
+      s_cdf[t] = run;
+    }
+  }
+  __syncthreads();
+  const uint64_t offset = offset0 + (epoch ? (epoch[0] << 44) : 0ull);
+  const Philox rng(seed);
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    long long t;
+    if (ts_in) {
+      t = ts_in[b];
+    } else {
+      const uint4 g = rng(offset + (uint64_t)b, 7ull);
+      const double u = ((double)(g.x >> 5) * 67108864.0 + (double)(g.y >> 6)) * (1.0 / 9007199254740992.0);  // [0,1), 53 bits
+      if (ready) {
+        const double target = u * s_cdf[T - 1];
+        int lo = 0, hi = T - 1;
+        while (lo < hi) {  // first t with cdf[t] > target
+          const int mid = (lo + hi) >> 1;
+          if (s_cdf[mid] > target) hi = mid; else lo = mid + 1;
+        }
+        t = lo;
+      } else {
+        t = min((long long)(u * (double)T), (long long)T - 1);
+      }
+      ts[b] = t;
+    }
+    pt[b] = ready ? s_p[t] * (double)T : 1.0;
+  }
+}
+
 }  // namespace train
 }  // namespace gd
 
@@ -291,6 +350,21 @@ extern "C" int gdmcf_lt_history_update(const int64_t* ts, const double* loss, do
   lt_history_kernel<<<(steps + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(ts), loss, lt_history, reinterpret_cast<long long*>(lt_count), batch, steps, history);
   return cuda_check_launch("lt_history_kernel");
+}
+
+extern "C" int gdmcf_sample_timesteps(const double* lt_history, const int64_t* lt_count, int steps, int history, int batch,
+                                      double uniform_prob, uint64_t seed, uint64_t offset, const uint64_t* epoch_dev,
+                                      const int64_t* ts_in, int64_t* ts_out, double* pt_out, gdmcf_stream_t stream) {
+  if (!lt_history || !lt_count || !pt_out || (!ts_in && !ts_out) || steps <= 0 || steps > 1024 || history <= 0 || batch <= 0) {
+    set_error("sample_timesteps: bad arguments (steps <= 1024)");
+    return GDMCF_EBADARG;
+  }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  sample_timesteps_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      lt_history, reinterpret_cast<const long long*>(lt_count), steps, history, batch, uniform_prob, seed, offset, epoch_dev,
+      reinterpret_cast<const long long*>(ts_in), reinterpret_cast<long long*>(ts_out), pt_out);
+  return cuda_check_launch("sample_timesteps_kernel");
 }
 
 #define GD_PRE()                 \

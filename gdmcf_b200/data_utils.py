@@ -54,6 +54,7 @@ class DeviceInteractions:
         m.sum_duplicates()
         m.sort_indices()
         self.n_user, self.n_item = m.shape
+        self.rowptr_host = m.indptr.astype(np.int64)  # host copy: slice bounds without a device sync
         self.rowptr = torch.from_numpy(m.indptr.astype(np.int32)).to(device)
         self.col = torch.from_numpy(m.indices.astype(np.int32)).to(device)
         self.device = device

@@ -25,22 +25,21 @@ class Dist:
             td.all_reduce(t, op=td.ReduceOp.SUM)
         return t
 
-    def all_reduce_gradients(self, model: torch.nn.Module, bucket_bytes: int = 512 << 20) -> None:
-        """Sum gradients across ranks (the 1/world_size is folded into FusedAdamW's grad_scale). Gradients are
-        reduced in parameter order in large buckets so NCCL runs near bus bandwidth without a 1 GB staging copy
-        of the 400 MB embedding gradient (it is reduced in place)."""
+    def all_reduce_gradients(self, model: torch.nn.Module) -> None:
+        """Sum gradients across ranks (the 1/world_size is folded into FusedAdamW's grad_scale)."""
+        self.all_reduce_tensors([p.grad for p in model.parameters() if p.grad is not None])
+
+    def all_reduce_tensors(self, tensors) -> None:
+        """In-place all-reduce(SUM) of a list of tensors: large ones one by one (no 1 GB staging copy of the 400 MB
+        embedding gradient), the small ones flattened into one message."""
         if self.world_size == 1:
             return
-        small, small_bytes = [], 0
-        for p in model.parameters():
-            if p.grad is None:
-                continue
-            g = p.grad
+        small = []
+        for g in tensors:
             if g.numel() * g.element_size() >= (8 << 20):
                 td.all_reduce(g, op=td.ReduceOp.SUM)
             else:
                 small.append(g)
-                small_bytes += g.numel() * g.element_size()
         if small:
             flat = torch.cat([g.reshape(-1) for g in small])
             td.all_reduce(flat, op=td.ReduceOp.SUM)

@@ -15,10 +15,23 @@ import torch
 from . import kernels as K
 
 
+_topn_cache: dict = {}
+
+
+def _topn_dev(topN: Sequence[int], device) -> torch.Tensor:
+    """Cut-offs as a cached device tensor (a fresh torch.tensor(...) is a pageable H2D copy: illegal in graph capture)."""
+    key = (tuple(int(x) for x in topN), str(device))
+    t = _topn_cache.get(key)
+    if t is None:
+        t = torch.tensor(list(key[0]), dtype=torch.int32, device=device)
+        _topn_cache[key] = t
+    return t
+
+
 def metrics_from_device(topk_idx: torch.Tensor, users, gt_rowptr: torch.Tensor, gt_col: torch.Tensor, topN: Sequence[int]):
     """Per-cutoff sums [len(topN), 4] (precision, recall, NDCG, MRR numerators) as a float64 device tensor."""
     assert max(topN) <= topk_idx.shape[1], "topN[-1] exceeds the number of ranked items"
-    topn_dev = torch.tensor(list(topN), dtype=torch.int32, device=topk_idx.device)
+    topn_dev = _topn_dev(topN, topk_idx.device)
     stats = K.topn_metrics(topk_idx, users, gt_rowptr, gt_col, topn_dev, len(topN))
     return K.colsum_f64(stats).reshape(len(topN), 4)
 

@@ -239,12 +239,16 @@ def onehot_noise(x0, rows: int, cols: int, out: torch.Tensor, *, ts=None, discre
                                     offset, ptr(epoch), ptr(out), out.stride(0), rows, cols, stream()), "onehot_noise")
 
 
-def onehot_tables(w2: torch.Tensor, d: int, n_items: int):
+def onehot_tables(w2: torch.Tensor, d: int, n_items: int, out=None):
+    """out: optional (base, delta) pair from an earlier call, refreshed in place (stable addresses for CUDA graphs)."""
     require_cuda(w2)
     assert w2.dtype == torch.float32 and w2.stride(1) == 1
     ld_delta = round_up(d, 4)
-    base = torch.empty(d, dtype=torch.float32, device=w2.device)
-    delta = torch.empty(n_items, ld_delta, dtype=torch.float32, device=w2.device)
+    if out is not None and out[0].shape == (d,) and out[1].shape == (n_items, ld_delta) and out[0].device == w2.device:
+        base, delta = out
+    else:
+        base = torch.empty(d, dtype=torch.float32, device=w2.device)
+        delta = torch.empty(n_items, ld_delta, dtype=torch.float32, device=w2.device)
     # in_layers2.0.weight is [d, 2I + e]: its row stride is odd when e is; the kernel needs float2-aligned
     # (2i, 2i+1) pairs, so stage the [d, 2I] block with an even leading dimension first when required.
     if w2.stride(0) % 2 or w2.data_ptr() % 8:
@@ -260,13 +264,17 @@ def encode_onehot_gather(rowptr, col, users, n_rows: int, base, delta, d: int, o
                                             delta.stride(0), d, ptr(out), out.stride(0), stream()), "encode_onehot_gather")
 
 
-def time_bias_table(w_emb, b_emb, w_layer: torch.Tensor, n_in: int, bias, T: int):
-    """[T, d] table of first-layer biases; w_layer is the layer's full fp32 weight [d, n_in + e]."""
+def time_bias_table(w_emb, b_emb, w_layer: torch.Tensor, n_in: int, bias, T: int, out=None):
+    """[T, d] table of first-layer biases; w_layer is the layer's full fp32 weight [d, n_in + e].
+    out: optional (table, emb_table) pair from an earlier call, refreshed in place."""
     require_cuda(w_emb, b_emb, w_layer, bias)
     d, e = w_layer.shape[0], w_layer.shape[1] - n_in
     assert w_emb.shape == (e, e) and w_emb.is_contiguous() and w_layer.stride(1) == 1
-    emb_table = torch.empty(T, e, dtype=torch.float32, device=w_layer.device)
-    out = torch.empty(T, d, dtype=torch.float32, device=w_layer.device)
+    if out is not None and out[0].shape == (T, d) and out[1].shape == (T, e) and out[0].device == w_layer.device:
+        out, emb_table = out
+    else:
+        emb_table = torch.empty(T, e, dtype=torch.float32, device=w_layer.device)
+        out = torch.empty(T, d, dtype=torch.float32, device=w_layer.device)
     w_time = w_layer[:, n_in:]
     check(load().gdmcf_time_bias_table(ptr(w_emb), ptr(b_emb), w_time.data_ptr(), w_layer.stride(0), ptr(bias), T, e, d,
                                        ptr(emb_table), ptr(out), d, stream()), "time_bias_table")
@@ -426,6 +434,22 @@ def lt_history_update(ts, loss, lt_history, lt_count) -> None:
     assert ts.is_contiguous() and loss.is_contiguous() and lt_history.is_contiguous() and lt_count.is_contiguous()
     check(load().gdmcf_lt_history_update(ptr(ts), ptr(loss), ptr(lt_history), ptr(lt_count), ts.numel(), lt_history.shape[0],
                                          lt_history.shape[1], stream()), "lt_history_update")
+
+
+def sample_timesteps(lt_history, lt_count, batch: int, *, uniform_prob: float = 0.001, seed: int = 0, offset: int = 0,
+                     epoch=None, ts_in=None):
+    """Importance timestep sampling on the device (gaussian_diffusion.py:959-986). Returns (ts int64 [B], pt fp64 [B])."""
+    require_cuda(lt_history, lt_count, epoch, ts_in)
+    assert lt_history.dtype == torch.float64 and lt_count.dtype == torch.int64 and lt_history.is_contiguous()
+    dev = lt_history.device
+    if ts_in is not None:
+        assert ts_in.dtype == torch.int64 and ts_in.is_contiguous() and ts_in.numel() == batch
+    ts = ts_in if ts_in is not None else torch.empty(batch, dtype=torch.int64, device=dev)
+    pt = torch.empty(batch, dtype=torch.float64, device=dev)
+    check(load().gdmcf_sample_timesteps(ptr(lt_history), ptr(lt_count), lt_history.shape[0], lt_history.shape[1], batch,
+                                        uniform_prob, seed, offset, ptr(epoch), ptr(ts_in), ptr(ts), ptr(pt), stream()),
+          "sample_timesteps")
+    return ts, pt
 
 
 def counter_add(counter: torch.Tensor, inc: int = 1) -> None:

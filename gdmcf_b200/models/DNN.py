@@ -36,7 +36,10 @@ def _as_i32(t: torch.Tensor) -> torch.Tensor:
 
 
 class _OperandCache:
-    """bf16 (hi[, lo]) operand copies and derived tables, keyed by name, invalidated by parameter version."""
+    """bf16 (hi[, lo]) operand copies and derived tables, keyed by name, invalidated by parameter version.
+    `build(prev)` receives the stale value (or None) and refreshes it IN PLACE when shapes still match, so every
+    operand keeps its address for the life of the model: a captured CUDA graph that contains the refresh kernels
+    stays valid across optimizer steps."""
 
     def __init__(self):
         self._items: Dict[str, tuple] = {}
@@ -47,7 +50,7 @@ class _OperandCache:
         hit = self._items.get(name)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        val = build()
+        val = build(hit[1] if hit is not None else None)
         self._items[name] = (ver, val)
         return val
 
@@ -93,11 +96,14 @@ class _EngineModule(nn.Module):
             K.gemm([a.hi], [b.hi], m, n, [k], **epi)
 
     def _weight_operand(self, name: str, param: torch.Tensor, cols: Optional[int] = None, transpose: bool = False) -> Bf16Mat:
-        def build():
+        def build(prev):
             w = param.detach()
             if cols is not None:
                 w = w[:, :cols]
-            return (K.cast_bf16_transpose if transpose else K.cast_bf16)(w, with_lo=self._lo)
+            shape = (w.shape[1], w.shape[0]) if transpose else tuple(w.shape)
+            if prev is not None and ((prev.rows, prev.cols) != shape or prev.hi.device != w.device or (prev.lo is None) == self._lo):
+                prev = None
+            return (K.cast_bf16_transpose if transpose else K.cast_bf16)(w, with_lo=self._lo, out=prev)
         return self._ops.get(name + (".T" if transpose else "") + self.precision, [param], build)
 
     def __getstate__(self):  # torch.save(model) (main.py:375): drop device caches
@@ -152,8 +158,8 @@ class DNN(_EngineModule):
     def _tables(self, T: int):
         l0 = self.in_layers[0]
         return self._ops.get(f"tb{T}", [self.emb_layer.weight, self.emb_layer.bias, l0.weight, l0.bias],
-                             lambda: K.time_bias_table(self.emb_layer.weight.detach(), self.emb_layer.bias.detach(),
-                                                       l0.weight.detach(), self.n_item, l0.bias.detach(), T)[0])
+                             lambda prev: K.time_bias_table(self.emb_layer.weight.detach(), self.emb_layer.bias.detach(),
+                                                            l0.weight.detach(), self.n_item, l0.bias.detach(), T, out=prev))[0]
 
     # -- forward -------------------------------------------------------------------------------
     def _encode(self, x_op: Bf16Mat, B: int, ts, t_const: int, T: int, h_out: Bf16Mat, h_f32=None):
@@ -304,21 +310,21 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         e = self.emb_layer
         l1, l2 = self.in_layers[0], self.in_layers2[0]
         tb1 = self._ops.get(f"tb1.{T}", [e.weight, e.bias, l1.weight, l1.bias],
-                            lambda: K.time_bias_table(e.weight.detach(), e.bias.detach(), l1.weight.detach(), self.n_item,
-                                                      l1.bias.detach(), T)[0])
+                            lambda prev: K.time_bias_table(e.weight.detach(), e.bias.detach(), l1.weight.detach(), self.n_item,
+                                                           l1.bias.detach(), T, out=prev))[0]
         tb2 = self._ops.get(f"tb2.{T}", [e.weight, e.bias, l2.weight, l2.bias],
-                            lambda: K.time_bias_table(e.weight.detach(), e.bias.detach(), l2.weight.detach(), 2 * self.n_item,
-                                                      l2.bias.detach(), T)[0])
+                            lambda prev: K.time_bias_table(e.weight.detach(), e.bias.detach(), l2.weight.detach(),
+                                                           2 * self.n_item, l2.bias.detach(), T, out=prev))[0]
         return tb1, tb2
 
     def _onehot_tables(self):
         w2 = self.in_layers2[0].weight
-        return self._ops.get("onehot", [w2], lambda: K.onehot_tables(w2.detach(), self.hidden, self.n_item))
+        return self._ops.get("onehot", [w2], lambda prev: K.onehot_tables(w2.detach(), self.hidden, self.n_item, out=prev))
 
     def _item_operands(self):
         E = self.embedding_item.weight
         e_op = self._weight_operand("E", E)
-        inv = self._ops.get("E.inv", [E], lambda: K.row_inv_norm(E.detach()))
+        inv = self._ops.get("E.inv", [E], lambda prev: K.row_inv_norm(E.detach(), out=prev))
         return e_op, inv
 
     # -- pieces of the forward -----------------------------------------------------------------

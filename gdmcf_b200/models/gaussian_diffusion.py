@@ -218,6 +218,13 @@ class GaussianDiffusionDiscrete(nn.Module):
 
     # -- timestep sampling (gaussian_diffusion.py:959-986) ----------------------------------------
     def sample_timesteps(self, batch_size, device, method="uniform", uniform_prob=0.001):
+        if method == "importance" and self.Lt_history.is_cuda:
+            # one kernel, no host sync (the reference's `.all()` / multinomial checks synchronise every call):
+            # uniform with pt = 1 until every Lt_count reaches history_num_per_term, importance sampling afterwards
+            if self._epoch is None:
+                self._begin_step(self.Lt_history.device)
+            return K.sample_timesteps(self.Lt_history, self.Lt_count, batch_size, uniform_prob=uniform_prob, seed=self.seed,
+                                      offset=self._offset(), epoch=self._epoch)
         if method == "importance":
             if not self._importance_ready:
                 self._importance_ready = bool((self.Lt_count == self.history_num_per_term).all())
@@ -237,6 +244,8 @@ class GaussianDiffusionDiscrete(nn.Module):
         raise ValueError
 
     def _pt_for(self, ts):
+        if self.Lt_history.is_cuda:
+            return K.sample_timesteps(self.Lt_history, self.Lt_count, ts.numel(), ts_in=ts.contiguous())[1]
         if not self._importance_ready:
             self._importance_ready = bool((self.Lt_count == self.history_num_per_term).all())
         if not self._importance_ready:

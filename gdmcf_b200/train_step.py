@@ -38,7 +38,13 @@ def _temb_table(model, T, dev):
 def _time_cols(model, name, W, n_in):
     """Contiguous [d, e] copy of a first layer's time-embedding columns (cached per weight version): the strided
     view W[:, n_in:] would make every lane of the skinny contraction touch a different 137 KB-apart row."""
-    return model._ops.get(name + ".tcols", [W], lambda: W.detach()[:, n_in:].contiguous())
+    def build(prev):
+        src = W.detach()[:, n_in:]
+        if prev is not None and prev.shape == src.shape and prev.device == src.device:
+            prev.copy_(src)
+            return prev
+        return src.contiguous()
+    return model._ops.get(name + ".tcols", [W], build)
 
 
 def _mm_auto(model, a: Bf16Mat, b: Bf16Mat, m, n, k, **epi):

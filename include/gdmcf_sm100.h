@@ -293,6 +293,13 @@ int gdmcf_ntxent_rows(const float* S, int64_t ld_s, int n, float tau, float eps,
  * ts int64 [batch], loss fp64 [batch], lt_history fp64 [steps, history], lt_count int64 [steps]. */
 int gdmcf_lt_history_update(const int64_t* ts, const double* loss, double* lt_history, int64_t* lt_count, int batch,
                             int steps, int history, gdmcf_stream_t stream);
+/* sample_timesteps(method="importance") (models/gaussian_diffusion.py:959-986) on the device, no host sync:
+ * uniform draws with pt = 1 until every lt_count[t] == history, then t ~ Categorical(p), p = sqrt(mean(Lt_history^2))
+ * normalised and mixed with uniform_prob, pt = p[t] * steps. ts_in != NULL: only pt for the given timesteps.
+ * ts int64 [batch], pt fp64 [batch]; Philox counter = offset + (epoch_dev[0] << 44) + row. */
+int gdmcf_sample_timesteps(const double* lt_history, const int64_t* lt_count, int steps, int history, int batch,
+                           double uniform_prob, uint64_t seed, uint64_t offset, const uint64_t* epoch_dev,
+                           const int64_t* ts_in, int64_t* ts_out, double* pt_out, gdmcf_stream_t stream);
 /* grad[idx[r],:] += v[r,:] (dense nn.Embedding gradient rows, models/DNN.py:1265). */
 int gdmcf_scatter_rows_add(const float* v, int64_t ld_v, const int32_t* idx, float* grad, int64_t ld_g, int rows,
                            int cols, gdmcf_stream_t stream);

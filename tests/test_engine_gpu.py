@@ -1,0 +1,124 @@
+"""StepEngine (CUDA-graph replay of train + denoise + rank) must be the eager public API, bit for bit: two identical
+models are stepped over the same batches, one through graph replays, one kernel by kernel. Also the device-side
+timestep sampler (gaussian_diffusion.py:959-986) against its closed form."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(seed_model=0, U=700, I=1203, D=64, B=64, T=5, k=20):
+    from gdmcf_b200 import data_utils, dist_utils
+    from gdmcf_b200.engine import StepEngine
+    from gdmcf_b200.models import gaussian_diffusion as gd
+    from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    from gdmcf_b200.optim import FusedAdamW
+    dev = torch.device("cuda")
+    tr, va, te = data_utils.synthetic_interactions(U, I, 21000, 5)
+    n_user, n_item = int(tr[:, 0].max()) + 1, int(tr[:, 1].max()) + 1
+    mk = lambda p: sp.csr_matrix((np.ones(len(p), dtype=np.float32), (p[:, 0], p[:, 1])), shape=(n_user, n_item))  # noqa: E731
+    train_sp, test_sp = mk(tr), mk(te)
+    train_dev, test_dev = data_utils.DeviceInteractions(train_sp, dev), data_utils.DeviceInteractions(test_sp, dev)
+
+    def make(graphs):
+        torch.manual_seed(seed_model)
+        model = DNNOneHotEmbeddingGCN([n_item, D], [D, n_item], 10, item_num=n_item, user_num=n_user).to(dev)
+        diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, T, dev,
+                                            discrete=0.9995, CatOneHot=True)
+        diff.indexIn = True
+        diff.seed = model.seed = 77
+        opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0, modules=[model], capturable=True)
+        eng = StepEngine(model, diff, opt, dist_utils.Dist(), batch_size=B, n_item=n_item, topk=k, topN=[10, k],
+                         cap_train_nnz=int(train_sp.nnz), cap_gt_nnz=int(test_sp.nnz), graphs=graphs)
+        return model, diff, eng
+
+    return make, train_dev, test_dev, train_sp, test_sp, B, n_user
+
+
+def test_graph_step_equals_eager_step():
+    make, train_dev, test_dev, _, _, B, n_user = _setup()
+    m_g, d_g, e_g = make(True)
+    m_e, d_e, e_e = make(False)
+    for e in (e_g, e_e):
+        e.load_resident(train_dev, test_dev, 0, B)
+        e.capture(warmup=3)
+    assert e_g.launches_per_step > 50 and e_e.launches_per_step == 0
+    for s in range(1, 6):
+        lo = (s * B) % (n_user - B)
+        outs = []
+        for e in (e_g, e_e):
+            e.load_resident(train_dev, test_dev, lo, lo + B)
+            loss, idx, sums = e.step()
+            outs.append((loss.clone(), idx.clone(), sums.clone()))
+        (lg, ig, sg), (le, ie, se) = outs
+        assert torch.equal(lg, le), (s, lg.item(), le.item())
+        assert torch.equal(ig, ie)
+        assert torch.equal(sg, se)
+    for (n, pg), (_, pe) in zip(m_g.named_parameters(), m_e.named_parameters()):
+        assert torch.equal(pg, pe), n
+    assert torch.equal(d_g.Lt_history, d_e.Lt_history) and torch.equal(d_g.Lt_count, d_e.Lt_count)
+    # the eager API stays coherent after replays: an eager rank on the graph-stepped model equals the eager model's
+    from gdmcf_b200.models.gaussian_diffusion import CsrBatch
+    users = torch.arange(5, 5 + B, dtype=torch.int32, device="cuda")
+    batch = train_dev.batch(users)
+    m_g.eval(); m_e.eval()
+    assert isinstance(batch, CsrBatch)
+    assert torch.equal(d_g.rank(m_g, batch, 20, hist=train_dev.csr), d_e.rank(m_e, batch, 20, hist=train_dev.csr))
+
+
+def test_graph_step_host_inputs_match_resident():
+    make, train_dev, test_dev, train_sp, test_sp, B, n_user = _setup(seed_model=1)
+    _, _, e_a = make(True)
+    _, _, e_b = make(True)
+    for e in (e_a, e_b):
+        e.load_resident(train_dev, test_dev, 0, B)
+        e.capture(warmup=2)
+    lo, hi = 130, 130 + B
+    e_a.load_resident(train_dev, test_dev, lo, hi)
+    hb = []
+    for m in (train_sp, test_sp):
+        rp = (m.indptr[lo:hi + 1] - m.indptr[lo]).astype(np.int32)
+        cl = m.indices[m.indptr[lo]:m.indptr[hi]].astype(np.int32)
+        hb.append((torch.from_numpy(rp).pin_memory(), torch.from_numpy(cl).pin_memory()))
+    e_b.load_host(torch.arange(lo, hi, dtype=torch.int32).pin_memory(), hb[0], hb[1])
+    la, ia, sa = e_a.step()
+    lb, ib, sb = e_b.step()
+    assert torch.equal(la, lb) and torch.equal(ia, ib) and torch.equal(sa, sb)
+
+
+def test_sample_timesteps_kernel():
+    from gdmcf_b200 import kernels as K
+    T, H, B = 7, 10, 200000
+    g = torch.Generator().manual_seed(3)
+    hist = (torch.rand(T, H, generator=g, dtype=torch.float64) * 3).cuda()
+    full = torch.full((T,), H, dtype=torch.int64, device="cuda")
+    epoch = torch.tensor([5], dtype=torch.int64, device="cuda")
+    ts, pt = K.sample_timesteps(hist, full, B, uniform_prob=0.001, seed=11, offset=1 << 40, epoch=epoch)
+    p = torch.sqrt((hist ** 2).mean(-1))
+    p = p / p.sum() * (1 - 0.001) + 0.001 / T
+    assert ts.min() >= 0 and ts.max() < T
+    torch.testing.assert_close(pt, p[ts] * T, rtol=1e-12, atol=0)
+    freq = torch.bincount(ts, minlength=T).double() / B
+    # binomial 5-sigma band per timestep
+    sigma = torch.sqrt(p * (1 - p) / B)
+    assert ((freq - p).abs() < 5 * sigma).all(), (freq, p)
+    # fresh draws per epoch, same draws for the same epoch
+    ts2, _ = K.sample_timesteps(hist, full, B, seed=11, offset=1 << 40, epoch=epoch)
+    assert torch.equal(ts, ts2)
+    epoch += 1
+    ts3, _ = K.sample_timesteps(hist, full, B, seed=11, offset=1 << 40, epoch=epoch)
+    assert not torch.equal(ts, ts3)
+    # history not full yet -> uniform draws, pt = 1 (gaussian_diffusion.py:961-962)
+    part = full.clone()
+    part[3] = H - 1
+    tu, pu = K.sample_timesteps(hist, part, B, seed=11, offset=1 << 40, epoch=epoch)
+    assert (pu == 1).all()
+    fu = torch.bincount(tu, minlength=T).double() / B
+    assert ((fu - 1.0 / T).abs() < 5 * (1.0 / T * (1 - 1.0 / T) / B) ** 0.5).all()
+    # injected timesteps: only pt
+    tin = torch.randint(0, T, (B,), device="cuda")
+    t_same, p_in = K.sample_timesteps(hist, full, B, ts_in=tin)
+    assert t_same is tin
+    torch.testing.assert_close(p_in, p[tin] * T, rtol=1e-12, atol=0)
