@@ -32,6 +32,7 @@ WORKLOADS = {  # name: (n_user, n_item, n_pairs, seed)
     "tiny": (2000, 1500, 40000, 3),
 }
 METRIC = "users/sec train+denoise+rank (Yelp shape)"
+OUT = sys.stdout
 
 
 def parse():
@@ -178,7 +179,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "users/s", "cores": arm.cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ======================================================================================================
@@ -198,7 +199,6 @@ def run_engine(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (engine arm) needs a CUDA device; there is no CPU fallback")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's banner off stdout (one JSON line only)
     dist = dist_utils.init("nccl")
     G, rank = dist.world_size, dist.rank
     assert G == max(args.gpus, 1) or G == 1, f"--gpus {args.gpus} but WORLD_SIZE={G}"
@@ -404,12 +404,15 @@ def run_engine(args):
                         "ms_per_step": ms_e2e / Kst},
                 "gpu_launches": int(launches), "launches_per_step": int(launches) // Kst, "cuda_graphs": bool(eng.launches_per_step),
                 "host_enqueue_ms_per_step": host_ms[0], "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     dist.shutdown()
 
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly one JSON line: anything a library prints to fd 1 (NCCL's version banner) goes to stderr
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

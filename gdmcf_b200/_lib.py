@@ -59,6 +59,19 @@ class Epilogue(C.Structure):
     ]
 
 
+class Refresh(C.Structure):
+    _fields_ = [
+        ("cols_used", C.c_int32),
+        ("n_tcols", C.c_int32),
+        ("hi", C.c_void_p), ("lo", C.c_void_p), ("ld_hi", C.c_int64),
+        ("t_hi", C.c_void_p), ("t_lo", C.c_void_p), ("ld_t", C.c_int64),
+        ("inv_norm", C.c_void_p),
+        ("delta", C.c_void_p), ("ld_delta", C.c_int64), ("base", C.c_void_p),
+        ("tcols", C.c_void_p),
+        ("rowpart", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/gdmcf_sm100.h declares.
 _P, _I, _L, _F, _U64, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t
 SIGNATURES = {
@@ -94,6 +107,8 @@ SIGNATURES = {
     "gdmcf_mse_rows": (_I, [_P, _L, _P, _L, _I, _I, _P, _P]),
     "gdmcf_adamw_fused": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
     "gdmcf_counter_add": (_I, [_P, _U64, _P]),
+    "gdmcf_adamw_refresh_splits": (_I, [_I, _I]),
+    "gdmcf_adamw_refresh": (_I, [_P, _P, _L, _P, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _F, C.POINTER(Refresh), _P]),
     "gdmcf_loss_grad": (_I, [_P, _L, _P, _L, _P, _P, _P, _I, _P, _P, _L, _P, _P, _L, _P, _P, _I, _I, _P]),
     "gdmcf_transpose_bf16": (_I, [_P, _L, _P, _L, _I, _I, _P]),
     "gdmcf_ew_binary": (_I, [_I, _P, _L, _P, _L, _F, _F, _P, _L, _P, _P, _L, _I, _I, _P]),

@@ -201,6 +201,39 @@ GD_DEV float2 box_muller(uint32_t a, uint32_t b) {
   return make_float2(r * c, r * s);
 }
 
+// One AdamW element update (torch.optim.AdamW, amsgrad=False, maximize=False) with every rounding spelled out, so that
+// the flat kernel and the fused update+refresh kernels produce bit-identical parameters whatever the compiler would
+// otherwise contract into FMAs.
+struct AdamwCoef {
+  float decay, one_m_b1, beta2, one_m_b2, eps, step_size, bc2_sqrt, gscale;
+};
+GD_DEV void adamw_update(const AdamwCoef& k, float& param, float gr, float& mi, float& vi) {
+  const float grad = __fmul_rn(gr, k.gscale);
+  param = __fmul_rn(param, k.decay);
+  mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(grad, mi), k.one_m_b1));                          // exp_avg.lerp_(grad, 1 - beta1)
+  vi = __fadd_rn(__fmul_rn(vi, k.beta2), __fmul_rn(__fmul_rn(k.one_m_b2, grad), grad));    // mul_(b2).addcmul_(g, g, 1 - b2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), k.bc2_sqrt), k.eps);
+  param = __fsub_rn(param, __fmul_rn(k.step_size, __fdiv_rn(mi, denom)));
+}
+GD_DEV AdamwCoef adamw_coef(float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+                            float grad_scale, const long long* step_dev) {
+  if (step_dev) {  // bias corrections from a device-resident step counter (CUDA-graph replays advance it on the device)
+    const double st = (double)step_dev[0];
+    bc1 = (float)(1.0 - pow((double)beta1, st));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, st));
+  }
+  AdamwCoef k;
+  k.decay = 1.0f - lr * weight_decay;
+  k.one_m_b1 = 1.0f - beta1;
+  k.beta2 = beta2;
+  k.one_m_b2 = 1.0f - beta2;
+  k.eps = eps;
+  k.step_size = lr / bc1;
+  k.bc2_sqrt = bc2_sqrt;
+  k.gscale = grad_scale;
+  return k;
+}
+
 GD_DEV float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

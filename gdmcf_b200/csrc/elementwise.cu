@@ -381,13 +381,32 @@ __global__ void row_inv_norm_kernel(const float* __restrict__ x, long long ld, f
   }
 }
 
-__global__ void mse_rows_kernel(const float* __restrict__ out, long long ld_out, const float* __restrict__ x0,
-                                long long ld_x0, int rows, int cols, float* __restrict__ mse) {
-  __shared__ float red[TPB / 32];
+// mean_flat((x0 - out)^2) per row (gaussian_diffusion.py:902,1194-1198): 512 threads per row, 16 B loads when both
+// matrices have 16 B-aligned rows (the engine's [B, ld4] buffers do), fixed summation order per launch geometry.
+__global__ void __launch_bounds__(512)
+mse_rows_kernel(const float* __restrict__ out, long long ld_out, const float* __restrict__ x0, long long ld_x0, int rows,
+                int cols, float* __restrict__ mse) {
+  __shared__ float red[16];
+  const bool vec = (((ld_out | ld_x0) & 3) == 0) && ((((uintptr_t)out | (uintptr_t)x0) & 15) == 0);
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* po = out + (long long)r * ld_out;
+    const float* px = x0 + (long long)r * ld_x0;
     float ss = 0.f;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-      const float dlt = x0[(long long)r * ld_x0 + c] - out[(long long)r * ld_out + c];
+    int c_begin = 0;
+    if (vec) {
+      const int n4 = cols >> 2;
+      const float4* po4 = reinterpret_cast<const float4*>(po);
+      const float4* px4 = reinterpret_cast<const float4*>(px);
+#pragma unroll 4
+      for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 a = __ldg(px4 + i), b = __ldg(po4 + i);
+        const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+        ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      }
+      c_begin = n4 << 2;
+    }
+    for (int c = c_begin + threadIdx.x; c < cols; c += blockDim.x) {
+      const float dlt = px[c] - po[c];
       ss += dlt * dlt;
     }
     const float tot = block_sum(ss, red);
@@ -402,21 +421,8 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
                              float weight_decay, float bc1, float bc2_sqrt, float grad_scale,
                              const long long* __restrict__ step_dev) {
-  if (step_dev) {  // bias corrections from a device-resident step counter (CUDA-graph replays advance it on the device)
-    const double st = (double)step_dev[0];
-    bc1 = (float)(1.0 - pow((double)beta1, st));
-    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, st));
-  }
-  const float step_size = lr / bc1;
-  const float decay = 1.0f - lr * weight_decay;
-  auto update = [&](float& param, float gr, float& mi, float& vi) {
-    const float grad = gr * grad_scale;
-    param *= decay;
-    mi = mi + (grad - mi) * (1.0f - beta1);                // exp_avg.lerp_(grad, 1 - beta1)
-    vi = vi * beta2 + (1.0f - beta2) * grad * grad;        // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    param -= step_size * (mi / denom);
-  };
+  const AdamwCoef kc = adamw_coef(lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, step_dev);
+  auto update = [&](float& param, float gr, float& mi, float& vi) { adamw_update(kc, param, gr, mi, vi); };
   // 128-bit streams (all four tensors are 16 B aligned: checked on the host), scalar tail
   const long long n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
@@ -573,7 +579,7 @@ extern "C" int gdmcf_mse_rows(const float* out, int64_t ld_out, const float* x0,
                               float* mse, gdmcf_stream_t stream) {
   if (!out || !x0 || !mse || rows <= 0 || cols <= 0 || ld_out < cols || ld_x0 < cols) { set_error("mse_rows: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
-  mse_rows_kernel<<<grid_1d(rows, 1), TPB, 0, st>>>(out, ld_out, x0, ld_x0, rows, cols, mse);
+  mse_rows_kernel<<<grid_1d(rows, 1), 512, 0, st>>>(out, ld_out, x0, ld_x0, rows, cols, mse);
   return cuda_check_launch("mse_rows_kernel");
 }
 

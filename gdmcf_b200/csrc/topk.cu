@@ -40,20 +40,47 @@ struct RowView {
   }
 };
 
+constexpr int CAND_CAP = 2048;  // candidate slots of the threshold path (>= MAX_K)
+
+// Bitonic sort of n (power of two) (key, idx) pairs in shared memory, descending by key, ties by ascending idx.
+GD_DEV void bitonic_desc(uint32_t* key, uint32_t* idx, int n, int tid) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < n; i += TPB) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const uint32_t ki = key[i], kj = key[j], ii = idx[i], ij = idx[j];
+          const bool i_before_j = (ki > kj) || (ki == kj && ii < ij);  // desired order: i first
+          const bool desc = ((i & size) == 0);
+          if (desc ? !i_before_j : i_before_j) {
+            key[i] = kj; key[j] = ki; idx[i] = ij; idx[j] = ii;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Threshold path (k <= TPB): every thread keeps the maximum of its strided slice; the k-th largest of the TPB slice
+// maxima is a lower bound L of the k-th largest key of the row (k distinct elements are >= L), so the exact top-k is
+// among the elements >= L — a few dozen for real score rows. Two coalesced passes over the row, no histogram atomics.
+// Rows where more than CAND_CAP elements reach L (massive ties) fall back to the exact 4-pass radix select.
 __global__ void __launch_bounds__(TPB)
 mask_topk_kernel(const float* __restrict__ scores, long long ld, int n_rows, int n_items, const int* __restrict__ users,
                  const int* __restrict__ h_rowptr, const int* __restrict__ h_col, const int* __restrict__ h_rowptr2,
                  const int* __restrict__ h_col2, int k, int kpad, int stage_keys, int* __restrict__ out_idx,
                  float* __restrict__ out_val) {
   extern __shared__ uint32_t sm[];
-  // layout: hist[256] | ctrl[8] | scan[TPB] | cand_key[kpad] | cand_idx[kpad] | bitmap[words] | keys[n_items]?
+  // layout: hist[256] | ctrl[8] | scan[TPB] | scan_idx[TPB] | cand_key[CAND_CAP] | cand_idx[CAND_CAP] | bitmap[words] | keys[n_items]?
   uint32_t* hist = sm;
   uint32_t* ctrl = hist + 256;
   uint32_t* scan = ctrl + 8;
-  uint32_t* cand_key = scan + TPB;
-  uint32_t* cand_idx = cand_key + kpad;
+  uint32_t* scan_idx = scan + TPB;
+  uint32_t* cand_key = scan_idx + TPB;
+  uint32_t* cand_idx = cand_key + CAND_CAP;
   const int words = (n_items + 31) >> 5;
-  uint32_t* bitmap = cand_idx + kpad;
+  uint32_t* bitmap = cand_idx + CAND_CAP;
   uint32_t* keys = stage_keys ? bitmap + words : nullptr;
   const int tid = threadIdx.x;
 
@@ -76,112 +103,134 @@ mask_topk_kernel(const float* __restrict__ scores, long long ld, int n_rows, int
       }
     }
     __syncthreads();
-    if (keys) {
+    RowView rv{row, keys, bitmap};
+    int n_sort = 0;  // number of candidate slots to sort (power of two); 0 -> radix fallback
+
+    if (k <= TPB) {
+      // ---- pass 1: slice maxima (and key staging when the row fits in shared memory)
+      uint32_t tmax = 0u;
+#pragma unroll 4
+      for (int i = tid; i < n_items; i += TPB) {
+        const uint32_t kk = (bitmap[i >> 5] & (1u << (i & 31))) ? 0u : f32_key(__ldg(row + i));
+        if (keys) keys[i] = kk;
+        tmax = max(tmax, kk);
+      }
+      scan[tid] = tmax;
+      scan_idx[tid] = (uint32_t)tid;
+      if (tid == 0) ctrl[2] = 0u;
+      __syncthreads();
+      bitonic_desc(scan, scan_idx, TPB, tid);
+      const uint32_t L = scan[k - 1];
+      // ---- pass 2: collect everything >= L
+      if (L > 0u) {
+#pragma unroll 4
+        for (int i = tid; i < n_items; i += TPB) {
+          const uint32_t kk = rv.key(i);
+          if (kk >= L) {
+            const uint32_t slot = atomicAdd(&ctrl[2], 1u);
+            if (slot < (uint32_t)CAND_CAP) { cand_key[slot] = kk; cand_idx[slot] = (uint32_t)i; }
+          }
+        }
+      }
+      __syncthreads();
+      const uint32_t cnt = ctrl[2];
+      if (L > 0u && cnt <= (uint32_t)CAND_CAP) {
+        n_sort = 2;
+        while (n_sort < (int)cnt) n_sort <<= 1;
+        for (int i = (int)cnt + tid; i < n_sort; i += TPB) { cand_key[i] = 0u; cand_idx[i] = 0x7FFFFFFFu; }
+      }
+      __syncthreads();
+    } else if (keys) {
       for (int i = tid; i < n_items; i += TPB)
         keys[i] = (bitmap[i >> 5] & (1u << (i & 31))) ? 0u : f32_key(row[i]);
       __syncthreads();
     }
-    RowView rv{row, keys, bitmap};
 
-    // ---- radix select of the k-th largest key
-    uint32_t prefix = 0u, known = 0u;
-    int remaining = k;
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = 24 - 8 * pass;
-      for (int b = tid; b < 256; b += TPB) hist[b] = 0u;
-      __syncthreads();
-      for (int i = tid; i < n_items; i += TPB) {
-        const uint32_t kk = rv.key(i);
-        if ((kk & known) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
-      }
-      __syncthreads();
-      if (tid < 32) {
-        // warp 0: lanes own 8 bins each, scanned from the top bin down
-        uint32_t local[8];
-        uint32_t lsum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { local[j] = hist[255 - (tid * 8 + j)]; lsum += local[j]; }
-        uint32_t incl = lsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-          if (tid >= o) incl += n;
+    if (n_sort == 0) {
+      // ---- exact radix select of the k-th largest key (4 passes of 8 bits)
+      uint32_t prefix = 0u, known = 0u;
+      int remaining = k;
+      for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int b = tid; b < 256; b += TPB) hist[b] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n_items; i += TPB) {
+          const uint32_t kk = rv.key(i);
+          if ((kk & known) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
         }
-        uint32_t before = incl - lsum;  // count in bins above this lane's range
-        if (before < (uint32_t)remaining && incl >= (uint32_t)remaining) {
-          uint32_t cum = before;
+        __syncthreads();
+        if (tid < 32) {
+          // warp 0: lanes own 8 bins each, scanned from the top bin down
+          uint32_t local[8];
+          uint32_t lsum = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (cum < (uint32_t)remaining && cum + local[j] >= (uint32_t)remaining) {
-              ctrl[0] = 255 - (tid * 8 + j);
-              ctrl[1] = cum;
-            }
-            cum += local[j];
+          for (int j = 0; j < 8; ++j) { local[j] = hist[255 - (tid * 8 + j)]; lsum += local[j]; }
+          uint32_t incl = lsum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += n;
           }
-        }
-      }
-      __syncthreads();
-      prefix |= ctrl[0] << shift;
-      known |= 255u << shift;
-      remaining -= (int)ctrl[1];
-      __syncthreads();
-    }
-    // prefix = key of the k-th largest element; `remaining` of the elements equal to it are selected.
-
-    // ---- collect
-    for (int i = tid; i < kpad; i += TPB) { cand_key[i] = 0u; cand_idx[i] = 0x7FFFFFFFu; }
-    if (tid == 0) ctrl[2] = 0u;
-    __syncthreads();
-    for (int i = tid; i < n_items; i += TPB) {
-      const uint32_t kk = rv.key(i);
-      if (kk > prefix) {
-        const uint32_t slot = atomicAdd(&ctrl[2], 1u);
-        cand_key[slot] = kk;
-        cand_idx[slot] = (uint32_t)i;
-      }
-    }
-    // ties: ordered by item id. Each thread owns a contiguous index range.
-    const int per = (n_items + TPB - 1) / TPB;
-    const int lo = min(n_items, tid * per), hi = min(n_items, lo + per);
-    uint32_t mine = 0;
-    for (int i = lo; i < hi; ++i) mine += (rv.key(i) == prefix) ? 1u : 0u;
-    scan[tid] = mine;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over TPB entries
-    for (int o = 1; o < TPB; o <<= 1) {
-      const uint32_t v = (tid >= o) ? scan[tid - o] : 0u;
-      __syncthreads();
-      scan[tid] += v;
-      __syncthreads();
-    }
-    const uint32_t n_gt = ctrl[2];  // == k - remaining
-    uint32_t rank = scan[tid] - mine;
-    for (int i = lo; i < hi && rank < (uint32_t)remaining; ++i) {
-      if (rv.key(i) == prefix) {
-        cand_key[n_gt + rank] = prefix;
-        cand_idx[n_gt + rank] = (uint32_t)i;
-        ++rank;
-      }
-    }
-    __syncthreads();
-
-    // ---- bitonic sort of kpad candidates, descending by (key, -idx)
-    for (int size = 2; size <= kpad; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = tid; i < kpad; i += TPB) {
-          const int j = i ^ stride;
-          if (j > i) {
-            const uint32_t ki = cand_key[i], kj = cand_key[j], ii = cand_idx[i], ij = cand_idx[j];
-            const bool i_before_j = (ki > kj) || (ki == kj && ii < ij);  // desired order: i first
-            const bool desc = ((i & size) == 0);
-            if (desc ? !i_before_j : i_before_j) {
-              cand_key[i] = kj; cand_key[j] = ki; cand_idx[i] = ij; cand_idx[j] = ii;
+          uint32_t before = incl - lsum;  // count in bins above this lane's range
+          if (before < (uint32_t)remaining && incl >= (uint32_t)remaining) {
+            uint32_t cum = before;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (cum < (uint32_t)remaining && cum + local[j] >= (uint32_t)remaining) {
+                ctrl[0] = 255 - (tid * 8 + j);
+                ctrl[1] = cum;
+              }
+              cum += local[j];
             }
           }
         }
         __syncthreads();
+        prefix |= ctrl[0] << shift;
+        known |= 255u << shift;
+        remaining -= (int)ctrl[1];
+        __syncthreads();
       }
+      // prefix = key of the k-th largest element; `remaining` of the elements equal to it are selected.
+      for (int i = tid; i < kpad; i += TPB) { cand_key[i] = 0u; cand_idx[i] = 0x7FFFFFFFu; }
+      if (tid == 0) ctrl[2] = 0u;
+      __syncthreads();
+      for (int i = tid; i < n_items; i += TPB) {
+        const uint32_t kk = rv.key(i);
+        if (kk > prefix) {
+          const uint32_t slot = atomicAdd(&ctrl[2], 1u);
+          cand_key[slot] = kk;
+          cand_idx[slot] = (uint32_t)i;
+        }
+      }
+      // ties: ordered by item id. Each thread owns a contiguous index range.
+      const int per = (n_items + TPB - 1) / TPB;
+      const int lo = min(n_items, tid * per), hi = min(n_items, lo + per);
+      uint32_t mine = 0;
+      for (int i = lo; i < hi; ++i) mine += (rv.key(i) == prefix) ? 1u : 0u;
+      scan[tid] = mine;
+      __syncthreads();
+      // Hillis-Steele inclusive scan over TPB entries
+      for (int o = 1; o < TPB; o <<= 1) {
+        const uint32_t v = (tid >= o) ? scan[tid - o] : 0u;
+        __syncthreads();
+        scan[tid] += v;
+        __syncthreads();
+      }
+      const uint32_t n_gt = ctrl[2];  // == k - remaining
+      uint32_t rank = scan[tid] - mine;
+      for (int i = lo; i < hi && rank < (uint32_t)remaining; ++i) {
+        if (rv.key(i) == prefix) {
+          cand_key[n_gt + rank] = prefix;
+          cand_idx[n_gt + rank] = (uint32_t)i;
+          ++rank;
+        }
+      }
+      __syncthreads();
+      n_sort = kpad;
     }
+
+    // ---- sort the candidates, descending by (key, -idx); the first k are the answer
+    bitonic_desc(cand_key, cand_idx, n_sort, tid);
     for (int i = tid; i < k; i += TPB) {
       out_idx[(long long)r * k + i] = (int)cand_idx[i];
       if (out_val) out_val[(long long)r * k + i] = key_f32(cand_key[i]);
@@ -290,11 +339,13 @@ extern "C" int gdmcf_mask_topk(const float* scores, int64_t ld, int n_rows, int 
   int kpad = 2;
   while (kpad < k) kpad <<= 1;
   const int words = (n_items + 31) >> 5;
-  const size_t base_bytes = (size_t)(256 + 8 + TPB + 2 * kpad + words) * 4;
+  const size_t base_bytes = (size_t)(256 + 8 + 2 * TPB + 2 * CAND_CAP + words) * 4;
   const size_t staged_bytes = base_bytes + (size_t)n_items * 4;
   const size_t limit = 200 * 1024;
   if (base_bytes > limit) { set_error("mask_topk: catalogue too wide for the history bitmap (%d items)", n_items); return GDMCF_EBADARG; }
-  const int stage = staged_bytes <= limit ? 1 : 0;
+  // Keys are staged in shared memory only on the radix-only path (k > 512); the threshold path re-reads the L2-resident
+  // row once instead, which keeps shared memory at ~25 KB and four CTAs resident per SM.
+  const int stage = (k > TPB && staged_bytes <= limit) ? 1 : 0;
   const size_t smem = stage ? staged_bytes : base_bytes;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {

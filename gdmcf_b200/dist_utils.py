@@ -36,6 +36,9 @@ class Dist:
             return
         small = []
         for g in tensors:
+            if not g.is_contiguous():  # [rows, cols] view of a padded [rows, ld] wgrad buffer: reduce the whole buffer
+                assert g.dim() == 2 and g.stride(1) == 1
+                g = g.as_strided((g.shape[0], g.stride(0)), (g.stride(0), 1))
             if g.numel() * g.element_size() >= (8 << 20):
                 td.all_reduce(g, op=td.ReduceOp.SUM)
             else:

@@ -382,6 +382,38 @@ def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.9
                                    ptr(step_dev), grad_scale, stream()), "adamw_fused")
 
 
+def adamw_refresh(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                  weight_decay: float = 0.0, step: int = 1, step_dev=None, grad_scale: float = 1.0, cols_used: int = 0,
+                  op: Optional[Bf16Mat] = None, op_t: Optional[Bf16Mat] = None, inv_norm=None, delta=None, base=None,
+                  tcols=None, rowpart=None) -> None:
+    """AdamW on a 2-D weight fused with the refresh of its derived tensors (gdmcf_adamw_refresh). g may be a
+    [rows, cols] view with a padded leading dimension."""
+    require_cuda(p, g, m, v, inv_norm, delta, base, tcols, rowpart)
+    assert p.dim() == 2 and p.is_contiguous() and m.is_contiguous() and v.is_contiguous() and g.shape == p.shape and g.stride(1) == 1
+    rows, cols = p.shape
+    r = _lib.Refresh()
+    r.cols_used = cols_used
+    if op is not None:
+        r.hi, r.lo, r.ld_hi = ptr(op.hi), ptr(op.lo), op.ld
+    if op_t is not None:
+        r.t_hi, r.t_lo, r.ld_t = ptr(op_t.hi), ptr(op_t.lo), op_t.ld
+    r.inv_norm = ptr(inv_norm)
+    if delta is not None:
+        r.delta, r.ld_delta, r.base = ptr(delta), delta.stride(0), ptr(base)
+    if tcols is not None:
+        assert tcols.is_contiguous()
+        r.tcols, r.n_tcols = ptr(tcols), tcols.shape[1]
+    if inv_norm is not None or delta is not None:
+        assert rowpart is not None and rowpart.numel() >= adamw_refresh_splits(rows, cols) * rows
+        r.rowpart = ptr(rowpart)
+    check(load().gdmcf_adamw_refresh(ptr(p), ptr(g), g.stride(0), ptr(m), ptr(v), rows, cols, lr, beta1, beta2, eps,
+                                     weight_decay, step, ptr(step_dev), grad_scale, C.byref(r), stream()), "adamw_refresh")
+
+
+def adamw_refresh_splits(rows: int, cols: int) -> int:
+    return load().gdmcf_adamw_refresh_splits(rows, cols)
+
+
 def loss_grad(out, x0, gs, rows: int, cols: int, G: Bf16Mat, *, GT: Optional[Bf16Mat] = None, row_scale=None,
               col_scale=None, with_out: bool = False, colsum=None, rowpart=None) -> None:
     require_cuda(out, x0, gs, G.hi, row_scale, col_scale, colsum, rowpart)

@@ -54,6 +54,17 @@ class _OperandCache:
         self._items[name] = (ver, val)
         return val
 
+    def peek(self, name: str):
+        """The cached value (possibly stale) or None."""
+        hit = self._items.get(name)
+        return hit[1] if hit is not None else None
+
+    def mark_fresh(self, name: str, params) -> None:
+        """The value was refreshed in place by someone else (FusedAdamW's fused refresh): adopt the current version."""
+        hit = self._items.get(name)
+        if hit is not None:
+            self._items[name] = ((self.epoch,) + tuple((p._version, p.data_ptr()) for p in params), hit[1])
+
     def clear(self):
         self._items.clear()
 
@@ -76,6 +87,33 @@ class _EngineModule(nn.Module):
     def weights_updated(self):
         """Called by optimizers that update parameters through raw pointers (gdmcf_b200.optim.FusedAdamW)."""
         self._ops.epoch += 1
+
+    def _refresh_entry(self, param, op=None, op_t=None, inv=None, onehot=None, tcols=None, cols_used=0):
+        """Description of the cached tensors derived from `param` for gdmcf_adamw_refresh: cache names + kernel arguments.
+        Only tensors that have been built once (and therefore exist with the right shapes) take part."""
+        names, kw = [], dict(cols_used=cols_used)
+        rows, cols = param.shape
+        for key, arg in ((op, "op"), (op_t, "op_t"), (inv, "inv_norm"), (tcols, "tcols")):
+            val = self._ops.peek(key) if key else None
+            if val is not None:
+                kw[arg] = val
+                names.append(key)
+        tabs = self._ops.peek(onehot) if onehot else None
+        if tabs is not None:
+            kw["base"], kw["delta"] = tabs
+            names.append(onehot)
+        if "inv_norm" in kw or "delta" in kw:
+            n = K.adamw_refresh_splits(rows, cols) * rows
+            kw["rowpart"] = self._buf(("rowpart", id(param)), lambda: torch.empty(n, dtype=torch.float32, device=param.device))
+        return (kw, names) if names else None
+
+    def refresh_specs(self) -> Dict[int, tuple]:
+        """id(param) -> (kwargs for kernels.adamw_refresh, cache names it refreshes). Overridden per backbone."""
+        return {}
+
+    def adopt_refreshed(self, param, names) -> None:
+        for n in names:
+            self._ops.mark_fresh(n, [param])
 
     def _next_offset(self) -> int:
         self._rng_calls += 1
@@ -160,6 +198,15 @@ class DNN(_EngineModule):
         return self._ops.get(f"tb{T}", [self.emb_layer.weight, self.emb_layer.bias, l0.weight, l0.bias],
                              lambda prev: K.time_bias_table(self.emb_layer.weight.detach(), self.emb_layer.bias.detach(),
                                                             l0.weight.detach(), self.n_item, l0.bias.detach(), T, out=prev))[0]
+
+    def refresh_specs(self):
+        pr, out = self.precision, {}
+        w1, wo = self.in_layers[0].weight, self.out_layers[0].weight
+        for prm, ent in ((w1, self._refresh_entry(w1, op="in0" + pr, tcols="in_layers.0.tcols", cols_used=self.n_item)),
+                         (wo, self._refresh_entry(wo, op="out0" + pr, op_t="out0.T" + pr))):
+            if ent is not None:
+                out[id(prm)] = ent
+        return out
 
     # -- forward -------------------------------------------------------------------------------
     def _encode(self, x_op: Bf16Mat, B: int, ts, t_const: int, T: int, h_out: Bf16Mat, h_f32=None):
@@ -326,6 +373,20 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         e_op = self._weight_operand("E", E)
         inv = self._ops.get("E.inv", [E], lambda prev: K.row_inv_norm(E.detach(), out=prev))
         return e_op, inv
+
+    def refresh_specs(self):
+        pr, out = self.precision, {}
+        w1, w2, E = self.in_layers[0].weight, self.in_layers2[0].weight, self.embedding_item.weight
+        g1, g2 = self.gcn_model.conv1.lin.weight, self.gcn_model.conv2.lin.weight
+        for prm, ent in (
+                (w1, self._refresh_entry(w1, op="in0" + pr, tcols="in_layers.0.tcols", cols_used=self.n_item)),
+                (w2, self._refresh_entry(w2, op="in2" + pr, onehot="onehot", tcols="in_layers2.0.tcols", cols_used=2 * self.n_item)),
+                (E, self._refresh_entry(E, op="E" + pr, op_t="E.T" + pr, inv="E.inv")),
+                (g1, self._refresh_entry(g1, op="gcn1" + pr, op_t="gcn1.T" + pr)),
+                (g2, self._refresh_entry(g2, op="gcn2" + pr, op_t="gcn2.T" + pr))):
+            if ent is not None:
+                out[id(prm)] = ent
+        return out
 
     # -- pieces of the forward -----------------------------------------------------------------
     def _hc_buffers(self, B: int, dev):

@@ -10,7 +10,8 @@ from . import kernels as K
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, modules=(), capturable=False):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, modules=(), capturable=False,
+                 fuse_refresh=True):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self._modules = list(modules)  # engine modules whose bf16 operand caches must be invalidated
@@ -18,6 +19,9 @@ class FusedAdamW(torch.optim.Optimizer):
         # so step() has no host-side state and can be replayed inside a CUDA graph
         self._capturable = capturable
         self._step_dev = None
+        # fuse_refresh: 2-D weights of `modules` are updated by gdmcf_adamw_refresh, which also rewrites the tensors the
+        # contractions derive from them (same update arithmetic; False keeps one flat pass per parameter)
+        self._fuse_refresh = fuse_refresh
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -27,21 +31,35 @@ class FusedAdamW(torch.optim.Optimizer):
                 dev = next(p for g in self.param_groups for p in g["params"]).device
                 self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
             K.counter_add(self._step_dev, 1)
+        # weights whose derived tensors (bf16 operands, transposes, norms, one-hot tables) are refreshed by the same pass
+        specs = {}
+        if self._fuse_refresh:
+            for mod in self._modules:
+                for pid, (kw, names) in mod.refresh_specs().items():
+                    specs[pid] = (kw, names, mod)
+        adopted = []
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 st = self.state[p]
                 if not st:
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
-                K.adamw_fused(p.data, g, st["exp_avg"], st["exp_avg_sq"], lr=group["lr"], beta1=b1, beta2=b2,
-                              eps=group["eps"], weight_decay=group["weight_decay"], step=st["step"],
-                              step_dev=self._step_dev if self._capturable else None, grad_scale=grad_scale)
+                hyper = dict(lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"],
+                             step=st["step"], step_dev=self._step_dev if self._capturable else None, grad_scale=grad_scale)
+                spec = specs.get(id(p))
+                if spec is not None and p.dim() == 2 and p.is_contiguous() and p.grad.stride(1) == 1:
+                    K.adamw_refresh(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], **hyper, **spec[0])
+                    adopted.append((spec[2], p, spec[1]))
+                else:
+                    g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                    K.adamw_fused(p.data, g, st["exp_avg"], st["exp_avg_sq"], **hyper)
         for m in self._modules:
             m.weights_updated()
+        for mod, p, names in adopted:
+            mod.adopt_refreshed(p, names)
         return loss

@@ -47,6 +47,17 @@ def _time_cols(model, name, W, n_in):
     return model._ops.get(name + ".tcols", [W], build)
 
 
+def _grad_buffer(W: torch.Tensor) -> torch.Tensor:
+    """fp32 gradient buffer for a [d, n] weight whose rows start 16 B aligned, so that the wgrad contraction can use the
+    TMA-store epilogue (nn.Linear(n_item + emb_size, d) weights have an odd row length). Returned as a [d, n] view;
+    autograd compacts it when it installs .grad."""
+    d, n = W.shape
+    ld = K.round_up(n, 4)
+    if ld == n:
+        return torch.empty_like(W)
+    return torch.empty(d, ld, dtype=W.dtype, device=W.device)[:, :n]
+
+
 def _mm_auto(model, a: Bf16Mat, b: Bf16Mat, m, n, k, **epi):
     """Contraction in the model's precision; operands that carry no lo part fall back to their hi part only."""
     if model._lo and a.lo is not None and b.lo is not None:
@@ -71,6 +82,25 @@ def _bf16_T(x: Bf16Mat, rows, cols, dev) -> Bf16Mat:
     if x.lo is not None:
         K.transpose_bf16(x.lo, rows, cols, out.lo)
     return out
+
+
+def _hand_over(model, grads: Dict[str, torch.Tensor], names):
+    """Gradients for autograd, in parameter order. A padded wgrad buffer (see _grad_buffer) is installed as .grad directly:
+    autograd's AccumulateGrad would compact it with a 137 MB copy; FusedAdamW and the all-reduce read it through its
+    leading dimension."""
+    params = dict(model.named_parameters())
+    out = []
+    for n in names:
+        g = grads[n]
+        if g.dim() == 2 and not g.is_contiguous():
+            prm = params[n]
+            if prm.grad is None:
+                prm.grad = g
+            else:
+                prm.grad.add_(g)
+            g = None
+        out.append(g)
+    return tuple(out)
 
 
 class _Ctx:
@@ -234,7 +264,7 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
     for name, dpre, dpreT, AT, n_in, first in (("in_layers.0", dh_pre, dh_preT, A1T, I, True),
                                               ("in_layers2.0", dhU_pre, dhU_preT, A2T, 2 * I, False)):
         W = P[name + ".weight"]
-        gW = torch.empty_like(W)
+        gW = _grad_buffer(W)
         _mm_auto(model, dpreT, AT, d, n_in, B, out_f32=gW)                                   # columns [0, n_in)
         K.sgemm_small(dpre, emb_rows, gW[:, n_in:], d, e, B, trans_a=True)                   # time-embedding columns
         grads[name + ".weight"] = gW
@@ -260,7 +290,7 @@ class _GdmcfTrainFn(torch.autograd.Function):
     def backward(ctx, g_mse, g_closs, g_out):
         grads = _gdmcf_backward(ctx.model, ctx.diff, ctx.c, g_mse, g_closs)
         ctx.c = None
-        return (None,) * 9 + tuple(grads[n] for n in _GDMCF_PARAMS)
+        return (None,) * 9 + _hand_over(ctx.model, grads, _GDMCF_PARAMS)
 
 
 # ======================================================================================================
@@ -316,7 +346,7 @@ def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
     dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)
     A1T = _bf16_T(c.A1, B, I, dev)
     W = P["in_layers.0.weight"]
-    gW = torch.empty_like(W)
+    gW = _grad_buffer(W)
     _mm_auto(model, dh_preT, A1T, d, I, B, out_f32=gW)
     emb_table = K.time_bias_table(model.emb_layer.weight.detach(), model.emb_layer.bias.detach(), W.detach(), I, None, T)[1]
     emb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
@@ -347,7 +377,7 @@ class _DnnTrainFn(torch.autograd.Function):
     def backward(ctx, g_mse, g_out):
         grads = _dnn_backward(ctx.model, ctx.diff, ctx.c, g_mse)
         ctx.c = None
-        return (None,) * 7 + tuple(grads[n] for n in _DNN_PARAMS)
+        return (None,) * 7 + _hand_over(ctx.model, grads, _DNN_PARAMS)
 
 
 # ======================================================================================================

@@ -257,6 +257,27 @@ int gdmcf_mse_rows(const float* out, int64_t ld_out, const float* x0, int64_t ld
 int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
                       float grad_scale, gdmcf_stream_t stream);
+/* AdamW on a [rows, cols] fp32 weight fused with the refresh of the tensors the contractions derive from it (all
+ * optional, NULL = skip): bf16 operand W[:, :cols_used] (hi[, lo], zero padded to ld_hi), its transpose (t_hi[, t_lo],
+ * [cols_used, ld_t]), row inverse norms 1/||W[r,:]|| (inv_norm; models/DNN.py:1320), the one-hot encoder tables
+ * delta[i,:] = W[:,2i+1] - W[:,2i] / base = sum_i W[:,2i] (models/DNN.py:1249-1251 at x_tU = one_hot(x0)), and a
+ * contiguous copy of the trailing columns W[:, cols_used:] (tcols [rows, n_tcols]). rowpart: workspace of
+ * gdmcf_adamw_refresh_splits(rows, cols) * rows floats (needed for inv_norm / delta). g may have a padded leading
+ * dimension ld_g. Same update arithmetic as gdmcf_adamw_fused. */
+typedef struct gdmcf_refresh {
+  int32_t cols_used;      /* 0 = all columns */
+  int32_t n_tcols;
+  void* hi; void* lo; int64_t ld_hi;
+  void* t_hi; void* t_lo; int64_t ld_t;
+  float* inv_norm;
+  float* delta; int64_t ld_delta; float* base;
+  float* tcols;
+  float* rowpart;
+} gdmcf_refresh;
+int gdmcf_adamw_refresh_splits(int rows, int cols);
+int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float* m, float* v, int rows, int cols, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
+                        float grad_scale, const gdmcf_refresh* out, gdmcf_stream_t stream);
 /* counter_dev[0] += inc on the stream: the device-resident step / RNG-epoch counters that keep captured CUDA graphs
  * advancing (Philox counter = offset + (epoch << 44); AdamW bias corrections from *step_dev when non-NULL). */
 int gdmcf_counter_add(uint64_t* counter_dev, uint64_t inc, gdmcf_stream_t stream);

@@ -396,3 +396,79 @@ def test_mix_rownorm_mse_adamw(K):
         opt.step()
         K.adamw_fused(p, grad, m, v, lr=1e-2, weight_decay=0.01, step=step)
     assert (p - pr.detach()).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("rows,cols,cols_used,with_lo,kind", [
+    (70, 203, 193, False, "tcols"),       # odd row length (scalar path), trailing time-embedding columns
+    (100, 256, 0, True, "t_inv"),         # 16 B path, transpose + row norms, hi/lo parts
+    (40, 112, 102, False, "onehot"),      # one-hot tables, 16 B path
+    (37, 110, 100, False, "onehot"),      # one-hot tables, scalar path, ragged row tile
+    (1000, 3000, 0, False, "t_inv"),      # many column splits
+])
+def test_adamw_refresh_equals_adamw_plus_separate_refresh(K, rows, cols, cols_used, with_lo, kind):
+    g0 = torch.Generator(device="cuda").manual_seed(rows + cols)
+    p = torch.randn(rows, cols, device="cuda", generator=g0) * 0.1
+    m = torch.randn(rows, cols, device="cuda", generator=g0) * 0.01
+    v = torch.rand(rows, cols, device="cuda", generator=g0) * 1e-3
+    ldg = K.round_up(cols, 4) + 4
+    gbuf = torch.randn(rows, ldg, device="cuda", generator=g0)
+    grad = gbuf[:, :cols]  # padded leading dimension
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    hyper = dict(lr=1e-2, weight_decay=0.01, step=3, grad_scale=0.5)
+    K.adamw_fused(p2.view(-1), grad.contiguous().view(-1), m2.view(-1), v2.view(-1), **hyper)
+    cu = cols_used or cols
+    kw = dict(cols_used=cols_used)
+    op = K.Bf16Mat.empty(rows, cu, "cuda", with_lo, zero=True)  # as built by cast_bf16: zero K padding
+    op.hi[:, :cu] = 7.0
+    kw["op"] = op
+    if kind == "t_inv":
+        kw["op_t"] = K.cast_bf16_transpose(p[:, :cu], with_lo=with_lo)  # built once (padding rows zeroed), then refreshed
+        kw["inv_norm"] = torch.empty(rows, device="cuda")
+    if kind == "onehot":
+        n_items = cu // 2
+        kw["base"] = torch.empty(rows, device="cuda")
+        kw["delta"] = torch.zeros(n_items, K.round_up(rows, 4), device="cuda")
+    if kind in ("t_inv", "onehot"):
+        kw["rowpart"] = torch.empty(K.adamw_refresh_splits(rows, cols) * rows, device="cuda")
+    if cols_used:
+        kw["tcols"] = torch.empty(rows, cols - cols_used, device="cuda")
+    K.adamw_refresh(p, grad, m, v, **hyper, **kw)
+    assert torch.equal(p, p2) and torch.equal(m, m2) and torch.equal(v, v2)
+    ref = K.cast_bf16(p2[:, :cu], with_lo=with_lo)
+    assert torch.equal(op.hi, ref.hi)
+    if with_lo:
+        assert torch.equal(op.lo, ref.lo)
+    if kind == "t_inv":
+        ref_t = K.cast_bf16_transpose(p2[:, :cu], with_lo=with_lo)
+        assert torch.equal(kw["op_t"].hi, ref_t.hi)
+        if with_lo:
+            assert torch.equal(kw["op_t"].lo, ref_t.lo)
+        torch.testing.assert_close(kw["inv_norm"], 1.0 / p2.norm(dim=1), rtol=2e-6, atol=0)
+    if kind == "onehot":
+        w = p2[:, :cu]
+        assert torch.equal(kw["delta"][:, :rows], (w[:, 1::2] - w[:, 0::2]).t())
+        torch.testing.assert_close(kw["base"], w[:, 0::2].double().sum(1).float(), rtol=1e-6, atol=1e-7)
+    if cols_used:
+        assert torch.equal(kw["tcols"], p2[:, cols_used:])
+
+
+@pytest.mark.parametrize("rows,cols,aligned", [(400, 34395, True), (70, 130, True), (33, 77, False)])
+def test_transpose_bf16(K, rows, cols, aligned):
+    ld_in = K.round_up(cols, 64) if aligned else cols + 3
+    ld_out = K.round_up(rows, 64) if aligned else rows + 1
+    x = torch.zeros(rows, ld_in, dtype=torch.bfloat16, device="cuda")
+    x[:, :cols] = torch.randn(rows, cols, device="cuda").to(torch.bfloat16)
+    out = torch.full((cols, ld_out), 5.0, dtype=torch.bfloat16, device="cuda")
+    K.transpose_bf16(x, rows, cols, out)
+    assert torch.equal(out[:, :rows], x[:, :cols].t())
+    if aligned:
+        assert (out[:, rows:] == 0).all()  # K padding of the transposed operand
+
+
+def test_mse_rows_ragged(K):
+    for rows, cols, ld in ((5, 34395, 34396), (3, 1001, 1001), (2, 7, 8)):
+        a = torch.randn(rows, ld, device="cuda")
+        b = torch.randn(rows, ld, device="cuda")
+        got = K.mse_rows(a[:, :cols] if ld == cols else a, b[:, :cols] if ld == cols else b, rows, cols)
+        ref = ((a[:, :cols].double() - b[:, :cols].double()) ** 2).mean(1)
+        torch.testing.assert_close(got.double(), ref, rtol=2e-6, atol=0)
