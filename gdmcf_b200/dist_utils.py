@@ -51,6 +51,33 @@ class Dist:
                 g.copy_(flat[off:off + g.numel()].view_as(g))
                 off += g.numel()
 
+    def all_reduce_async(self, tensors):
+        """Starts the all-reduce(SUM) of `tensors` on NCCL's stream (it waits for the work already queued on the current
+        stream). Returns (works, after): call w.wait() for every work, then every function of `after` (they copy the
+        flattened small tensors back)."""
+        works, after, small = [], [], []
+        if self.world_size == 1:
+            return works, after
+        for g in tensors:
+            if not g.is_contiguous():
+                assert g.dim() == 2 and g.stride(1) == 1
+                g = g.as_strided((g.shape[0], g.stride(0)), (g.stride(0), 1))
+            if g.numel() * g.element_size() >= (8 << 20):
+                works.append(td.all_reduce(g, op=td.ReduceOp.SUM, async_op=True))
+            else:
+                small.append(g)
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            works.append(td.all_reduce(flat, op=td.ReduceOp.SUM, async_op=True))
+
+            def copy_back():
+                off = 0
+                for g in small:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+            after.append(copy_back)
+        return works, after
+
     def broadcast_parameters(self, model: torch.nn.Module) -> None:
         if self.world_size == 1:
             return

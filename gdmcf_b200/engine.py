@@ -9,10 +9,13 @@ issued one by one from Python the step is bound by host enqueue time, not by the
 once, around *static* device inputs (the batch's CSR rows, ground-truth rows and user ids), and replays it per batch.
 Everything that changes from step to step lives on the device: the Philox epoch and AdamW step counters are advanced
 by kernels inside the graph, timesteps are drawn by gdmcf_sample_timesteps, bf16 weight operands are refreshed in place.
-With world_size > 1 the step is two graphs with the NCCL all-reduce of the gradient buffers between them.
+With world_size > 1 the step is a chain of graph segments with NCCL between them: the backward pass hands over
+gradient groups as they become final (item table first), their all-reduces run asynchronously on NCCL's stream while the
+next segment computes, and AdamW updates each group as soon as its reduction has landed.
 
-The public calls (`diffusion.training_losses`, `loss.backward()`, `optimizer.step()`, `diffusion.rank`) are exactly the
-ones a user of the eager API makes; `graphs=False` runs the same code without capture (used by parity tests)."""
+The training half is `train_step.fused_train_stages` — the kernels and arithmetic of `diffusion.training_losses(...)
+["loss"].mean().backward()` without the autograd bookkeeping; `optimizer.update`, `diffusion.rank` and
+`metrics_from_device` are the public calls. `graphs=False` runs the same program without capture (parity tests)."""
 from __future__ import annotations
 
 from typing import Optional, Sequence
@@ -20,8 +23,12 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
+import torch.distributed as td
+
 from . import _lib, evaluate_utils
+from . import kernels as K
 from .models.gaussian_diffusion import CsrBatch
+from .train_step import fused_train_stages
 
 
 class StepEngine:
@@ -40,11 +47,19 @@ class StepEngine:
         self.gt_rowptr = torch.zeros(batch_size + 1, **i32)         # batch-local CSR of the ground-truth rows
         self.gt_col = torch.zeros(max(cap_gt_nnz, 1), **i32)
         self.local_ids = torch.arange(batch_size, **i32)
-        self._g1: Optional[torch.cuda.CUDAGraph] = None
-        self._g2: Optional[torch.cuda.CUDAGraph] = None
-        self._grads = None
-        self._out = None
+        self._segments = []          # [(CUDAGraph, communication action after it or None)]
+        self._works, self._after, self._result = {}, {}, None
         self.launches_per_step = 0
+        # data parallel: the user table's gradient has B non-zero rows per rank -> all-gather (ids, rows), 1.6 MB instead
+        # of all-reducing the dense [n_user, d] gradient (218 MB at the Yelp shape)
+        G = dist.world_size
+        self.sparse_user_rows = G > 1 and hasattr(model, "embedding_user")
+        if self.sparse_user_rows:
+            d = model.embedding_user.weight.shape[1]
+            self._send_idx = torch.zeros(batch_size, **i32)
+            self._send_rows = torch.zeros(batch_size, d, dtype=torch.float32, device=dev)
+            self._recv_idx = torch.zeros(G, batch_size, **i32)
+            self._recv_rows = torch.zeros(G, batch_size, d, dtype=torch.float32, device=dev)
 
     # -- inputs ------------------------------------------------------------------------------------
     def load_resident(self, train_dev, gt_dev, lo: int, hi: int) -> None:
@@ -71,28 +86,69 @@ class StepEngine:
     def _batch(self) -> CsrBatch:
         return CsrBatch(self.tr_rowptr, self.tr_col, self.local_ids, self.n_item)
 
-    def _train_part(self):
-        self.model.train()
-        self.opt.zero_grad(set_to_none=True)
-        losses = self.diffusion.training_losses(self.model, self._batch(), self.reweight, index=self.users)
-        loss = losses["loss"].mean()
-        loss.backward()
-        return loss.detach()
-
-    def _update_part(self):
-        self.opt.step(grad_scale=1.0 / self.dist.world_size)
-        self.model.eval()
+    def _program(self):
+        """The step as a generator. Between two yields everything is device work on the current stream (one CUDA graph
+        segment when capturing); a yield is a communication point: ("reduce", key, tensors) starts the asynchronous
+        all-reduce of a finished gradient group, ("wait", key) makes the stream wait for it. With one rank there are no
+        yields and the whole step is a single graph."""
+        model, diff, opt, G = self.model, self.diffusion, self.opt, self.dist.world_size
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        params = dict(model.named_parameters())
+        stages = fused_train_stages(diff, model, self._batch(), self.reweight, index=self.users)
+        _, loss = next(stages)
+        groups = []
+        for _, grads in stages:
+            names = list(grads)
+            for n in names:
+                params[n].grad = grads[n]
+            groups.append([params[n] for n in names])
+            if G > 1:
+                dense = [grads[n] for n in names if not (self.sparse_user_rows and n == "embedding_user.weight")]
+                if self.sparse_user_rows and "embedding_user.weight" in grads:
+                    # only B rows of the user table carry a gradient: exchange (ids, rows) instead of the dense table
+                    idx, rows = model._user_grad_rows
+                    self._send_idx.copy_(idx)
+                    self._send_rows.copy_(rows)
+                    yield ("gather_rows", len(groups) - 1, dense)
+                else:
+                    yield ("reduce", len(groups) - 1, dense)
+        opt.begin_step()
+        for gi, plist in enumerate(groups):
+            if G > 1:
+                yield ("wait", gi, None)
+                if self.sparse_user_rows and any(p is params.get("embedding_user.weight") for p in plist):
+                    gU = params["embedding_user.weight"].grad
+                    d = gU.shape[1]
+                    for r in range(G):
+                        if r != self.dist.rank:
+                            K.scatter_rows_add(self._recv_rows[r], self._recv_idx[r], gU, self.B, d)
+            opt.update(plist, grad_scale=1.0 / G)
+        opt.end_step()
+        model.eval()
         batch = self._batch()
-        idx = self.diffusion.rank(self.model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
+        idx = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
         sums = evaluate_utils.metrics_from_device(idx, batch.users, self.gt_rowptr, self.gt_col, self.topN)
-        return idx, sums
+        self._result = (loss, idx, sums)
+
+    # -- communication actions (eager NCCL between graph segments) -----------------------------------
+    def _comm(self, action, key, tensors) -> None:
+        if action == "wait":
+            for w in self._works.pop(key, []):
+                w.wait()
+            for fn in self._after.pop(key, []):
+                fn()
+            return
+        works, after = self.dist.all_reduce_async(tensors)
+        if action == "gather_rows":
+            works.append(td.all_gather_into_tensor(self._recv_idx.view(-1), self._send_idx, async_op=True))
+            works.append(td.all_gather_into_tensor(self._recv_rows.view(-1), self._send_rows.view(-1), async_op=True))
+        self._works[key], self._after[key] = works, after
 
     def _eager_step(self):
-        loss = self._train_part()
-        if self.dist.world_size > 1:
-            self.dist.all_reduce_tensors([p.grad for p in self.model.parameters() if p.grad is not None])
-        idx, sums = self._update_part()
-        return loss, idx, sums
+        for action, key, tensors in self._program():
+            self._comm(action, key, tensors)
+        return self._result
 
     def capture(self, warmup: int = 3) -> None:
         """Eager warm-up on whatever the static inputs hold (call load_* first), then capture. The warm-up allocates the
@@ -110,34 +166,40 @@ class StepEngine:
         assert getattr(self.opt, "_capturable", False), "graph capture needs FusedAdamW(..., capturable=True)"
         self.opt.zero_grad(set_to_none=True)
         n0 = lib.gdmcf_launch_count()
-        self._g1 = torch.cuda.CUDAGraph()
-        if self.dist.world_size == 1:
-            with torch.cuda.graph(self._g1):
-                loss = self._train_part()
-                idx, sums = self._update_part()
-        else:
-            with torch.cuda.graph(self._g1):
-                loss = self._train_part()
-            self._grads = [p.grad for p in self.model.parameters() if p.grad is not None]
-            self._g1.replay()  # gradients of the current static batch (capture itself executes nothing)
-            self.dist.all_reduce_tensors(self._grads)
-            self._g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._g2, pool=self._g1.pool()):
-                idx, sums = self._update_part()
-            self._g2.replay()
+        self._segments = []
+        pool = None
+
+        def begin():
+            nonlocal pool
+            g = torch.cuda.CUDAGraph()
+            ctx = torch.cuda.graph(g, pool=pool, stream=side)
+            ctx.__enter__()
+            return g, ctx
+
+        g, ctx = begin()
+        try:
+            for action in self._program():
+                ctx.__exit__(None, None, None)
+                pool = pool or g.pool()
+                self._segments.append((g, action))
+                g, ctx = begin()
+        except BaseException:
+            ctx.__exit__(None, None, None)
+            raise
+        ctx.__exit__(None, None, None)
+        self._segments.append((g, None))
         self.launches_per_step = int(lib.gdmcf_launch_count() - n0)
-        self._out = (loss, idx, sums)
-        self.model.weights_updated()  # operands were refreshed in place by the replays; eager users must rebuild
+        self.model.weights_updated()  # capture executed nothing: cached operands follow the replays from here on
         torch.cuda.synchronize(self.dev)
 
     def step(self):
         """Run one step on the loaded inputs. Returns (loss scalar f64, top-k indices int32 [B, k], metric sums f64
         [len(topN), 4]) — device tensors that the next step overwrites."""
-        if self._g1 is None:
+        if not self._segments:
             return self._eager_step()
-        self._g1.replay()
-        if self._g2 is not None:
-            self.dist.all_reduce_tensors(self._grads)
-            self._g2.replay()
+        for g, action in self._segments:
+            g.replay()
+            if action is not None:
+                self._comm(*action)
         self.model.weights_updated()  # keeps the eager API coherent: its cached operands are stale after a replay
-        return self._out
+        return self._result

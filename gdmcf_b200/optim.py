@@ -26,22 +26,36 @@ class FusedAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         loss = closure() if closure is not None else None
+        self.begin_step()
+        self.update(None, grad_scale)
+        self.end_step()
+        return loss
+
+    # -- the three phases of step(), exposed so that a data-parallel engine can update parameter groups as their
+    #    gradient all-reduces complete (engine.StepEngine)
+    @torch.no_grad()
+    def begin_step(self) -> None:
+        self._adopted = []
         if self._capturable:
             if self._step_dev is None:
                 dev = next(p for g in self.param_groups for p in g["params"]).device
                 self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
             K.counter_add(self._step_dev, 1)
+
+    @torch.no_grad()
+    def update(self, params=None, grad_scale: float = 1.0) -> None:
+        """AdamW on `params` (default: every parameter with a gradient)."""
+        only = None if params is None else {id(p) for p in params}
         # weights whose derived tensors (bf16 operands, transposes, norms, one-hot tables) are refreshed by the same pass
         specs = {}
         if self._fuse_refresh:
             for mod in self._modules:
                 for pid, (kw, names) in mod.refresh_specs().items():
                     specs[pid] = (kw, names, mod)
-        adopted = []
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or (only is not None and id(p) not in only):
                     continue
                 st = self.state[p]
                 if not st:
@@ -54,12 +68,15 @@ class FusedAdamW(torch.optim.Optimizer):
                 spec = specs.get(id(p))
                 if spec is not None and p.dim() == 2 and p.is_contiguous() and p.grad.stride(1) == 1:
                     K.adamw_refresh(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], **hyper, **spec[0])
-                    adopted.append((spec[2], p, spec[1]))
+                    self._adopted.append((spec[2], p, spec[1]))
                 else:
                     g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                     K.adamw_fused(p.data, g, st["exp_avg"], st["exp_avg_sq"], **hyper)
+
+    @torch.no_grad()
+    def end_step(self) -> None:
         for m in self._modules:
             m.weights_updated()
-        for mod, p, names in adopted:
+        for mod, p, names in self._adopted:
             mod.adopt_refreshed(p, names)
-        return loss
+        self._adopted = []

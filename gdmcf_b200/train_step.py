@@ -171,6 +171,16 @@ def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc,
 
 
 def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Tensor, g_closs: torch.Tensor):
+    grads: Dict[str, torch.Tensor] = {}
+    for stage in _gdmcf_backward_stages(model, diff, c, g_mse, g_closs):
+        grads.update(stage)
+    return grads
+
+
+def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Tensor, g_closs: torch.Tensor):
+    """Generator over the backward pass: yields {parameter name: gradient} as soon as a group is final, so that a
+    data-parallel caller can start its all-reduce while the rest of the backward runs. Stage 1: the item table
+    (412 MB at the Yelp shape, needs only dL/d(out) and the user tower); stage 2: everything else."""
     B, I, d, dev, T = c.B, c.I, model.hidden, c.x0.device, diff.steps
     d3, e = 3 * d, model.time_emb_dim
     lo = model._lo
@@ -186,20 +196,20 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
     rowpart = torch.empty(n_cb, B, dtype=torch.float32, device=dev)
     K.loss_grad(c.out, c.x0, g_mse.float().contiguous(), B, I, Gs, GT=GsT, row_scale=c.inv_u, col_scale=c.inv_i,
                 with_out=True, colsum=colsum, rowpart=rowpart)
-    r_b = K.colsum_f32(rowpart, n_cb, B)
-    # ---- cosine backward w.r.t. the user tower: d hc' = Gs E - hc' * ru^2 * r_b
-    eT = model._weight_operand("E", model.embedding_item.weight, transpose=True)  # [3d, I]
-    d_hcp = torch.empty(B, d3, dtype=torch.float32, device=dev)
-    coef_u = -(c.inv_u * c.inv_u) * r_b
-    _mm_auto(model, Gs, eT, B, d3, I, out_f32=d_hcp, row_t=_arange32(model, B, dev),
-             c1=_ones(model, B, dev), c2=coef_u, xt=c.hcp_f32)
     # ---- d E = Gs^T hc' - E * ri^2 * c_i   (written straight into the parameter's gradient)
     hcpT = K.cast_bf16_transpose(c.hcp_f32, with_lo=lo)  # [3d, B]
     gE = torch.empty_like(P["embedding_item.weight"])
     coef_i = -(c.inv_i * c.inv_i) * colsum
     _mm_auto(model, GsT, hcpT, I, d3, B, out_f32=gE, row_t=_arange32(model, I, dev),
              c1=_ones(model, I, dev), c2=coef_i, xt=P["embedding_item.weight"].detach())
-    grads["embedding_item.weight"] = gE
+    yield {"embedding_item.weight": gE}
+    # ---- cosine backward w.r.t. the user tower: d hc' = Gs E - hc' * ru^2 * r_b
+    r_b = K.colsum_f32(rowpart, n_cb, B)
+    eT = model._weight_operand("E", model.embedding_item.weight, transpose=True)  # [3d, I]
+    d_hcp = torch.empty(B, d3, dtype=torch.float32, device=dev)
+    coef_u = -(c.inv_u * c.inv_u) * r_b
+    _mm_auto(model, Gs, eT, B, d3, I, out_f32=d_hcp, row_t=_arange32(model, B, dev),
+             c1=_ones(model, B, dev), c2=coef_u, xt=c.hcp_f32)
     # ---- sumW mix backward
     d_hc = torch.empty(B, d3, dtype=torch.float32, device=dev)
     d_g2 = torch.empty(B, d3, dtype=torch.float32, device=dev)
@@ -274,7 +284,9 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
     K.sgemm_small(d_emb, temb_rows, gWe, e, e, B, trans_a=True)
     grads["emb_layer.weight"] = gWe
     grads["emb_layer.bias"] = K.colsum_f32(d_emb, B, e)
-    return grads
+    # the rows of the user table that received a gradient (for a sparse exchange instead of a dense all-reduce)
+    model._user_grad_rows = (c.idx32, d_hc_tot[:, 2 * d:])
+    yield grads
 
 
 class _GdmcfTrainFn(torch.autograd.Function):
@@ -383,12 +395,8 @@ class _DnnTrainFn(torch.autograd.Function):
 # ======================================================================================================
 # training_losses
 # ======================================================================================================
-def training_losses(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None):
-    """GaussianDiffusionDiscrete.training_losses (models/gaussian_diffusion.py:834-957). Returns {"loss": [B] f64}
-    (+ "model_output", "mse", "closs" for tests). `inject` may carry ts_discrete / ts / noise / u_keep / keep_x /
-    keep_xU to replace the in-kernel Philox draws."""
-    from .models.gaussian_diffusion import CsrBatch
-    inject = inject or {}
+def _prepare(diff, model, x_start, index, inject):
+    """Shared front end of the autograd and the explicit training paths: dense start rows, timestep draws."""
     x0, _, _, users, B, I = diff._dense_start(x_start, want_op=False, lo=False)
     dev = x0.device
     diff._begin_step(dev)
@@ -402,34 +410,78 @@ def training_losses(diff, model, x_start, reweight=False, index=None, inject: Op
     if gdmcf != bool(diff.CatOneHot and diff.indexIn):
         raise ValueError("diffusion flags (CatOneHot/indexIn) do not match the backbone")
     # two timestep draws like the reference (:845 shapes the discrete noise, :865 feeds the model and the weights)
+    ts_disc = None
     if gdmcf:
         ts_disc = inject["ts_discrete"] if "ts_discrete" in inject else diff.sample_timesteps(B, dev, "importance")[0]
+        ts_disc = ts_disc.to(dev).to(torch.int32)
     if "ts" in inject:
         ts = inject["ts"].to(dev).long()
         pt = diff._pt_for(ts)
     else:
         ts, pt = diff.sample_timesteps(B, dev, "importance")
-    ts32 = ts.to(torch.int32)
+    idx32 = None
     if gdmcf:
         assert index is not None, "DNNOneHotEmbeddingGCN needs the user index of every row"
         idx32 = index.to(dev).to(torch.int32)
-        params = dict(model.named_parameters())
-        mse, closs, out = _GdmcfTrainFn.apply(model, diff, x0, B, I, idx32, ts_disc.to(dev).to(torch.int32), ts32, inject,
+    return x0, B, I, dev, gdmcf, idx32, ts_disc, ts, ts.to(torch.int32), pt
+
+
+def _loss_weight(diff, ts, B, dev, reweight):
+    if reweight:
+        weight = diff.SNR(ts - 1) - diff.SNR(ts)
+        return torch.where((ts == 0), 1.0, weight)
+    return torch.ones(B, device=dev)
+
+
+def training_losses(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None):
+    """GaussianDiffusionDiscrete.training_losses (models/gaussian_diffusion.py:834-957). Returns {"loss": [B] f64}
+    (+ "model_output", "mse", "closs" for tests). `inject` may carry ts_discrete / ts / noise / u_keep / keep_x /
+    keep_xU to replace the in-kernel Philox draws."""
+    inject = inject or {}
+    x0, B, I, dev, gdmcf, idx32, ts_disc, ts, ts32, pt = _prepare(diff, model, x_start, index, inject)
+    params = dict(model.named_parameters())
+    if gdmcf:
+        mse, closs, out = _GdmcfTrainFn.apply(model, diff, x0, B, I, idx32, ts_disc, ts32, inject,
                                               *[params[n] for n in _GDMCF_PARAMS])
     else:
-        params = dict(model.named_parameters())
         mse, out = _DnnTrainFn.apply(model, diff, x0, B, I, ts32, inject, *[params[n] for n in _DNN_PARAMS])
         closs = None
     terms = {}
-    if reweight:
-        weight = diff.SNR(ts - 1) - diff.SNR(ts)
-        weight = torch.where((ts == 0), 1.0, weight)
-    else:
-        weight = torch.ones(B, device=dev)
-    terms["loss"] = weight * mse
+    terms["loss"] = _loss_weight(diff, ts, B, dev, reweight) * mse
     diff._update_history(ts, terms["loss"])
     terms["loss"] = terms["loss"] / pt
     if closs is not None:
         terms["loss"] = terms["loss"] + closs * 0.1
     terms["model_output"], terms["mse"], terms["closs"] = out.detach()[:, :I], mse.detach(), closs.detach() if closs is not None else None
     return terms
+
+
+@torch.no_grad()
+def fused_train_stages(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None):
+    """`training_losses(...)["loss"].mean().backward()` without autograd, as a generator (used by engine.StepEngine):
+    yields ("loss", mean loss [] f64) after the forward and loss bookkeeping, then ("grads", {parameter name: gradient})
+    once per backward stage, in the order the gradients become final — a data-parallel caller starts the all-reduce of a
+    stage while the generator computes the next one. Same kernels and arithmetic as the autograd path; the gradient
+    seeds are d mean(loss) / d mse_b = weight_b / (pt_b * B) and d mean(loss) / d closs = 0.1."""
+    inject = inject or {}
+    x0, B, I, dev, gdmcf, idx32, ts_disc, ts, ts32, pt = _prepare(diff, model, x_start, index, inject)
+    if gdmcf:
+        c = _gdmcf_forward(model, diff, x0, B, I, idx32, ts_disc, ts32, inject)
+        closs = c.closs_rows.mean()
+    else:
+        c = _dnn_forward(model, diff, x0, B, I, ts32, inject)
+        closs = None
+    weight = _loss_weight(diff, ts, B, dev, reweight)
+    loss = weight * c.mse
+    diff._update_history(ts, loss)
+    loss = loss / pt
+    if closs is not None:
+        loss = loss + closs * 0.1
+    yield "loss", loss.mean()
+    g_mse = (weight / pt / B).float()
+    if gdmcf:
+        g_closs = torch.full((), 0.1, dtype=torch.float32, device=dev)
+        for stage in _gdmcf_backward_stages(model, diff, c, g_mse, g_closs):
+            yield "grads", stage
+    else:
+        yield "grads", _dnn_backward(model, diff, c, g_mse)

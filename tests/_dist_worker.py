@@ -41,7 +41,20 @@ def main(out_dir):
     dist.all_reduce_gradients(model)
     sums = torch.full((2, 4), float(dist.rank + 1), dtype=torch.float64)
     dist.all_reduce(sums)
-    torch.save({"rank": dist.rank, "mine": mine, "sums": sums,
+    # asynchronous form used by engine.StepEngine: large, flattened small and padded-view tensors
+    def make(rank):
+        gen = torch.Generator().manual_seed(11 + rank)
+        pad = torch.randn(6, 12, generator=gen)
+        return [torch.randn(2_100_000, generator=gen), torch.randn(7, generator=gen), torch.randn(3, 5, generator=gen), pad[:, :10]]
+    own, other = make(dist.rank), make(1 - dist.rank)
+    expect = [a + b for a, b in zip(own, other)]
+    works, after = dist.all_reduce_async(own)
+    for w in works:
+        w.wait()
+    for fn in after:
+        fn()
+    async_ok = all(torch.equal(a, b) for a, b in zip(own, expect))
+    torch.save({"rank": dist.rank, "mine": mine, "sums": sums, "async_ok": async_ok,
                 "params": {k: v.detach().clone() for k, v in model.named_parameters()},
                 "grads": {k: (v.grad.clone() if v.grad is not None else None) for k, v in model.named_parameters()},
                 "draws": draws, "users": users, "dense": dense},

@@ -122,3 +122,29 @@ def test_sample_timesteps_kernel():
     t_same, p_in = K.sample_timesteps(hist, full, B, ts_in=tin)
     assert t_same is tin
     torch.testing.assert_close(p_in, p[tin] * T, rtol=1e-12, atol=0)
+
+
+def test_explicit_stages_match_autograd_path():
+    """fused_train_stages (engine path, no autograd) vs training_losses(...).mean().backward() on identical draws."""
+    from gdmcf_b200.train_step import fused_train_stages
+    make, train_dev, test_dev, _, _, B, n_user = _setup(seed_model=2)
+    m_a, d_a, _ = make(False)
+    m_b, d_b, _ = make(False)
+    users = torch.arange(40, 40 + B, dtype=torch.int32, device="cuda")
+    batch = train_dev.batch(users)
+    m_a.train(); m_b.train()
+    la = d_a.training_losses(m_a, batch, True, index=users)["loss"].mean()
+    la.backward()
+    stages = fused_train_stages(d_b, m_b, batch, True, index=users)
+    _, lb = next(stages)
+    grads = {}
+    for _, g in stages:
+        grads.update(g)
+    assert torch.equal(la.detach(), lb)
+    pa = dict(m_a.named_parameters())
+    for n, g in grads.items():
+        ref = pa[n].grad
+        assert ref is not None, n
+        err = (g - ref).norm() / ref.norm().clamp_min(1e-30)
+        assert err < 1e-6, (n, err.item())
+    assert {n for n, p in pa.items() if p.grad is not None} == set(grads)
