@@ -22,6 +22,7 @@
 // user rows :1082-1100, torch.mm + norm division :1320-1325, posterior mean
 // models/gaussian_diffusion.py:1041-1050.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "api_internal.h"
 
@@ -520,6 +521,185 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): the two CTAs of a cluster compute one 256 x BN tile. Each CTA loads its 128 rows of A
+// and HALF of the B tile (BN/2 rows), so a k-block costs 32 KB of L2 -> SM traffic per CTA instead of 48 KB — the
+// 1-CTA kernel is bound by exactly that traffic on the batch-sized (M = 400) contractions. The leader (cluster rank 0)
+// issues tcgen05.mma.cta_group::2 for both; accumulator rows live in each CTA's own TMEM, so the epilogue is the
+// 1-CTA epilogue on the CTA's own 128 rows.
+//   full_bar  (leader's only): one arrive.expect_tx by the leader's producer for the bytes of BOTH CTAs; the peer's TMA
+//                              loads signal the leader's barrier (cp.async.bulk.tensor.cta_group::2).
+//   empty_bar (each CTA)     : tcgen05.commit multicast from the leader once the MMAs that read the stage retired.
+//   tfull_bar (each CTA)     : tcgen05.commit multicast — accumulator complete.
+//   tempty_bar (leader's)    : 8 arrivals = 4 epilogue warps x 2 CTAs (the peer's arrive through the cluster).
+// ---------------------------------------------------------------------------------------------
+struct Cfg2 {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 5;  // 5 x 32 KB in flight; with the 64 KB epilogue staging this is exactly the 227 KB limit
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int COLVEC_BYTES = 2 * BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 4 * EPI_WARP_BYTES + COLVEC_BYTES;
+};
+
+// unit -> (pair of m-blocks, n-block, split); m-pair fastest so neighbouring clusters share the weight tile in L2
+GD_DEV UnitCoord unit_coord_pair(const Shape& s, int unit, int pairs_m, int rank) {
+  UnitCoord u;
+  u.m_blk = 2 * (unit % pairs_m) + rank;
+  int r = unit / pairs_m;
+  u.n_blk = r % s.tiles_n;
+  u.split = r / s.tiles_n;
+  u.kb_begin = u.split * s.kb_per_split;
+  u.kb_end = min(u.kb_begin + s.kb_per_split, s.total_kb);
+  return u;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, const gdmcf_epilogue epi) {
+  using C = Cfg2;
+  constexpr int BN = C::BN;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;
+  uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint8_t* epi_stage = smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES;
+  float* colvec = reinterpret_cast<float*>(epi_stage + 4 * EPI_WARP_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pairs_m = (shape.tiles_m + 1) / 2;
+  const int num_units = pairs_m * shape.tiles_n * shape.splits;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < shape.n_seg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 2) tmem_alloc_2cta<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers and TMEM exist before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const UnitCoord u = unit_coord_pair(shape, unit, pairs_m, (int)rank);
+        int seg = 0, kb_in_seg = u.kb_begin;
+        while (kb_in_seg >= shape.kb[seg]) { kb_in_seg -= shape.kb[seg]; ++seg; }
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);  // the leader's barrier
+          tma_load_2d_2cta(sa, &maps.a[seg], fb, kb_in_seg * BK, u.m_blk * BM);
+          tma_load_2d_2cta(sb, &maps.b[seg], fb, kb_in_seg * BK, u.n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++kb_in_seg == shape.kb[seg]) { kb_in_seg = 0; ++seg; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader only) =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
+        const UnitCoord u = unit_coord_pair(shape, unit, pairs_m, 0);
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > u.kb_begin || k > 0) ? 1u : 0u);
+          umma_commit_2cta(&empty_bar[stage], 3);  // frees the stage in both CTAs
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tfull_bar[acc], 3);  // accumulator complete -> both epilogues
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ================= epilogue (both CTAs, own 128 rows) =================
+    const int ew = warp & 3;
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    uint8_t* stg = epi_stage + ew * EPI_WARP_BYTES;
+    int local = 0;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
+      const UnitCoord u = unit_coord_pair(shape, unit, pairs_m, (int)rank);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int m_warp0 = u.m_blk * BM + ew * 32;
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const int n_tile0 = u.n_blk * BN;
+      if (shape.tma_store) {
+        named_bar_sync(1, 128);
+        for (int j = et; j < BN; j += 128) {
+          const int n = n_tile0 + j;
+          colvec[j] = (epi.col_scale && n < shape.n) ? epi.col_scale[n] : 1.0f;
+          colvec[BN + j] = (epi.bias && n < shape.n) ? epi.bias[n] : 0.0f;
+        }
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (shape.tma_store)
+        epilogue_tile_tma<BN>(maps, shape, epi, stg, colvec, t_row, m_warp0, n_tile0, lane);
+      else
+        epilogue_tile_transposed<BN>(shape, epi, u, reinterpret_cast<float*>(stg), t_row, m_warp0, n_tile0, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+    }
+    if (shape.tma_store && lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be reading its accumulators / receiving multicast arrivals
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base);
+  }
+}
+
 // Sum split-K slabs in fixed order and apply the epilogue. One thread per 8 columns.
 __global__ void splitk_reduce_kernel(const Shape shape, const gdmcf_epilogue epi) {
   const int groups = (shape.n + 7) / 8;
@@ -595,6 +775,27 @@ static int launch(const TmaMaps& maps, const Shape& shape, const gdmcf_epilogue&
   return cuda_check_launch("gemm_bf16_tn_kernel");
 }
 
+static int launch_2cta(const TmaMaps& maps, const Shape& shape, const gdmcf_epilogue& epi, int clusters, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(gemm 2cta)");
+    attr_set = true;
+  }
+  gemm_bf16_tn_2cta_kernel<<<2 * clusters, NUM_THREADS, Cfg2::SMEM_BYTES, st>>>(maps, shape, epi);
+  return cuda_check_launch("gemm_bf16_tn_2cta_kernel");
+}
+
+// GDMCF_GEMM_2CTA=0 routes every contraction through the 1-CTA kernel (A/B comparisons, fallback).
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GDMCF_GEMM_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace gemm
 }  // namespace gd
 
@@ -632,6 +833,7 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
   int rc = gdmcf_device_check();
   if (rc) return rc;
   const int bn = pick_bn(g->n);
+  const bool pair = bn == 256 && use_2cta() && e->mode != 100 && e->mode != 101;
   Shape shape{};
   shape.m = g->m;
   shape.n = g->n;
@@ -648,7 +850,7 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
     shape.kb[s] = (g->k[s] + BK - 1) / BK;
     shape.total_kb += shape.kb[s];
     if ((rc = make_map(&maps.a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->a[s], g->m, g->k[s], g->lda[s], BM, BK))) return rc;
-    if ((rc = make_map(&maps.b[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->b[s], g->n, g->k[s], g->ldb[s], bn, BK))) return rc;
+    if ((rc = make_map(&maps.b[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g->b[s], g->n, g->k[s], g->ldb[s], pair ? bn / 2 : bn, BK))) return rc;
   }
   if (e->mode < 0 || (e->mode > GDMCF_EPI_COSINE && e->mode != 100 && e->mode != 101)) { set_error("gemm: bad epilogue mode %d", e->mode); return GDMCF_EBADARG; }
   if (e->c1 && (!e->c2 || !e->xt)) {
@@ -689,11 +891,16 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
     if (e->out_bf16 && (rc = make_map(&maps.o16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->out_bf16, g->m, g->n, e->ld_bf16, 32, 64))) return rc;
     if (e->out_bf16_lo && (rc = make_map(&maps.olo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->out_bf16_lo, g->m, g->n, e->ld_bf16, 32, 64))) return rc;
   }
-  const int num_units = shape.tiles_m * shape.tiles_n * shape.splits;
   const int sms = gdmcf_num_sms();
-  const int grid = std::min(num_units, sms > 0 ? sms : 148);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  rc = (bn == 256) ? launch<256>(maps, shape, *e, grid, st) : launch<128>(maps, shape, *e, grid, st);
+  if (pair) {
+    const int units = ((shape.tiles_m + 1) / 2) * shape.tiles_n * shape.splits;
+    rc = launch_2cta(maps, shape, *e, std::min(units, (sms > 0 ? sms : 148) / 2), st);
+  } else {
+    const int num_units = shape.tiles_m * shape.tiles_n * shape.splits;
+    const int grid = std::min(num_units, sms > 0 ? sms : 148);
+    rc = (bn == 256) ? launch<256>(maps, shape, *e, grid, st) : launch<128>(maps, shape, *e, grid, st);
+  }
   if (rc) return rc;
   if (shape.splits > 1) {
     const long long total = (long long)g->m * ((g->n + 7) / 8);

@@ -19,6 +19,7 @@ class Dist:
     world_size: int = 1
     local_rank: int = 0
     owns_group: bool = False
+    small_group: object = None  # second communicator: small messages do not queue behind a 400 MB all-reduce
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.world_size > 1:
@@ -51,7 +52,7 @@ class Dist:
                 g.copy_(flat[off:off + g.numel()].view_as(g))
                 off += g.numel()
 
-    def all_reduce_async(self, tensors):
+    def all_reduce_async(self, tensors, group=None):
         """Starts the all-reduce(SUM) of `tensors` on NCCL's stream (it waits for the work already queued on the current
         stream). Returns (works, after): call w.wait() for every work, then every function of `after` (they copy the
         flattened small tensors back)."""
@@ -63,12 +64,12 @@ class Dist:
                 assert g.dim() == 2 and g.stride(1) == 1
                 g = g.as_strided((g.shape[0], g.stride(0)), (g.stride(0), 1))
             if g.numel() * g.element_size() >= (8 << 20):
-                works.append(td.all_reduce(g, op=td.ReduceOp.SUM, async_op=True))
+                works.append(td.all_reduce(g, op=td.ReduceOp.SUM, group=group, async_op=True))
             else:
                 small.append(g)
         if small:
             flat = torch.cat([g.reshape(-1) for g in small])
-            works.append(td.all_reduce(flat, op=td.ReduceOp.SUM, async_op=True))
+            works.append(td.all_reduce(flat, op=td.ReduceOp.SUM, group=group, async_op=True))
 
             def copy_back():
                 off = 0
@@ -107,4 +108,4 @@ def init(backend: str | None = None) -> Dist:
             torch.cuda.set_device(local)
         td.init_process_group(backend=backend, rank=rank, world_size=world)
         owns = True
-    return Dist(rank, world, local, owns)
+    return Dist(rank, world, local, owns, td.new_group(backend=backend))

@@ -49,6 +49,7 @@ class StepEngine:
         self.local_ids = torch.arange(batch_size, **i32)
         self._segments = []          # [(CUDAGraph, communication action after it or None)]
         self._works, self._after, self._result = {}, {}, None
+        self._small_keys = set()     # gradient groups exchanged over dist.small_group
         self.launches_per_step = 0
         # data parallel: the user table's gradient has B non-zero rows per rank -> all-gather (ids, rows), 1.6 MB instead
         # of all-reducing the dense [n_user, d] gradient (218 MB at the Yelp shape)
@@ -105,6 +106,8 @@ class StepEngine:
             groups.append([params[n] for n in names])
             if G > 1:
                 dense = [grads[n] for n in names if not (self.sparse_user_rows and n == "embedding_user.weight")]
+                if sum(t.numel() * t.element_size() for t in dense) < (64 << 20):
+                    self._small_keys.add(len(groups) - 1)
                 if self.sparse_user_rows and "embedding_user.weight" in grads:
                     # only B rows of the user table carry a gradient: exchange (ids, rows) instead of the dense table
                     idx, rows = model._user_grad_rows
@@ -114,7 +117,11 @@ class StepEngine:
                 else:
                     yield ("reduce", len(groups) - 1, dense)
         opt.begin_step()
-        for gi, plist in enumerate(groups):
+        # update order: groups whose exchange went over the small-message communicator first (they are complete long
+        # before the big all-reduces), then the others in the order their all-reduces were issued
+        order = sorted(range(len(groups)), key=lambda gi: (0 if gi in self._small_keys else 1, gi))
+        for gi in order:
+            plist = groups[gi]
             if G > 1:
                 yield ("wait", gi, None)
                 if self.sparse_user_rows and any(p is params.get("embedding_user.weight") for p in plist):
@@ -139,10 +146,11 @@ class StepEngine:
             for fn in self._after.pop(key, []):
                 fn()
             return
-        works, after = self.dist.all_reduce_async(tensors)
+        group = self.dist.small_group if key in self._small_keys else None
+        works, after = self.dist.all_reduce_async(tensors, group=group)
         if action == "gather_rows":
-            works.append(td.all_gather_into_tensor(self._recv_idx.view(-1), self._send_idx, async_op=True))
-            works.append(td.all_gather_into_tensor(self._recv_rows.view(-1), self._send_rows.view(-1), async_op=True))
+            works.append(td.all_gather_into_tensor(self._recv_idx.view(-1), self._send_idx, group=group, async_op=True))
+            works.append(td.all_gather_into_tensor(self._recv_rows.view(-1), self._send_rows.view(-1), group=group, async_op=True))
         self._works[key], self._after[key] = works, after
 
     def _eager_step(self):

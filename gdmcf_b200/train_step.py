@@ -180,7 +180,8 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
 def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Tensor, g_closs: torch.Tensor):
     """Generator over the backward pass: yields {parameter name: gradient} as soon as a group is final, so that a
     data-parallel caller can start its all-reduce while the rest of the backward runs. Stage 1: the item table
-    (412 MB at the Yelp shape, needs only dL/d(out) and the user tower); stage 2: everything else."""
+    (412 MB at the Yelp shape, needs only dL/d(out) and the user tower); stage 2: sumW, GCN linears, user table;
+    stage 3: the first-layer weights."""
     B, I, d, dev, T = c.B, c.I, model.hidden, c.x0.device, diff.steps
     d3, e = 3 * d, model.time_emb_dim
     lo = model._lo
@@ -244,6 +245,10 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     gU = torch.zeros_like(P["embedding_user.weight"])
     K.scatter_rows_add(d_hc_tot[:, 2 * d:], c.idx32, gU, B, d)
     grads["embedding_user.weight"] = gU
+    # the rows of the user table that received a gradient (for a sparse exchange instead of a dense all-reduce)
+    model._user_grad_rows = (c.idx32, d_hc_tot[:, 2 * d:])
+    yield grads  # stage 2: sumW, the GCN linears, the user table — small messages, final before the two big wgrads
+    grads = {}
     # ---- nt_xent backward (DNN.py:479-508) into h and h_U
     dS = torch.empty(B, K.round_up(B, 4), dtype=torch.float32, device=dev)
     K.ntxent_rows(c.S, B, dscale=g_closs.float().reshape(1), dS=dS)
@@ -284,9 +289,7 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     K.sgemm_small(d_emb, temb_rows, gWe, e, e, B, trans_a=True)
     grads["emb_layer.weight"] = gWe
     grads["emb_layer.bias"] = K.colsum_f32(d_emb, B, e)
-    # the rows of the user table that received a gradient (for a sparse exchange instead of a dense all-reduce)
-    model._user_grad_rows = (c.idx32, d_hc_tot[:, 2 * d:])
-    yield grads
+    yield grads  # stage 3: the two first-layer weights (+ their biases and the time-embedding layer)
 
 
 class _GdmcfTrainFn(torch.autograd.Function):
