@@ -69,6 +69,7 @@ class Refresh(C.Structure):
         ("delta", C.c_void_p), ("ld_delta", C.c_int64), ("base", C.c_void_p),
         ("tcols", C.c_void_p),
         ("rowpart", C.c_void_p),
+        ("row_coef", C.c_void_p),
     ]
 
 

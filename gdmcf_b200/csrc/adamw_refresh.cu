@@ -33,6 +33,7 @@ struct Args {
   float* rowpart;   // [col_splits, rows] partial row sums (sum p^2, or sum of even columns when delta != NULL)
   float* delta; long long ld_delta;
   float* tcols; int n_tcols;
+  const float* row_coef;  // optional: effective gradient = g + row_coef[r] * p (deferred row-wise term, see header)
   int col_splits, tiles_per_split;
 };
 
@@ -81,6 +82,11 @@ adamw_refresh_kernel(const Args a) {
           gv[0] = G.x; gv[1] = G.y; gv[2] = G.z; gv[3] = G.w;
           mv[0] = M.x; mv[1] = M.y; mv[2] = M.z; mv[3] = M.w;
           vv[0] = V.x; vv[1] = V.y; vv[2] = V.z; vv[3] = V.w;
+          if (a.row_coef) {
+            const float rc = a.row_coef[r];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[j] = fmaf(rc, pv[j], gv[j]);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) update(pv[j], gv[j], mv[j], vv[j]);
           *reinterpret_cast<float4*>(a.p + off) = make_float4(pv[0], pv[1], pv[2], pv[3]);
@@ -95,9 +101,11 @@ adamw_refresh_kernel(const Args a) {
             mv[j] = ok ? a.m[off + j] : 0.f;
             vv[j] = ok ? a.v[off + j] : 0.f;
           }
+          const float rc = a.row_coef ? a.row_coef[r] : 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (c + j < a.cols) {
+              gv[j] = fmaf(rc, pv[j], gv[j]);
               update(pv[j], gv[j], mv[j], vv[j]);
               a.p[off + j] = pv[j]; a.m[off + j] = mv[j]; a.v[off + j] = vv[j];
             } else {
@@ -208,7 +216,9 @@ adamw_flat_hi_kernel(const Args a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (idx + j < total) {
-        adamw_update(kc, pv[j], a.g[(long long)r * a.ld_g + c], mv[j], vv[j]);
+        float gr = a.g[(long long)r * a.ld_g + c];
+        if (a.row_coef) gr = fmaf(a.row_coef[r], pv[j], gr);
+        adamw_update(kc, pv[j], gr, mv[j], vv[j]);
         if (c < a.cols_used) {
           if (a.hi) {
             __nv_bfloat16 hh, ll;
@@ -293,6 +303,7 @@ extern "C" int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float
   a.rowpart = (o.inv_norm || o.delta) ? o.rowpart : nullptr;
   a.delta = o.delta; a.ld_delta = o.ld_delta;
   a.tcols = o.tcols; a.n_tcols = o.n_tcols;
+  a.row_coef = o.row_coef;
   const int row_groups = (rows + TR - 1) / TR, tiles_c = (cols + TC - 1) / TC;
   a.col_splits = gdmcf_adamw_refresh_splits(rows, cols);
   a.tiles_per_split = (tiles_c + a.col_splits - 1) / a.col_splits;

@@ -150,32 +150,53 @@ spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, co
   }
 }
 
-// long_rows: {row, first_slot, n_slots}; one warp per (row, 64-column slab).
+// long_rows: {row, first_slot, n_slots}; one CTA per (row, 64-column slab). The 8 warps sum contiguous ranges of the
+// row's partial sums (slot order inside a range, 8 independent loads in flight), then warp 0 adds the 8 range sums in
+// range order: a fixed summation tree (deterministic), ~n_slots/64 L2 round trips for a hub row instead of n_slots.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 spmm_long_reduce_kernel(const int* __restrict__ long_rows, int n_long, const float* __restrict__ scratch,
                         const float* __restrict__ Z, float* __restrict__ Y, int d, float alpha, float beta) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float2 part_sm[WARPS_PER_CTA][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slabs = d >> 6;
   const long long total = (long long)n_long * slabs;
-  const long long warp0 = (long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * WARPS_PER_CTA;
-  for (long long w = warp0; w < total; w += nwarps) {
+  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
     const int lr = (int)(w / slabs);
     const int coff = (int)(w % slabs) * 64 + lane * 2;
     const int row = long_rows[3 * lr], first = long_rows[3 * lr + 1], cnt = long_rows[3 * lr + 2];
+    const int per = (cnt + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int s_begin = min(cnt, warp * per), s_end = min(cnt, s_begin + per);
     float2 acc = make_float2(0.f, 0.f);
-    for (int s = 0; s < cnt; ++s) {
-      const float2 p = *reinterpret_cast<const float2*>(scratch + (long long)(first + s) * d + coff);
-      acc.x += p.x;
-      acc.y += p.y;
+    const float* sp = scratch + (long long)first * d + coff;
+    for (int s = s_begin; s < s_end; s += 8) {
+      float2 part[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        part[q] = (s + q < s_end) ? *reinterpret_cast<const float2*>(sp + (long long)(s + q) * d) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        acc.x += part[q].x;
+        acc.y += part[q].y;
+      }
     }
-    float2 o = make_float2(alpha * acc.x, alpha * acc.y);
-    if (Z) {
-      const float2 z = *reinterpret_cast<const float2*>(Z + (long long)row * d + coff);
-      o.x = fmaf(beta, z.x, o.x);
-      o.y = fmaf(beta, z.y, o.y);
+    part_sm[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      float2 tot = part_sm[0][lane];
+#pragma unroll
+      for (int q = 1; q < WARPS_PER_CTA; ++q) {
+        tot.x += part_sm[q][lane].x;
+        tot.y += part_sm[q][lane].y;
+      }
+      float2 o = make_float2(alpha * tot.x, alpha * tot.y);
+      if (Z) {
+        const float2 z = *reinterpret_cast<const float2*>(Z + (long long)row * d + coff);
+        o.x = fmaf(beta, z.x, o.x);
+        o.y = fmaf(beta, z.y, o.y);
+      }
+      *reinterpret_cast<float2*>(Y + (long long)row * d + coff) = o;
     }
-    *reinterpret_cast<float2*>(Y + (long long)row * d + coff) = o;
+    __syncthreads();
   }
 }
 
@@ -299,7 +320,8 @@ extern "C" int gdmcf_spmm_csr_f32(const int32_t* col, const float* val, const in
     if ((rc = cuda_check_launch("spmm_items_kernel"))) return rc;
   }
   if (n_long > 0) {
-    spmm_long_reduce_kernel<<<grid_for_warps((long long)n_long * slabs), WARPS_PER_CTA * 32, 0, st>>>(
+    const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+    spmm_long_reduce_kernel<<<(int)std::min<long long>((long long)n_long * slabs, (long long)sms * 8), WARPS_PER_CTA * 32, 0, st>>>(
         long_rows, n_long, scratch, Z, Y, d, alpha, beta);
     if ((rc = cuda_check_launch("spmm_long_reduce_kernel"))) return rc;
   }

@@ -385,10 +385,10 @@ def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.9
 def adamw_refresh(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
                   weight_decay: float = 0.0, step: int = 1, step_dev=None, grad_scale: float = 1.0, cols_used: int = 0,
                   op: Optional[Bf16Mat] = None, op_t: Optional[Bf16Mat] = None, inv_norm=None, delta=None, base=None,
-                  tcols=None, rowpart=None) -> None:
+                  tcols=None, rowpart=None, row_coef=None) -> None:
     """AdamW on a 2-D weight fused with the refresh of its derived tensors (gdmcf_adamw_refresh). g may be a
     [rows, cols] view with a padded leading dimension."""
-    require_cuda(p, g, m, v, inv_norm, delta, base, tcols, rowpart)
+    require_cuda(p, g, m, v, inv_norm, delta, base, tcols, rowpart, row_coef)
     assert p.dim() == 2 and p.is_contiguous() and m.is_contiguous() and v.is_contiguous() and g.shape == p.shape and g.stride(1) == 1
     rows, cols = p.shape
     r = _lib.Refresh()
@@ -403,6 +403,9 @@ def adamw_refresh(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0
     if tcols is not None:
         assert tcols.is_contiguous()
         r.tcols, r.n_tcols = ptr(tcols), tcols.shape[1]
+    if row_coef is not None:
+        assert row_coef.dtype == torch.float32 and row_coef.is_contiguous() and row_coef.numel() == rows
+        r.row_coef = ptr(row_coef)
     if inv_norm is not None or delta is not None:
         assert rowpart is not None and rowpart.numel() >= adamw_refresh_splits(rows, cols) * rows
         r.rowpart = ptr(rowpart)

@@ -43,8 +43,10 @@ class FusedAdamW(torch.optim.Optimizer):
             K.counter_add(self._step_dev, 1)
 
     @torch.no_grad()
-    def update(self, params=None, grad_scale: float = 1.0) -> None:
-        """AdamW on `params` (default: every parameter with a gradient)."""
+    def update(self, params=None, grad_scale: float = 1.0, row_coef=None) -> None:
+        """AdamW on `params` (default: every parameter with a gradient). row_coef: {id(param): coef [rows]} — the
+        parameter's effective gradient is grad + coef[r] * param[r, :] (deferred norm term of the cosine scorer)."""
+        row_coef = row_coef or {}
         only = None if params is None else {id(p) for p in params}
         # weights whose derived tensors (bf16 operands, transposes, norms, one-hot tables) are refreshed by the same pass
         specs = {}
@@ -66,10 +68,13 @@ class FusedAdamW(torch.optim.Optimizer):
                 hyper = dict(lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"],
                              step=st["step"], step_dev=self._step_dev if self._capturable else None, grad_scale=grad_scale)
                 spec = specs.get(id(p))
+                rc = row_coef.get(id(p))
                 if spec is not None and p.dim() == 2 and p.is_contiguous() and p.grad.stride(1) == 1:
-                    K.adamw_refresh(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], **hyper, **spec[0])
+                    K.adamw_refresh(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], **hyper, **spec[0], row_coef=rc)
                     self._adopted.append((spec[2], p, spec[1]))
                 else:
+                    if rc is not None:
+                        p.grad.addcmul_(rc[:, None], p.data)
                     g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                     K.adamw_fused(p.data, g, st["exp_avg"], st["exp_avg_sq"], **hyper)
 

@@ -177,7 +177,8 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
     return grads
 
 
-def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Tensor, g_closs: torch.Tensor):
+def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Tensor, g_closs: torch.Tensor,
+                           defer_item_norm: bool = False):
     """Generator over the backward pass: yields {parameter name: gradient} as soon as a group is final, so that a
     data-parallel caller can start its all-reduce while the rest of the backward runs. Stage 1: the item table
     (412 MB at the Yelp shape, needs only dL/d(out) and the user tower); stage 2: sumW, GCN linears, user table;
@@ -201,8 +202,15 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     hcpT = K.cast_bf16_transpose(c.hcp_f32, with_lo=lo)  # [3d, B]
     gE = torch.empty_like(P["embedding_item.weight"])
     coef_i = -(c.inv_i * c.inv_i) * colsum
-    _mm_auto(model, GsT, hcpT, I, d3, B, out_f32=gE, row_t=_arange32(model, I, dev),
-             c1=_ones(model, I, dev), c2=coef_i, xt=P["embedding_item.weight"].detach())
+    if defer_item_norm:
+        # engine path: the row-wise norm term -E_i * ri^2 * c_i is applied by the optimizer pass, which reads E anyway
+        # (FusedAdamW.update(row_coef=...)); the contraction then writes 412 MB instead of reading and writing it
+        _mm_auto(model, GsT, hcpT, I, d3, B, out_f32=gE)
+        model._item_grad_rowcoef = coef_i
+    else:
+        _mm_auto(model, GsT, hcpT, I, d3, B, out_f32=gE, row_t=_arange32(model, I, dev),
+                 c1=_ones(model, I, dev), c2=coef_i, xt=P["embedding_item.weight"].detach())
+        model._item_grad_rowcoef = None
     yield {"embedding_item.weight": gE}
     # ---- cosine backward w.r.t. the user tower: d hc' = Gs E - hc' * ru^2 * r_b
     r_b = K.colsum_f32(rowpart, n_cb, B)
@@ -460,12 +468,15 @@ def training_losses(diff, model, x_start, reweight=False, index=None, inject: Op
 
 
 @torch.no_grad()
-def fused_train_stages(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None):
+def fused_train_stages(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None,
+                       defer_item_norm: bool = False):
     """`training_losses(...)["loss"].mean().backward()` without autograd, as a generator (used by engine.StepEngine):
     yields ("loss", mean loss [] f64) after the forward and loss bookkeeping, then ("grads", {parameter name: gradient})
     once per backward stage, in the order the gradients become final — a data-parallel caller starts the all-reduce of a
     stage while the generator computes the next one. Same kernels and arithmetic as the autograd path; the gradient
-    seeds are d mean(loss) / d mse_b = weight_b / (pt_b * B) and d mean(loss) / d closs = 0.1."""
+    seeds are d mean(loss) / d mse_b = weight_b / (pt_b * B) and d mean(loss) / d closs = 0.1.
+    defer_item_norm: the item table's gradient is yielded WITHOUT its row-wise norm term; the caller must pass
+    model._item_grad_rowcoef to FusedAdamW.update(row_coef=...) (and all-reduce it with the gradient)."""
     inject = inject or {}
     x0, B, I, dev, gdmcf, idx32, ts_disc, ts, ts32, pt = _prepare(diff, model, x_start, index, inject)
     if gdmcf:
@@ -484,7 +495,7 @@ def fused_train_stages(diff, model, x_start, reweight=False, index=None, inject:
     g_mse = (weight / pt / B).float()
     if gdmcf:
         g_closs = torch.full((), 0.1, dtype=torch.float32, device=dev)
-        for stage in _gdmcf_backward_stages(model, diff, c, g_mse, g_closs):
+        for stage in _gdmcf_backward_stages(model, diff, c, g_mse, g_closs, defer_item_norm):
             yield "grads", stage
     else:
         yield "grads", _dnn_backward(model, diff, c, g_mse)

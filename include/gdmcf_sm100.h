@@ -263,7 +263,9 @@ int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, f
  * delta[i,:] = W[:,2i+1] - W[:,2i] / base = sum_i W[:,2i] (models/DNN.py:1249-1251 at x_tU = one_hot(x0)), and a
  * contiguous copy of the trailing columns W[:, cols_used:] (tcols [rows, n_tcols]). rowpart: workspace of
  * gdmcf_adamw_refresh_splits(rows, cols) * rows floats (needed for inv_norm / delta). g may have a padded leading
- * dimension ld_g. Same update arithmetic as gdmcf_adamw_fused. */
+ * dimension ld_g. row_coef (optional, [rows]): the effective gradient is g + row_coef[r] * W[r,:] — the norm term of the
+ * cosine scorer's backward, d/dE of 1/||E_i||, is -E_i * c_i (models/DNN.py:1320-1325); deferring it to this pass saves
+ * the wgrad contraction a full read of E. Same update arithmetic as gdmcf_adamw_fused. */
 typedef struct gdmcf_refresh {
   int32_t cols_used;      /* 0 = all columns */
   int32_t n_tcols;
@@ -273,6 +275,7 @@ typedef struct gdmcf_refresh {
   float* delta; int64_t ld_delta; float* base;
   float* tcols;
   float* rowpart;
+  const float* row_coef;
 } gdmcf_refresh;
 int gdmcf_adamw_refresh_splits(int rows, int cols);
 int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float* m, float* v, int rows, int cols, float lr,

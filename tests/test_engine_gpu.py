@@ -148,3 +148,43 @@ def test_explicit_stages_match_autograd_path():
         err = (g - ref).norm() / ref.norm().clamp_min(1e-30)
         assert err < 1e-6, (n, err.item())
     assert {n for n, p in pa.items() if p.grad is not None} == set(grads)
+
+
+def test_deferred_item_norm_term_equals_epilogue_form():
+    """The engine applies the cosine scorer's row-wise norm gradient (-E_i * ri^2 * c_i) inside the AdamW pass; the
+    autograd path applies it in the wgrad contraction's epilogue. The effective gradients must agree."""
+    make, train_dev, test_dev, _, _, B, n_user = _setup(seed_model=3)
+    m_a, _, e_a = make(False)
+    m_b, _, e_b = make(False)
+    e_b.defer_item_norm = False
+    assert e_a.defer_item_norm
+    grads = []
+    for m, e in ((m_a, e_a), (m_b, e_b)):
+        e.load_resident(train_dev, test_dev, 0, B)
+        e.capture(warmup=1)
+        e.load_resident(train_dev, test_dev, 200, 200 + B)
+        before = m.embedding_item.weight.detach().clone()
+        e.step()
+        g = m.embedding_item.weight.grad.clone()
+        if e.defer_item_norm:
+            g = g + m._item_grad_rowcoef[:, None] * before
+        grads.append(g)
+    err = (grads[0] - grads[1]).norm() / grads[1].norm()
+    assert err < 1e-6, err.item()
+
+
+def test_adamw_row_coef_kernel():
+    from gdmcf_b200 import kernels as K
+    rows, cols = 130, 192
+    g0 = torch.Generator(device="cuda").manual_seed(5)
+    p = torch.randn(rows, cols, device="cuda", generator=g0) * 0.1
+    g = torch.randn(rows, cols, device="cuda", generator=g0)
+    coef = torch.randn(rows, device="cuda", generator=g0)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    op = K.cast_bf16(p)
+    K.adamw_refresh(p, g, m, v, lr=1e-2, weight_decay=0.0, step=1, op=op, row_coef=coef)
+    K.adamw_fused(p2.view(-1), torch.addcmul(g, coef[:, None], p2).view(-1), m2.view(-1), v2.view(-1), lr=1e-2, weight_decay=0.0, step=1)
+    torch.testing.assert_close(m, m2, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(p, p2, rtol=0, atol=1e-5)
+    assert torch.equal(op.hi, K.cast_bf16(p).hi)
