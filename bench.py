@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_graphs", action="store_true", help="launch the step kernel by kernel instead of replaying CUDA graphs")
+    ap.add_argument("--rank_after_update", action="store_true",
+                    help="step order train -> AdamW -> rank (default: train -> rank -> AdamW, which hides the all-reduces)")
+    ap.add_argument("--nccl_sms", type=int, default=32, help="SMs the contractions leave to NCCL while all-reduces are in flight (N > 1)")
     ap.add_argument("--kernel_times", action="store_true", help="print a per-kernel device-time table (torch.profiler) to stderr")
     ap.add_argument("--cpu_sample_users", type=int, default=200)
     return ap.parse_args()
@@ -60,7 +63,9 @@ def config_of(args, n_gpus):
             "interactions": P, "backbone": "DNNOneHotEmbeddingGCN", "dims": [args.dims], "steps": args.diff_steps,
             "noise_scale": 0.01, "batch_size": args.batch, "top_k": args.topk, "users_per_step": args.batch * n_gpus,
             "parallelism": f"dp{n_gpus} (user batches; grad all-reduce)", "l2": "inputs larger than L2 (weights+state ~4 GB)",
-            "precision": args.precision}
+            "precision": args.precision,
+            "step_order": "train(fwd+bwd) -> AdamW -> denoise+rank" if args.rank_after_update else "train(fwd+bwd) -> denoise+rank -> AdamW",
+            "nccl_sms": args.nccl_sms}
 
 
 def peaks():
@@ -242,7 +247,7 @@ def run_engine(args):
     # FusedAdamW.step -> diffusion.rank -> metrics_from_device, captured once as CUDA graph(s) around static inputs.
     eng = StepEngine(model, diffusion, opt, dist, batch_size=B, n_item=n_item, topk=k, topN=topN,
                      cap_train_nnz=window_nnz(train_sp), cap_gt_nnz=window_nnz(test_sp), reweight=True,
-                     graphs=not args.no_graphs)
+                     graphs=not args.no_graphs, rank_before_update=not args.rank_after_update, nccl_sms=args.nccl_sms)
     eng.load_resident(train_dev, test_dev, *users_of(0))
     eng.capture(warmup=3)
 
@@ -371,7 +376,7 @@ def run_engine(args):
 
     clocks = sampler.stop() if sampler is not None else None
 
-    if args.kernel_times and rank == 0:
+    if args.kernel_times:  # every rank runs the steps (they contain collectives); rank 0 prints
         # per-kernel device times of 3 steps (CUPTI through torch.profiler) -> stderr table; not part of the JSON line
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -381,9 +386,10 @@ def run_engine(args):
             torch.cuda.synchronize()
         rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
         tot = sum(e.device_time_total for e in rows)
-        print(f"kernel times over 3 steps: total {tot / 3e3:.3f} ms/step", file=sys.stderr)
-        for e in rows[:45]:
-            print(f"{e.device_time_total / 3e3:9.3f} ms/step  x{e.count / 3:6.1f}  {e.key[:100]}", file=sys.stderr)
+        if rank == 0:
+            print(f"kernel times over 3 steps: total {tot / 3e3:.3f} ms/step", file=sys.stderr)
+            for e in rows[:45]:
+                print(f"{e.device_time_total / 3e3:9.3f} ms/step  x{e.count / 3:6.1f}  {e.key[:100]}", file=sys.stderr)
 
     cpu = None
     if rank == 0 and G == 1 and not args.no_cpu_baseline:

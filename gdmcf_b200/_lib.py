@@ -86,6 +86,7 @@ SIGNATURES = {
     "gdmcf_lightgcn_propagate_f32": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "gdmcf_build_norm_adj": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "gdmcf_gemm_auto_splits": (_I, [_I, _I, _I]),
+    "gdmcf_gemm_set_sm_limit": (_I, [_I]),
     "gdmcf_gemm_workspace_bytes": (_SZ, [_I, _I, _I]),
     "gdmcf_gemm_bf16_tn": (_I, [C.POINTER(GemmDesc), C.POINTER(Epilogue), _I, _P, _SZ, _P]),
     "gdmcf_cast_bf16": (_I, [_P, _L, _P, _P, _L, _I, _I, _P]),

@@ -786,6 +786,15 @@ static int launch_2cta(const TmaMaps& maps, const Shape& shape, const gdmcf_epil
   return cuda_check_launch("gemm_bf16_tn_2cta_kernel");
 }
 
+// Upper bound on the SMs a contraction may occupy (0 = all). A data-parallel caller lowers it while gradient all-reduces
+// are in flight: the persistent kernels assume that all their CTAs run at once, so NCCL's CTAs must find free SMs instead
+// of delaying a few tiles' owners (which would double the kernel's duration).
+static int g_sm_limit = 0;
+static int sm_budget() {
+  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  return (g_sm_limit > 0 && g_sm_limit < sms) ? g_sm_limit : sms;
+}
+
 // GDMCF_GEMM_2CTA=0 routes every contraction through the 1-CTA kernel (A/B comparisons, fallback).
 static bool use_2cta() {
   static int v = -1;
@@ -802,12 +811,18 @@ static bool use_2cta() {
 using namespace gd;
 using namespace gd::gemm;
 
+extern "C" int gdmcf_gemm_set_sm_limit(int sms) {
+  if (sms < 0) { set_error("gemm_set_sm_limit: negative"); return GDMCF_EBADARG; }
+  g_sm_limit = sms;
+  return GDMCF_OK;
+}
+
 extern "C" int gdmcf_gemm_auto_splits(int m, int n, int k_total) {
   if (m <= 0 || n <= 0 || k_total <= 0) return 1;
   const int bn = pick_bn(n);
   const int tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
   const int total_kb = (k_total + BK - 1) / BK;
-  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  const int sms = sm_budget();
   if (tiles >= sms) return 1;
   int splits = sms / tiles;
   // keep at least 4 k-blocks per split so the pipeline prologue stays amortised
@@ -891,14 +906,14 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
     if (e->out_bf16 && (rc = make_map(&maps.o16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->out_bf16, g->m, g->n, e->ld_bf16, 32, 64))) return rc;
     if (e->out_bf16_lo && (rc = make_map(&maps.olo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->out_bf16_lo, g->m, g->n, e->ld_bf16, 32, 64))) return rc;
   }
-  const int sms = gdmcf_num_sms();
+  const int sms = sm_budget();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (pair) {
     const int units = ((shape.tiles_m + 1) / 2) * shape.tiles_n * shape.splits;
-    rc = launch_2cta(maps, shape, *e, std::min(units, (sms > 0 ? sms : 148) / 2), st);
+    rc = launch_2cta(maps, shape, *e, std::max(1, std::min(units, sms / 2)), st);
   } else {
     const int num_units = shape.tiles_m * shape.tiles_n * shape.splits;
-    const int grid = std::min(num_units, sms > 0 ? sms : 148);
+    const int grid = std::min(num_units, sms);
     rc = (bn == 256) ? launch<256>(maps, shape, *e, grid, st) : launch<128>(maps, shape, *e, grid, st);
   }
   if (rc) return rc;

@@ -106,6 +106,13 @@ def init(backend: str | None = None) -> Dist:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        td.init_process_group(backend=backend, rank=rank, world_size=world)
+        opts = None
+        if backend == "nccl" and os.environ.get("GDMCF_NCCL_HIGH_PRIORITY", "1") != "0":
+            # the all-reduces overlap with large-grid compute kernels: on a high-priority stream NCCL's CTAs take the
+            # SM slots that free up first instead of queueing behind the compute kernel's pending CTAs
+            opts = td.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+        td.init_process_group(backend=backend, rank=rank, world_size=world, pg_options=opts)
         owns = True
+        return Dist(rank, world, local, owns, td.new_group(backend=backend, pg_options=opts))
     return Dist(rank, world, local, owns, td.new_group(backend=backend))

@@ -33,13 +33,18 @@ from .train_step import fused_train_stages
 
 class StepEngine:
     def __init__(self, model, diffusion, optimizer, dist, *, batch_size: int, n_item: int, topk: int, topN: Sequence[int],
-                 cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None):
+                 cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
+                 rank_before_update: bool = True, nccl_sms: int = 0):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
         # the item table's norm-term gradient (-E_i * ri^2 * c_i) is applied inside the AdamW pass instead of the wgrad
         # contraction's epilogue (saves a 412 MB read of E per step at the Yelp shape)
         self.defer_item_norm = hasattr(model, "embedding_item")
+        # order inside a step: train (forward + backward) -> denoise + rank -> optimizer update (True), or the update
+        # before the ranking (False: the batch is ranked with the weights that already include its own gradient)
+        self.rank_before_update = rank_before_update
+        self.nccl_sms = nccl_sms  # SMs the contractions leave free while all-reduces are in flight (world_size > 1)
         dev = torch.device(device) if device is not None else next(model.parameters()).device
         self.dev = dev
         i32 = dict(dtype=torch.int32, device=dev)
@@ -123,6 +128,21 @@ class StepEngine:
                     yield ("gather_rows", len(groups) - 1, dense)
                 else:
                     yield ("reduce", len(groups) - 1, dense)
+                if self.nccl_sms > 0 and len(groups) == 1:
+                    # all-reduces are in flight from here to the last wait: the contractions leave SMs to NCCL
+                    K.gemm_set_sm_limit(max(2, _lib.load().gdmcf_num_sms() - self.nccl_sms))
+
+        def rank_and_metrics():
+            model.eval()
+            batch = self._batch()
+            idx_ = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
+            return idx_, evaluate_utils.metrics_from_device(idx_, batch.users, self.gt_rowptr, self.gt_col, self.topN)
+
+        if self.rank_before_update:
+            # denoise + rank this batch with the weights the training step just used; the optimizer update (and, with
+            # several ranks, the wait for the gradient all-reduces) comes after, so the collectives hide behind ~1.3 ms of
+            # inference work. One train step and one rank step per batch either way.
+            idx, sums = rank_and_metrics()
         opt.begin_step()
         # update order: groups whose exchange went over the small-message communicator first (they are complete long
         # before the big all-reduces), then the others in the order their all-reduces were issued
@@ -139,10 +159,10 @@ class StepEngine:
                             K.scatter_rows_add(self._recv_rows[r], self._recv_idx[r], gU, self.B, d)
             opt.update(plist, grad_scale=1.0 / G, row_coef=row_coef)
         opt.end_step()
-        model.eval()
-        batch = self._batch()
-        idx = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
-        sums = evaluate_utils.metrics_from_device(idx, batch.users, self.gt_rowptr, self.gt_col, self.topN)
+        if G > 1 and self.nccl_sms > 0:
+            K.gemm_set_sm_limit(0)
+        if not self.rank_before_update:
+            idx, sums = rank_and_metrics()
         self._result = (loss, idx, sums)
 
     # -- communication actions (eager NCCL between graph segments) -----------------------------------

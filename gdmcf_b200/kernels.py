@@ -145,6 +145,11 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+def gemm_set_sm_limit(sms: int) -> None:
+    """Upper bound on the SMs the contraction kernels occupy from now on (0 = all). See gdmcf_gemm_set_sm_limit."""
+    check(load().gdmcf_gemm_set_sm_limit(int(sms)), "gemm_set_sm_limit")
+
+
 def gemm(a: Sequence[torch.Tensor], b: Sequence[torch.Tensor], m: int, n: int, k: Sequence[int], *,
          mode: int = EPI_STORE, act: int = ACT_NONE, alpha: float = 1.0, out_f32=None, out_bf16=None, out_bf16_lo=None,
          bias=None, ld_bias: int = 0, row_t=None, t_const: int = 0, row_scale=None, col_scale=None, c1=None, c2=None,

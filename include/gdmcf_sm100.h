@@ -133,6 +133,9 @@ typedef struct {
 
 /* Split count that fills the SMs for this shape (1 = no split-K). */
 int gdmcf_gemm_auto_splits(int m, int n, int k_total);
+/* Upper bound on the SMs the persistent contraction kernels occupy from now on (0 = all SMs): lets a data-parallel
+ * caller leave SMs to NCCL while all-reduces overlap with contractions. Process-wide, not thread-safe. */
+int gdmcf_gemm_set_sm_limit(int sms);
 /* Bytes of fp32 workspace needed for `splits` > 1 (0 for splits == 1). */
 size_t gdmcf_gemm_workspace_bytes(int m, int n, int splits);
 int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue* e, int splits, void* workspace,
