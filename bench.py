@@ -29,9 +29,10 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {  # name: (n_user, n_item, n_pairs, seed)
     "yelp": (54574, 34395, 1402736, 0),
     "amazon": (108822, 94949, 3146256, 1),
+    "scaled": (1000000, 200000, 50000000, 2),  # BASELINE.json configs[4]
     "tiny": (2000, 1500, 40000, 3),
 }
-METRIC = "users/sec train+denoise+rank (Yelp shape)"
+METRIC = "users/sec train+denoise+rank (Yelp shape)"  # the workload actually run is named in config.workload
 OUT = sys.stdout
 
 
@@ -339,9 +340,19 @@ def run_engine(args):
     breakdown = [{"mnk": kk, "launches_per_step": v_[0] / n_prof, "ms_per_step": v_[1] / n_prof,
                   "tflops": v_[2] / (v_[1] * 1e-3) / 1e12} for kk, v_ in sorted(by_shape.items(), key=lambda kv: -kv[1][1])]
     pk = peaks()
+    # DRAM traffic of the dominant launch shape (the reverse-step scorer) from the committed ncu --set full capture
+    traffic, traffic_src = None, None
+    ncu_path = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
+    if args.workload == "yelp" and os.path.exists(ncu_path):
+        with open(ncu_path) as f:
+            cap = json.load(f).get("gemm_scorer_post")
+        if cap:
+            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+            traffic_src = ("profiles/r1_ncu_summary.json: scorer launch (400 x 34395 x 3000, posterior epilogue), algorithmic "
+                           f"{cap['algorithmic_bytes']} B")
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (+ splitk_reduce_kernel)", "achieved": achieved,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_of": traffic_src,
                 "peak_source": f"{pk['src']} (sustained bf16)", "launches_per_step": len(records) / n_prof,
                 "gemm_ms_per_step": gemm_ms / n_prof, "gemm_share_of_step": (gemm_ms / n_prof) / (ms / Kst),
                 "flops_per_step": gemm_flops / n_prof, "by_shape": breakdown}
@@ -369,9 +380,14 @@ def run_engine(args):
         bytes_alg = 3 * (nnz * 8 + (N + 1) * 4 + 2 * N * 64 * 4)
         t_med = sorted(ts)[len(ts) // 2]
         gbs = bytes_alg / (t_med * 1e-3) / 1e9
-        spmm = {"bound": "hbm", "kernel": "spmm_items_kernel x3 (lightgcn_propagate, K=3, d=64, fp32)", "achieved": gbs,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "ms": t_med, "algorithmic_bytes": bytes_alg,
-                "N": N, "nnz": nnz, "l2": "flushed between iterations (256 MiB write)"}
+        gather_bytes = 3 * nnz * 64 * 4  # rows the kernel must pull from L2 (the tables are L2 resident): nnz x d x 4 per layer
+        spmm = {"bound": "hbm", "kernel": "spmm_items_kernel + spmm_long_reduce_kernel x3 (lightgcn_propagate, K=3, d=64, fp32)",
+                "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "ms": t_med,
+                "algorithmic_bytes": bytes_alg, "N": N, "nnz": nnz, "l2": "flushed between iterations (256 MiB write)",
+                "l2_gather": {"bytes": gather_bytes, "achieved_tbs": gather_bytes / (t_med * 1e-3) / 1e12,
+                              "note": "the binding resource: nnz x 256 B row gathers over the L2 -> SM fabric (measured "
+                                      "ceiling ~9 TB/s, profiles/r1_ncu_summary.json); 70 % of HBM peak on the algorithmic "
+                                      "bytes would need 33 TB/s of gathers"}}
         del lg, flush
 
     clocks = sampler.stop() if sampler is not None else None

@@ -1,0 +1,130 @@
+"""Full-size checks (BASELINE.json shapes: Yelp 54 574 x 34 395, Amazon-Book 108 822 x 94 949) through size-independent
+properties: the oracle is too slow at these sizes, so the CUDA path is checked against plain torch fp32 evaluations of
+the same op on the device (SpMM, top-k), against invariants of the domain (no history item is ranked, scores sorted,
+idempotence of the noise-free reverse loop, linearity of the propagation), and against the CPU metric oracle on the
+ranked lists."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {"yelp": (54574, 34395, 1402736, 0), "amazon": (108822, 94949, 3146256, 1)}
+
+
+def _data(name):
+    from gdmcf_b200 import data_utils
+    U, I, P, seed = SHAPES[name]
+    tr, va, te = data_utils.synthetic_interactions(U, I, P, seed)
+    n_user, n_item = int(tr[:, 0].max()) + 1, int(tr[:, 1].max()) + 1
+    mk = lambda p: sp.csr_matrix((np.ones(len(p), dtype=np.float32), (p[:, 0], p[:, 1])), shape=(n_user, n_item))  # noqa: E731
+    return tr, mk(tr), mk(te), n_user, n_item
+
+
+@pytest.fixture(scope="module")
+def yelp():
+    return _data("yelp")
+
+
+def test_yelp_shape_denoise_rank_invariants(yelp):
+    from gdmcf_b200 import data_utils, evaluate_utils
+    from gdmcf_b200.models import gaussian_diffusion as gd
+    from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    from oracle import gdmcf_oracle as O
+    _, train_sp, test_sp, n_user, n_item = yelp
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    model = DNNOneHotEmbeddingGCN([n_item, 1000], [1000, n_item], 10, item_num=n_item, user_num=n_user).to(dev).eval()
+    diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, 5, dev, discrete=0.9995,
+                                        CatOneHot=True)
+    diff.indexIn = True
+    train_dev, test_dev = data_utils.DeviceInteractions(train_sp, dev), data_utils.DeviceInteractions(test_sp, dev)
+    B, k = 400, 20
+    users = torch.arange(1200, 1200 + B, dtype=torch.int32, device=dev)
+    batch = train_dev.batch(users)
+    idx, val = diff.rank(model, batch, k, hist=train_dev.csr, with_values=True)
+    idx2, val2 = diff.rank(model, batch, k, hist=train_dev.csr, with_values=True)
+    assert torch.equal(idx, idx2) and torch.equal(val, val2)             # noise-free reverse loop: idempotent
+    assert (val[:, :-1] >= val[:, 1:]).all() and torch.isfinite(val).all()  # sorted, finite
+    pred = diff.p_sample(model, batch, 0, index=users).clone()
+    rows = train_sp[users.cpu().numpy()]
+    hist = torch.from_numpy(np.asarray(rows.todense(), dtype=bool)).to(dev)
+    assert not hist.gather(1, idx.long()).any()                          # no training item is ranked (main.py:299)
+    pred[hist] = -float("inf")
+    tv, ti = torch.topk(pred, k)                                         # plain torch evaluation of main.py:299-301
+    assert torch.equal(tv, val)
+    same = (ti == idx.long())
+    gap_ok = same | (tv == pred.gather(1, idx.long()))                   # only exact score ties may order differently
+    assert gap_ok.all()
+    # metric sums on the device == computeTopNAccuracy (evaluate_utils.py:6-52) of the CPU oracle on the same lists
+    sums = evaluate_utils.metrics_from_device(idx, users, test_dev.rowptr, test_dev.col, [10, 20])
+    got = evaluate_utils.finalize_metrics(sums, B)
+    un = users.cpu().numpy()
+    target = [test_sp.indices[test_sp.indptr[u]:test_sp.indptr[u + 1]].tolist() for u in un]
+    want = O.computeTopNAccuracy(target, idx.cpu().tolist(), [10, 20])
+    assert [list(x) for x in got] == [list(x) for x in want]
+
+
+def test_yelp_shape_lightgcn_vs_torch_sparse_and_linearity(yelp):
+    from gdmcf_b200 import kernels as K
+    from gdmcf_b200.lightGCN import LightGCN
+    tr, _, _, n_user, n_item = yelp
+    lg = LightGCN({"user_id_idx": tr[:, 0], "item_id_idx": tr[:, 1]}, n_user, n_item, 3, 64, device="cuda")
+    rowptr, col, val = lg.norm_adj_csr
+    N = n_user + n_item
+    # A~ is symmetric with entries d_u^-1/2 d_i^-1/2 (lightGCN.py:145-178)
+    A = torch.sparse_csr_tensor(rowptr.long(), col.long(), val, size=(N, N))
+    E0 = lg.E0.weight.detach()
+    ref, cur = E0.clone(), E0
+    for _ in range(3):
+        cur = torch.sparse.mm(A, cur)
+        ref = ref + cur
+    ref = ref / 4                                                         # mean over the K+1 layer outputs (:188-189)
+    got = K.lightgcn_propagate(lg.plan, col, val, E0, 3)
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-5
+    X = torch.randn_like(E0)
+    lin = K.lightgcn_propagate(lg.plan, col, val, 0.5 * E0 - 2.0 * X, 3)
+    comb = 0.5 * got - 2.0 * K.lightgcn_propagate(lg.plan, col, val, X, 3)
+    assert ((lin - comb).norm() / comb.norm()).item() < 1e-5
+    # determinism of the fixed summation order
+    assert torch.equal(got, K.lightgcn_propagate(lg.plan, col, val, E0, 3))
+
+
+def test_amazon_shape_engine_step_bookkeeping():
+    """One captured step at the Amazon-Book shape: finite loss, Lt_count advanced by exactly B draws, every trained
+    parameter moved, the dead out_layers untouched, ranked lists free of history items."""
+    from gdmcf_b200 import data_utils, dist_utils
+    from gdmcf_b200.engine import StepEngine
+    from gdmcf_b200.models import gaussian_diffusion as gd
+    from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    from gdmcf_b200.optim import FusedAdamW
+    _, train_sp, test_sp, n_user, n_item = _data("amazon")
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    model = DNNOneHotEmbeddingGCN([n_item, 1000], [1000, n_item], 10, item_num=n_item, user_num=n_user).to(dev)
+    diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, 5, dev, discrete=0.9995,
+                                        CatOneHot=True)
+    diff.indexIn = True
+    opt = FusedAdamW(model.parameters(), lr=1e-5, weight_decay=0.0, modules=[model], capturable=True)
+    B, k = 400, 20
+    train_dev, test_dev = data_utils.DeviceInteractions(train_sp, dev), data_utils.DeviceInteractions(test_sp, dev)
+    cap = lambda m: int(np.diff(m.indptr[::B]).max())  # noqa: E731
+    eng = StepEngine(model, diff, opt, dist_utils.Dist(), batch_size=B, n_item=n_item, topk=k, topN=[10, k],
+                     cap_train_nnz=cap(train_sp), cap_gt_nnz=cap(test_sp))
+    eng.load_resident(train_dev, test_dev, 0, B)
+    eng.capture(warmup=1)
+    before = {n: p.detach().clone() for n, p in model.named_parameters() if p.numel() < 4_000_000 or n == "sumW"}
+    count0 = diff.Lt_count.sum().item()
+    eng.load_resident(train_dev, test_dev, 4000, 4000 + B)
+    loss, idx, sums = eng.step()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss) and torch.isfinite(sums).all()
+    assert diff.Lt_count.max().item() <= diff.history_num_per_term and diff.Lt_count.sum().item() >= count0
+    for n, p0 in before.items():
+        moved = not torch.equal(p0, dict(model.named_parameters())[n].detach())
+        assert moved == (not n.startswith("out_layers")), n
+    rows = train_sp[np.arange(4000, 4000 + B)]
+    hist = torch.from_numpy(np.asarray(rows.todense(), dtype=bool)).to(dev)
+    assert not hist.gather(1, idx.long()).any()
+    assert (sums[:, 0] >= 0).all() and (sums[:, 1] <= B).all()
