@@ -75,7 +75,15 @@ adamw_refresh_kernel(const Args a) {
         const long long off = (long long)r * a.cols + c;
         const long long goff = (long long)r * a.ld_g + c;
         float gv[4], mv[4], vv[4];
-        if (VEC == 4) {
+        if (!a.g) {  // refresh only: derive the tensors from the current weights, no update
+          if (VEC == 4) {
+            const float4 P = *reinterpret_cast<const float4*>(a.p + off);
+            pv[0] = P.x; pv[1] = P.y; pv[2] = P.z; pv[3] = P.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pv[j] = (c + j < a.cols) ? a.p[off + j] : 0.f;
+          }
+        } else if (VEC == 4) {
           const float4 P = *reinterpret_cast<const float4*>(a.p + off), G = *reinterpret_cast<const float4*>(a.g + goff);
           const float4 M = *reinterpret_cast<const float4*>(a.m + off), V = *reinterpret_cast<const float4*>(a.v + off);
           pv[0] = P.x; pv[1] = P.y; pv[2] = P.z; pv[3] = P.w;
@@ -272,13 +280,15 @@ extern "C" int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float
                                    float beta1, float beta2, float eps, float weight_decay, int step,
                                    const int64_t* step_dev, float grad_scale, const gdmcf_refresh* out,
                                    gdmcf_stream_t stream) {
-  if (!p || !g || !m || !v || !out || rows <= 0 || cols <= 0 || ld_g < cols || (step < 1 && !step_dev)) {
+  // g == NULL: refresh only (m, v unused): the derived tensors are recomputed from the current weights by the same code
+  // that produces them during training, so both paths agree bit for bit (row sums have a fixed order per geometry)
+  if (!p || !out || rows <= 0 || cols <= 0 || (g && (!m || !v || ld_g < cols || (step < 1 && !step_dev)))) {
     set_error("adamw_refresh: bad arguments");
     return GDMCF_EBADARG;
   }
   const gdmcf_refresh& o = *out;
   const int cols_used = o.cols_used > 0 ? o.cols_used : cols;
-  const bool vec = (cols % 4 == 0) && (ld_g % 4 == 0) && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  const bool vec = (cols % 4 == 0) && (!g || ld_g % 4 == 0) && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   if (cols_used > cols || (o.hi && ((o.ld_hi & 7) || o.ld_hi < cols_used || ((uintptr_t)o.hi & 15) || ((uintptr_t)o.lo & 15))) ||
       (o.t_hi && ((o.ld_t & 7) || o.ld_t < rows || ((uintptr_t)o.t_hi & 15) || ((uintptr_t)o.t_lo & 15))) ||
       (o.lo && !o.hi) || (o.t_lo && !o.t_hi) ||
@@ -309,7 +319,7 @@ extern "C" int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float
   a.tiles_per_split = (tiles_c + a.col_splits - 1) / a.col_splits;
   const long long ctas = (long long)row_groups * a.col_splits;
   if (ctas > 0x7fffffffLL) { set_error("adamw_refresh: too many tiles"); return GDMCF_EBADARG; }
-  const bool flat_ok = !vec && !a.t_hi && !a.delta && !a.rowpart && ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  const bool flat_ok = g && !vec && !a.t_hi && !a.delta && !a.rowpart && ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   if (vec) {
     adamw_refresh_kernel<4><<<(int)ctas, THREADS, 0, st>>>(a);
   } else if (flat_ok) {

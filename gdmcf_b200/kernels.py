@@ -418,6 +418,32 @@ def adamw_refresh(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0
                                      weight_decay, step, ptr(step_dev), grad_scale, C.byref(r), stream()), "adamw_refresh")
 
 
+def refresh_derived(p, *, cols_used: int = 0, op: Optional[Bf16Mat] = None, op_t: Optional[Bf16Mat] = None, inv_norm=None,
+                    delta=None, base=None, tcols=None, rowpart=None) -> None:
+    """The derived tensors of a 2-D weight, computed from its current value by the same kernel that refreshes them during
+    training (gdmcf_adamw_refresh with g == NULL), so that lazily built and in-training values agree bit for bit."""
+    require_cuda(p, inv_norm, delta, base, tcols, rowpart)
+    assert p.dim() == 2 and p.is_contiguous()
+    rows, cols = p.shape
+    r = _lib.Refresh()
+    r.cols_used = cols_used
+    if op is not None:
+        r.hi, r.lo, r.ld_hi = ptr(op.hi), ptr(op.lo), op.ld
+    if op_t is not None:
+        r.t_hi, r.t_lo, r.ld_t = ptr(op_t.hi), ptr(op_t.lo), op_t.ld
+    r.inv_norm = ptr(inv_norm)
+    if delta is not None:
+        r.delta, r.ld_delta, r.base = ptr(delta), delta.stride(0), ptr(base)
+    if tcols is not None:
+        r.tcols, r.n_tcols = ptr(tcols), tcols.shape[1]
+    if inv_norm is not None or delta is not None:
+        if rowpart is None:
+            rowpart = torch.empty(adamw_refresh_splits(rows, cols) * rows, dtype=torch.float32, device=p.device)
+        r.rowpart = ptr(rowpart)
+    check(load().gdmcf_adamw_refresh(ptr(p), None, 0, None, None, rows, cols, 0.0, 0.9, 0.999, 1e-8, 0.0, 1, None, 1.0,
+                                     C.byref(r), stream()), "adamw_refresh(refresh only)")
+
+
 def adamw_refresh_splits(rows: int, cols: int) -> int:
     return load().gdmcf_adamw_refresh_splits(rows, cols)
 

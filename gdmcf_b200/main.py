@@ -91,6 +91,31 @@ def evaluate(diffusion, model, train_dev, gt_dev, hist_devs, n_user, batch_size,
     return evaluate_utils.finalize_metrics(sums, n_batches * batch_size)
 
 
+def save_checkpoint(path, epoch, model, optimizer, diffusion, rng, best):
+    """Everything a bit-exact continuation needs: weights, AdamW moments and step counters, the
+    importance-sampling history, the device-resident RNG epoch, the shuffle generator and the model-selection state."""
+    torch.save({"epoch": epoch, "model": model.state_dict(), "optimizer": optimizer.state_dict(),
+                "optimizer_step_dev": None if optimizer._step_dev is None else int(optimizer._step_dev.item()),
+                "Lt_history": diffusion.Lt_history.cpu(), "Lt_count": diffusion.Lt_count.cpu(),
+                "rng_epoch": None if diffusion._epoch is None else int(diffusion._epoch.item()),
+                "shuffle_rng": rng.bit_generator.state, "best": best}, path)
+
+
+def load_checkpoint(path, model, optimizer, diffusion, rng, device):
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    model.load_state_dict(ck["model"])
+    model.weights_updated()
+    optimizer.load_state_dict(ck["optimizer"])
+    if ck["optimizer_step_dev"] is not None:
+        optimizer._step_dev = torch.tensor([ck["optimizer_step_dev"]], dtype=torch.int64, device=device)
+    diffusion.Lt_history = ck["Lt_history"].to(device)
+    diffusion.Lt_count = ck["Lt_count"].to(device)
+    if ck["rng_epoch"] is not None:
+        diffusion._epoch = torch.tensor([ck["rng_epoch"]], dtype=torch.int64, device=device)
+    rng.bit_generator.state = ck["shuffle_rng"]
+    return ck["epoch"], ck["best"]
+
+
 def main(args):
     dist = dist_utils.init()
     out_path = os.path.join(args.log_name, args.dataset, datetime.now().strftime('%Y%m%d'), args.out_name)
@@ -135,8 +160,14 @@ def main(args):
     best_recall, best_epoch = -100, 0
     best_test_results = None
     rng = np.random.default_rng(args.random_seed)
+    start_epoch = 1
+    if args.resume:
+        last, best = load_checkpoint(args.resume, model, optimizer, diffusion, rng, device)
+        best_recall, best_epoch, best_test_results = best
+        start_epoch = last + 1
+        print('resumed from', args.resume, 'after epoch', last)
     print("Start training...")
-    for epoch in range(1, args.epochs + 1):
+    for epoch in range(start_epoch, args.epochs + 1):
         if epoch - best_epoch >= 200:
             print('-' * 18)
             print('Exiting from training early')
@@ -171,6 +202,9 @@ def main(args):
                     model_path = os.path.join(out_path, 'model.pth')
                     print('model_path:', model_path)
                     torch.save(model, model_path)
+        if args.checkpoint_every and epoch % args.checkpoint_every == 0 and dist.rank == 0:
+            save_checkpoint(os.path.join(out_path, 'checkpoint.pt'), epoch, model, optimizer, diffusion, rng,
+                            (best_recall, best_epoch, best_test_results))
         print("Runing Epoch {:03d} ".format(epoch) + 'train loss {:.4f}'.format(float(total_loss)) + " costs " +
               time.strftime("%H: %M: %S", time.gmtime(time.time() - start_time)))
         print('---' * 18)
@@ -178,6 +212,7 @@ def main(args):
     print('===' * 18)
     print("End. Best Epoch {:03d} ".format(best_epoch))
     evaluate_utils.print_results(None, None, best_test_results)
+    main.last_model = model  # handle for callers / tests (the reference keeps everything local to main())
     print("End time: ", time.strftime('%Y-%m-%d %H:%M:%S', time.localtime(time.time())))
     dist.shutdown()
     return best_test_results

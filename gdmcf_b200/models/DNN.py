@@ -366,12 +366,25 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
 
     def _onehot_tables(self):
         w2 = self.in_layers2[0].weight
-        return self._ops.get("onehot", [w2], lambda prev: K.onehot_tables(w2.detach(), self.hidden, self.n_item, out=prev))
+        def build(prev):
+            d, I = self.hidden, self.n_item
+            ok = prev is not None and prev[0].shape == (d,) and prev[1].shape == (I, K.round_up(d, 4)) and prev[0].device == w2.device
+            base = prev[0] if ok else torch.empty(d, dtype=torch.float32, device=w2.device)
+            delta = prev[1] if ok else torch.zeros(I, K.round_up(d, 4), dtype=torch.float32, device=w2.device)
+            # same producer as FusedAdamW's fused refresh: values agree bit for bit with the in-training tables
+            K.refresh_derived(w2.detach(), cols_used=2 * I, delta=delta, base=base)
+            return base, delta
+        return self._ops.get("onehot", [w2], build)
 
     def _item_operands(self):
         E = self.embedding_item.weight
         e_op = self._weight_operand("E", E)
-        inv = self._ops.get("E.inv", [E], lambda prev: K.row_inv_norm(E.detach(), out=prev))
+        def build_inv(prev):
+            ok = prev is not None and prev.shape == (E.shape[0],) and prev.device == E.device
+            inv = prev if ok else torch.empty(E.shape[0], dtype=torch.float32, device=E.device)
+            K.refresh_derived(E.detach(), inv_norm=inv)  # same producer as FusedAdamW's fused refresh
+            return inv
+        inv = self._ops.get("E.inv", [E], build_inv)
         return e_op, inv
 
     def refresh_specs(self):

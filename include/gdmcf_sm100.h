@@ -268,7 +268,8 @@ int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, int64_t n, f
  * gdmcf_adamw_refresh_splits(rows, cols) * rows floats (needed for inv_norm / delta). g may have a padded leading
  * dimension ld_g. row_coef (optional, [rows]): the effective gradient is g + row_coef[r] * W[r,:] — the norm term of the
  * cosine scorer's backward, d/dE of 1/||E_i||, is -E_i * c_i (models/DNN.py:1320-1325); deferring it to this pass saves
- * the wgrad contraction a full read of E. Same update arithmetic as gdmcf_adamw_fused. */
+ * the wgrad contraction a full read of E. Same update arithmetic as gdmcf_adamw_fused.
+ * g == NULL: refresh only — no update, m / v ignored; the derived tensors are recomputed from the current weights. */
 typedef struct gdmcf_refresh {
   int32_t cols_used;      /* 0 = all columns */
   int32_t n_tcols;

@@ -450,6 +450,15 @@ def test_adamw_refresh_equals_adamw_plus_separate_refresh(K, rows, cols, cols_us
         torch.testing.assert_close(kw["base"], w[:, 0::2].double().sum(1).float(), rtol=1e-6, atol=1e-7)
     if cols_used:
         assert torch.equal(kw["tcols"], p2[:, cols_used:])
+    # refresh-only form (lazy builders): same producer, bit-identical derived tensors
+    if kind == "t_inv":
+        inv2 = torch.empty(rows, device="cuda")
+        K.refresh_derived(p, inv_norm=inv2)
+        assert torch.equal(inv2, kw["inv_norm"])
+    if kind == "onehot":
+        base2, delta2 = torch.empty_like(kw["base"]), torch.zeros_like(kw["delta"])
+        K.refresh_derived(p, cols_used=cols_used, delta=delta2, base=base2)
+        assert torch.equal(base2, kw["base"]) and torch.equal(delta2, kw["delta"])
 
 
 @pytest.mark.parametrize("rows,cols,aligned", [(400, 34395, True), (70, 130, True), (33, 77, False)])
