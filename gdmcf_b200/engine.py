@@ -34,7 +34,8 @@ from .train_step import fused_train_stages
 class StepEngine:
     def __init__(self, model, diffusion, optimizer, dist, *, batch_size: int, n_item: int, topk: int, topN: Sequence[int],
                  cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
-                 rank_before_update: bool = True, nccl_sms: int = 0):
+                 rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
+                 shard_min_bytes: int = 64 << 20):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
@@ -62,6 +63,12 @@ class StepEngine:
         # data parallel: the user table's gradient has B non-zero rows per rank -> all-gather (ids, rows), 1.6 MB instead
         # of all-reducing the dense [n_user, d] gradient (218 MB at the Yelp shape)
         G = dist.world_size
+        # data parallel: the big matrices' gradients are reduce-scattered by row blocks, each rank runs AdamW on its block
+        # only (1/G of the optimizer pass) and the updated blocks are all-gathered; the derived tensors are then refreshed
+        # from the gathered weights. Same communication volume as an all-reduce, 1/G of the optimizer's HBM traffic.
+        self._shards = {}
+        if G > 1 and shard_optimizer:
+            self._setup_shards(shard_min_bytes)
         self.sparse_user_rows = G > 1 and hasattr(model, "embedding_user")
         if self.sparse_user_rows:
             d = model.embedding_user.weight.shape[1]
@@ -69,6 +76,23 @@ class StepEngine:
             self._send_rows = torch.zeros(batch_size, d, dtype=torch.float32, device=dev)
             self._recv_idx = torch.zeros(G, batch_size, **i32)
             self._recv_rows = torch.zeros(G, batch_size, d, dtype=torch.float32, device=dev)
+
+    def _setup_shards(self, min_bytes: int) -> None:
+        G, dev = self.dist.world_size, self.dev
+        views = {}
+        for name, p in self.model.named_parameters():
+            if p.dim() != 2 or p.numel() * 4 < min_bytes or name.startswith("embedding_user") or name.startswith("out_layers"):
+                continue
+            rows, cols = p.shape
+            R = (rows + G - 1) // G
+            gbuf = torch.zeros(R * G, K.round_up(cols, 4), dtype=torch.float32, device=dev)  # 16 B-aligned rows (TMA store)
+            pbuf = torch.zeros(R * G, cols, dtype=torch.float32, device=dev)
+            pbuf[:rows].copy_(p.data)
+            p.data = pbuf[:rows]  # the parameter now lives in a row-padded buffer: equal blocks for the all-gather
+            views[name] = gbuf[:rows, :cols]
+            self._shards[name] = dict(p=p, R=R, gbuf=gbuf, pbuf=pbuf, gview=views[name])
+        self.model._grad_views = views
+        self.model.weights_updated()
 
     # -- inputs ------------------------------------------------------------------------------------
     def load_resident(self, train_dev, gt_dev, lo: int, hi: int) -> None:
@@ -111,15 +135,22 @@ class StepEngine:
         for _, grads in stages:
             names = list(grads)
             for n in names:
+                sh = self._shards.get(n)
+                if sh is not None and grads[n].data_ptr() != sh["gview"].data_ptr():
+                    sh["gview"].copy_(grads[n])  # gradient not produced in place (no _grad_buffer hook for this weight)
+                    grads[n] = sh["gview"]
                 params[n].grad = grads[n]
             groups.append([params[n] for n in names])
             if "embedding_item.weight" in grads and getattr(model, "_item_grad_rowcoef", None) is not None:
                 row_coef[id(params["embedding_item.weight"])] = model._item_grad_rowcoef
             if G > 1:
-                dense = [grads[n] for n in names if not (self.sparse_user_rows and n == "embedding_user.weight")]
+                dense = [grads[n] for n in names
+                         if not (self.sparse_user_rows and n == "embedding_user.weight") and n not in self._shards]
                 dense += [row_coef[id(params[n])] for n in names if id(params[n]) in row_coef]  # summed like the gradient
-                if sum(t.numel() * t.element_size() for t in dense) < (64 << 20):
+                rs = [n for n in names if n in self._shards]
+                if not rs and sum(t.numel() * t.element_size() for t in dense) < (64 << 20):
                     self._small_keys.add(len(groups) - 1)
+                dense = (dense, rs)
                 if self.sparse_user_rows and "embedding_user.weight" in grads:
                     # only B rows of the user table carry a gradient: exchange (ids, rows) instead of the dense table
                     idx, rows = model._user_grad_rows
@@ -147,6 +178,8 @@ class StepEngine:
         # update order: groups whose exchange went over the small-message communicator first (they are complete long
         # before the big all-reduces), then the others in the order their all-reduces were issued
         order = sorted(range(len(groups)), key=lambda gi: (0 if gi in self._small_keys else 1, gi))
+        by_param = {id(sh["p"]): (n, sh) for n, sh in self._shards.items()}
+        gathers = []
         for gi in order:
             plist = groups[gi]
             if G > 1:
@@ -157,8 +190,26 @@ class StepEngine:
                     for r in range(G):
                         if r != self.dist.rank:
                             K.scatter_rows_add(self._recv_rows[r], self._recv_idx[r], gU, self.B, d)
-            opt.update(plist, grad_scale=1.0 / G, row_coef=row_coef)
+            opt.update([p for p in plist if id(p) not in by_param], grad_scale=1.0 / G, row_coef=row_coef)
+            mine = [by_param[id(p)] for p in plist if id(p) in by_param]
+            for n, sh in mine:  # this rank's row block of the reduce-scattered gradient
+                r0 = self.dist.rank * sh["R"]
+                opt.update_rows(sh["p"], sh["gview"], r0, r0 + sh["R"], grad_scale=1.0 / G, row_coef=row_coef.get(id(sh["p"])))
+            if mine:
+                yield ("gather", ("ag", gi), [n for n, _ in mine])
+                gathers.append((("ag", gi), mine))
+        refreshed = []
+        specs = model.refresh_specs() if gathers else {}
+        for key, mine in gathers:
+            yield ("wait", key, None)
+            for n, sh in mine:
+                spec = specs.get(id(sh["p"]))
+                if spec is not None:  # derived tensors from the gathered weights (same producer as the fused refresh)
+                    K.refresh_derived(sh["p"].data, **spec[0])
+                    refreshed.append((sh["p"], spec[1]))
         opt.end_step()
+        for p_, names_ in refreshed:
+            model.adopt_refreshed(p_, names_)
         if G > 1 and self.nccl_sms > 0:
             K.gemm_set_sm_limit(0)
         if not self.rank_before_update:
@@ -166,15 +217,27 @@ class StepEngine:
         self._result = (loss, idx, sums)
 
     # -- communication actions (eager NCCL between graph segments) -----------------------------------
-    def _comm(self, action, key, tensors) -> None:
+    def _comm(self, action, key, payload) -> None:
+        G, rank = self.dist.world_size, self.dist.rank
         if action == "wait":
             for w in self._works.pop(key, []):
                 w.wait()
             for fn in self._after.pop(key, []):
                 fn()
             return
+        if action == "gather":  # all-gather of the updated row blocks, in place in the parameter's padded buffer
+            works = []
+            for n in payload:
+                pbuf = self._shards[n]["pbuf"]
+                works.append(td.all_gather_into_tensor(pbuf.view(-1), pbuf.view(G, -1)[rank], async_op=True))
+            self._works[key], self._after[key] = works, []
+            return
+        tensors, rs = payload
         group = self.dist.small_group if key in self._small_keys else None
         works, after = self.dist.all_reduce_async(tensors, group=group)
+        for n in rs:  # reduce-scatter by row blocks, in place: block `rank` of the buffer receives the sum
+            gbuf = self._shards[n]["gbuf"]
+            works.append(td.reduce_scatter_tensor(gbuf.view(G, -1)[rank], gbuf.view(-1), op=td.ReduceOp.SUM, async_op=True))
         if action == "gather_rows":
             works.append(td.all_gather_into_tensor(self._recv_idx.view(-1), self._send_idx, group=group, async_op=True))
             works.append(td.all_gather_into_tensor(self._recv_rows.view(-1), self._send_rows.view(-1), group=group, async_op=True))

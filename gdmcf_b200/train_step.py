@@ -47,10 +47,14 @@ def _time_cols(model, name, W, n_in):
     return model._ops.get(name + ".tcols", [W], build)
 
 
-def _grad_buffer(W: torch.Tensor) -> torch.Tensor:
+def _grad_buffer(W: torch.Tensor, model=None, name: str = "") -> torch.Tensor:
     """fp32 gradient buffer for a [d, n] weight whose rows start 16 B aligned, so that the wgrad contraction can use the
     TMA-store epilogue (nn.Linear(n_item + emb_size, d) weights have an odd row length). Returned as a [d, n] view;
-    autograd compacts it when it installs .grad."""
+    autograd compacts it when it installs .grad. A caller-owned buffer registered in model._grad_views[name] (the
+    data-parallel engine's persistent, row-padded reduce-scatter buffers) takes precedence."""
+    views = getattr(model, "_grad_views", None) if model is not None else None
+    if views and name in views:
+        return views[name]
     d, n = W.shape
     ld = K.round_up(n, 4)
     if ld == n:
@@ -200,7 +204,7 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
                 with_out=True, colsum=colsum, rowpart=rowpart)
     # ---- d E = Gs^T hc' - E * ri^2 * c_i   (written straight into the parameter's gradient)
     hcpT = K.cast_bf16_transpose(c.hcp_f32, with_lo=lo)  # [3d, B]
-    gE = torch.empty_like(P["embedding_item.weight"])
+    gE = _grad_buffer(P["embedding_item.weight"], model, "embedding_item.weight")
     coef_i = -(c.inv_i * c.inv_i) * colsum
     if defer_item_norm:
         # engine path: the row-wise norm term -E_i * ri^2 * c_i is applied by the optimizer pass, which reads E anyway
@@ -287,7 +291,7 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     for name, dpre, dpreT, AT, n_in, first in (("in_layers.0", dh_pre, dh_preT, A1T, I, True),
                                               ("in_layers2.0", dhU_pre, dhU_preT, A2T, 2 * I, False)):
         W = P[name + ".weight"]
-        gW = _grad_buffer(W)
+        gW = _grad_buffer(W, model, name + ".weight")
         _mm_auto(model, dpreT, AT, d, n_in, B, out_f32=gW)                                   # columns [0, n_in)
         K.sgemm_small(dpre, emb_rows, gW[:, n_in:], d, e, B, trans_a=True)                   # time-embedding columns
         grads[name + ".weight"] = gW
