@@ -58,6 +58,8 @@ class StepEngine:
         self.local_ids = torch.arange(batch_size, **i32)
         self._segments = []          # [(CUDAGraph, communication action after it or None)]
         self._works, self._after, self._result = {}, {}, None
+        self._opt_stream = torch.cuda.Stream(device=dev)   # side stream of the sharded optimizer (world_size > 1)
+        self._main_stream = None
         self._small_keys = set()     # gradient groups exchanged over dist.small_group
         self.launches_per_step = 0
         # data parallel: the user table's gradient has B non-zero rows per rank -> all-gather (ids, rows), 1.6 MB instead
@@ -169,36 +171,64 @@ class StepEngine:
             idx_ = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
             return idx_, evaluate_utils.metrics_from_device(idx_, batch.users, self.gt_rowptr, self.gt_col, self.topN)
 
-        if self.rank_before_update:
-            # denoise + rank this batch with the weights the training step just used; the optimizer update (and, with
-            # several ranks, the wait for the gradient all-reduces) comes after, so the collectives hide behind ~1.3 ms of
-            # inference work. One train step and one rank step per batch either way.
-            idx, sums = rank_and_metrics()
-        opt.begin_step()
-        # update order: groups whose exchange went over the small-message communicator first (they are complete long
-        # before the big all-reduces), then the others in the order their all-reduces were issued
         order = sorted(range(len(groups)), key=lambda gi: (0 if gi in self._small_keys else 1, gi))
         by_param = {id(sh["p"]): (n, sh) for n, sh in self._shards.items()}
-        gathers = []
-        for gi in order:
+        gathers, refreshed = [], []
+
+        def finish_group(gi, sharded_rows: bool, replicated: bool):
             plist = groups[gi]
-            if G > 1:
-                yield ("wait", gi, None)
+            if replicated:
                 if self.sparse_user_rows and any(p is params.get("embedding_user.weight") for p in plist):
                     gU = params["embedding_user.weight"].grad
                     d = gU.shape[1]
                     for r in range(G):
                         if r != self.dist.rank:
                             K.scatter_rows_add(self._recv_rows[r], self._recv_idx[r], gU, self.B, d)
-            opt.update([p for p in plist if id(p) not in by_param], grad_scale=1.0 / G, row_coef=row_coef)
-            mine = [by_param[id(p)] for p in plist if id(p) in by_param]
+                opt.update([p for p in plist if id(p) not in by_param], grad_scale=1.0 / G, row_coef=row_coef)
+            mine = [by_param[id(p)] for p in plist if id(p) in by_param] if sharded_rows else []
             for n, sh in mine:  # this rank's row block of the reduce-scattered gradient
                 r0 = self.dist.rank * sh["R"]
                 opt.update_rows(sh["p"], sh["gview"], r0, r0 + sh["R"], grad_scale=1.0 / G, row_coef=row_coef.get(id(sh["p"])))
-            if mine:
+            return mine
+
+        side_opt = bool(self._shards) and self.rank_before_update
+        if side_opt:
+            # Sharded optimizer on a side stream: as each reduce-scatter lands, this rank's row block is updated and the
+            # all-gather of the weights starts, all concurrently with the denoise + rank phase on the main stream (which
+            # reads only the bf16 operands / tables derived from the OLD weights; they are refreshed after the join).
+            opt.begin_step()
+            big = [gi for gi in order if any(id(p) in by_param for p in groups[gi])]
+            yield ("to_opt", None, None)
+            for gi in big:
+                yield ("wait", gi, None)
+                mine = finish_group(gi, True, False)
                 yield ("gather", ("ag", gi), [n for n, _ in mine])
                 gathers.append((("ag", gi), mine))
-        refreshed = []
+            yield ("to_main", None, None)
+            idx, sums = rank_and_metrics()
+            for gi in order:
+                if gi not in big:
+                    yield ("wait", gi, None)
+                    finish_group(gi, False, True)
+            yield ("join_opt", None, None)
+            for gi in big:  # the small tensors that travelled with a big group (biases, time-embedding layer)
+                finish_group(gi, False, True)
+        else:
+            if self.rank_before_update:
+                # denoise + rank this batch with the weights the training step just used; the optimizer update (and, with
+                # several ranks, the wait for the gradient all-reduces) comes after, so the collectives hide behind ~1.3 ms
+                # of inference work. One train step and one rank step per batch either way.
+                idx, sums = rank_and_metrics()
+            opt.begin_step()
+            # update order: groups whose exchange went over the small-message communicator first (they are complete long
+            # before the big all-reduces), then the others in the order their all-reduces were issued
+            for gi in order:
+                if G > 1:
+                    yield ("wait", gi, None)
+                mine = finish_group(gi, True, True)
+                if mine:
+                    yield ("gather", ("ag", gi), [n for n, _ in mine])
+                    gathers.append((("ag", gi), mine))
         specs = model.refresh_specs() if gathers else {}
         for key, mine in gathers:
             yield ("wait", key, None)
@@ -219,6 +249,16 @@ class StepEngine:
     # -- communication actions (eager NCCL between graph segments) -----------------------------------
     def _comm(self, action, key, payload) -> None:
         G, rank = self.dist.world_size, self.dist.rank
+        if action == "to_opt":  # fork: the optimizer stream continues from here, the main stream stays free
+            self._opt_stream.wait_stream(self._main_stream)
+            torch.cuda.set_stream(self._opt_stream)
+            return
+        if action == "to_main":
+            torch.cuda.set_stream(self._main_stream)
+            return
+        if action == "join_opt":
+            self._main_stream.wait_stream(self._opt_stream)
+            return
         if action == "wait":
             for w in self._works.pop(key, []):
                 w.wait()
@@ -244,8 +284,12 @@ class StepEngine:
         self._works[key], self._after[key] = works, after
 
     def _eager_step(self):
-        for action, key, tensors in self._program():
-            self._comm(action, key, tensors)
+        self._main_stream = torch.cuda.current_stream(self.dev)
+        try:
+            for action, key, tensors in self._program():
+                self._comm(action, key, tensors)
+        finally:
+            torch.cuda.set_stream(self._main_stream)
         return self._result
 
     def capture(self, warmup: int = 3) -> None:
@@ -274,18 +318,23 @@ class StepEngine:
             ctx.__enter__()
             return g, ctx
 
+        on_opt = False  # which stream the segment being captured will be replayed on
         g, ctx = begin()
         try:
             for action in self._program():
                 ctx.__exit__(None, None, None)
                 pool = pool or g.pool()
-                self._segments.append((g, action))
+                self._segments.append((g, on_opt, action))
+                if action[0] == "to_opt":
+                    on_opt = True
+                elif action[0] == "to_main":
+                    on_opt = False
                 g, ctx = begin()
         except BaseException:
             ctx.__exit__(None, None, None)
             raise
         ctx.__exit__(None, None, None)
-        self._segments.append((g, None))
+        self._segments.append((g, on_opt, None))
         self.launches_per_step = int(lib.gdmcf_launch_count() - n0)
         self.model.weights_updated()  # capture executed nothing: cached operands follow the replays from here on
         torch.cuda.synchronize(self.dev)
@@ -295,9 +344,14 @@ class StepEngine:
         [len(topN), 4]) — device tensors that the next step overwrites."""
         if not self._segments:
             return self._eager_step()
-        for g, action in self._segments:
-            g.replay()
-            if action is not None:
-                self._comm(*action)
+        self._main_stream = torch.cuda.current_stream(self.dev)
+        try:
+            for g, on_opt, action in self._segments:
+                # the stream is set by the fork / join actions themselves; a segment replays on the stream it follows
+                g.replay()
+                if action is not None:
+                    self._comm(*action)
+        finally:
+            torch.cuda.set_stream(self._main_stream)
         self.model.weights_updated()  # keeps the eager API coherent: its cached operands are stale after a replay
         return self._result
