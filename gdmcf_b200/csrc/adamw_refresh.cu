@@ -45,7 +45,8 @@ GD_DEV uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-template <int VEC>
+// UPDATE = false: refresh only (derive the tensors from the current weights; g, m, v are not touched).
+template <int VEC, bool UPDATE>
 __global__ void __launch_bounds__(THREADS)
 adamw_refresh_kernel(const Args a) {
   __shared__ float tile[TR][TC + 1];
@@ -75,7 +76,7 @@ adamw_refresh_kernel(const Args a) {
         const long long off = (long long)r * a.cols + c;
         const long long goff = (long long)r * a.ld_g + c;
         float gv[4], mv[4], vv[4];
-        if (!a.g) {  // refresh only: derive the tensors from the current weights, no update
+        if (!UPDATE) {
           if (VEC == 4) {
             const float4 P = *reinterpret_cast<const float4*>(a.p + off);
             pv[0] = P.x; pv[1] = P.y; pv[2] = P.z; pv[3] = P.w;
@@ -320,14 +321,17 @@ extern "C" int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float
   const long long ctas = (long long)row_groups * a.col_splits;
   if (ctas > 0x7fffffffLL) { set_error("adamw_refresh: too many tiles"); return GDMCF_EBADARG; }
   const bool flat_ok = g && !vec && !a.t_hi && !a.delta && !a.rowpart && ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
-  if (vec) {
-    adamw_refresh_kernel<4><<<(int)ctas, THREADS, 0, st>>>(a);
+  if (!g) {
+    if (vec) adamw_refresh_kernel<4, false><<<(int)ctas, THREADS, 0, st>>>(a);
+    else adamw_refresh_kernel<1, false><<<(int)ctas, THREADS, 0, st>>>(a);
+  } else if (vec) {
+    adamw_refresh_kernel<4, true><<<(int)ctas, THREADS, 0, st>>>(a);
   } else if (flat_ok) {
     const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
     const long long groups = ((long long)rows * cols + 3) / 4;
     adamw_flat_hi_kernel<<<(int)std::min<long long>((groups + THREADS - 1) / THREADS, (long long)sms * 8), THREADS, 0, st>>>(a);
   } else {
-    adamw_refresh_kernel<1><<<(int)ctas, THREADS, 0, st>>>(a);
+    adamw_refresh_kernel<1, true><<<(int)ctas, THREADS, 0, st>>>(a);
   }
   if ((rc = cuda_check_launch("adamw_refresh_kernel"))) return rc;
   if (a.rowpart) {

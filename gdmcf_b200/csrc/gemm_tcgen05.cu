@@ -825,8 +825,14 @@ extern "C" int gdmcf_gemm_auto_splits(int m, int n, int k_total) {
   const int sms = sm_budget();
   if (tiles >= sms) return 1;
   int splits = sms / tiles;
-  // keep at least 4 k-blocks per split so the pipeline prologue stays amortised
-  splits = std::min(splits, std::max(1, total_kb / 4));
+  // keep at least GDMCF_GEMM_MIN_KB (default 8) k-blocks per split: a split costs a partial-slab epilogue (the slow
+  // transposed form) plus a share of the reduce kernel, which only pays off against a long enough main loop
+  static int min_kb = 0;
+  if (min_kb == 0) {
+    const char* e = getenv("GDMCF_GEMM_MIN_KB");
+    min_kb = (e && atoi(e) > 0) ? atoi(e) : 8;
+  }
+  splits = std::min(splits, std::max(1, total_kb / min_kb));
   splits = std::max(splits, 1);
   const int per = (total_kb + splits - 1) / splits;
   return (total_kb + per - 1) / per;

@@ -186,23 +186,56 @@ skinny_nn_kernel(const float* __restrict__ A, long long lda, const float* __rest
   }
 }
 // TN form (A stored [K,M]): 32 output rows x 8 K-slices per CTA (coalesced over m), smem reduce in fixed order.
+// The skinny operand B [K, N] (16 KB for the time-embedding products) is staged in shared memory once per CTA when it
+// fits, so the K loop issues only the independent A loads (4 in flight per thread) instead of N dependent global loads.
 template <int NMAX>
 __global__ void __launch_bounds__(256)
 skinny_tn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, int tb,
-                 float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, float beta) {
+                 float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, float beta, int stage_b) {
   __shared__ float red[8][NMAX][33];
+  extern __shared__ float sB[];  // [K][N] when stage_b
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (stage_b) {
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+      const int k = i / N, j = i - k * N;
+      sB[i] = tb ? B[(long long)j * ldb + k] : B[(long long)k * ldb + j];
+    }
+    __syncthreads();
+  }
   for (int m0 = blockIdx.x * 32; m0 < M; m0 += gridDim.x * 32) {
     const int m = m0 + tx;
     float acc[NMAX];
 #pragma unroll
     for (int j = 0; j < NMAX; ++j) acc[j] = 0.f;
     if (m < M) {
-      for (int k = ty; k < K; k += 8) {
-        const float a = A[(long long)k * lda + m];
+      if (stage_b) {
+        int k = ty;
+        for (; k + 24 < K; k += 32) {  // 4 K-slices of this thread per trip: independent A loads
+          float a[4];
 #pragma unroll
-        for (int j = 0; j < NMAX; ++j)
-          if (j < N) acc[j] = fmaf(a, tb ? B[(long long)j * ldb + k] : B[(long long)k * ldb + j], acc[j]);
+          for (int u = 0; u < 4; ++u) a[u] = A[(long long)(k + 8 * u) * lda + m];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* b = sB + (k + 8 * u) * N;  // same address for the whole warp: broadcast
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j)
+              if (j < N) acc[j] = fmaf(a[u], b[j], acc[j]);
+          }
+        }
+        for (; k < K; k += 8) {
+          const float a = A[(long long)k * lda + m];
+          const float* b = sB + k * N;
+#pragma unroll
+          for (int j = 0; j < NMAX; ++j)
+            if (j < N) acc[j] = fmaf(a, b[j], acc[j]);
+        }
+      } else {
+        for (int k = ty; k < K; k += 8) {
+          const float a = A[(long long)k * lda + m];
+#pragma unroll
+          for (int j = 0; j < NMAX; ++j)
+            if (j < N) acc[j] = fmaf(a, tb ? B[(long long)j * ldb + k] : B[(long long)k * ldb + j], acc[j]);
+        }
       }
     }
 #pragma unroll
@@ -279,7 +312,10 @@ extern "C" int gdmcf_sgemm_small(const float* A, int64_t lda, int trans_a, const
   GD_PRE();
   if (n <= 16) {  // time-embedding columns: a 32x32 tile would be mostly padding and the K loop would be serial
     if (trans_a) {
-      skinny_tn_kernel<16><<<grid_1d((m + 31) / 32, 1), 256, 0, st>>>(A, lda, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
+      const size_t sb_bytes = (size_t)k * n * sizeof(float);
+      const int stage_b = sb_bytes <= 28 * 1024 ? 1 : 0;  // + 16.9 KB static: stays under the 48 KB default limit
+      skinny_tn_kernel<16><<<grid_1d((m + 31) / 32, 1), 256, stage_b ? sb_bytes : 0, st>>>(A, lda, B, ldb, trans_b, C, ldc, m, n, k,
+                                                                                        alpha, beta, stage_b);
       return cuda_check_launch("skinny_tn_kernel");
     }
     skinny_nn_kernel<16><<<grid_1d((long long)m * 32), 256, 0, st>>>(A, lda, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);

@@ -66,7 +66,7 @@ GD_DEV void bitonic_desc(uint32_t* key, uint32_t* idx, int n, int tid) {
 // maxima is a lower bound L of the k-th largest key of the row (k distinct elements are >= L), so the exact top-k is
 // among the elements >= L — a few dozen for real score rows. Two coalesced passes over the row, no histogram atomics.
 // Rows where more than CAND_CAP elements reach L (massive ties) fall back to the exact 4-pass radix select.
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 3)  // 3 CTAs per SM: 444 rows resident, a 400-user batch is a single wave
 mask_topk_kernel(const float* __restrict__ scores, long long ld, int n_rows, int n_items, const int* __restrict__ users,
                  const int* __restrict__ h_rowptr, const int* __restrict__ h_col, const int* __restrict__ h_rowptr2,
                  const int* __restrict__ h_col2, int k, int kpad, int stage_keys, int* __restrict__ out_idx,

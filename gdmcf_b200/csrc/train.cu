@@ -268,49 +268,46 @@ __global__ void scatter_rows_add_kernel(const float* __restrict__ v, long long l
 }
 
 // Lt_history / Lt_count update of training_losses (models/gaussian_diffusion.py:935-949) with the reference's
-// sequential semantics: thread t replays the batch in order and touches only its own row of the history.
-__global__ void lt_history_kernel(const long long* __restrict__ ts, const double* __restrict__ loss, double* __restrict__ hist,
-                                  long long* __restrict__ count, int B, int T, int H) {
-  // the batch is staged through shared memory in slabs (a serial walk over global memory costs ~0.6 us per row)
-  constexpr int SLAB = 1024;
-  __shared__ int s_ts[SLAB];
-  __shared__ double s_loss[SLAB];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  double* grow = hist + (long long)min(t, T - 1) * H;
-  double lrow[32];  // the row is edited in thread-local storage (H <= 32, checked on the host) and written back once
-  if (t < T)
-    for (int j = 0; j < H; ++j) lrow[j] = grow[j];
-  double* row = lrow;
-  int start = 0;
-  long long cnt = t < T ? count[t] : 0;
-  for (int b0 = 0; b0 < B; b0 += SLAB) {
-    const int nb = min(SLAB, B - b0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-      s_ts[i] = (int)ts[b0 + i];
-      s_loss[i] = loss[b0 + i];
-    }
-    __syncthreads();
-    if (t < T) {
-      for (int b = 0; b < nb; ++b) {
-        if (s_ts[b] != t) continue;
-        if (cnt == H) {  // shift-left-and-append == overwrite the oldest slot of a ring
-          row[start] = s_loss[b];
-          start = (start + 1 == H) ? 0 : start + 1;
-        } else {
-          row[cnt] = s_loss[b];  // start is still 0 while the row is filling up
-          ++cnt;
-        }
-      }
-    }
+// sequential semantics: per timestep the new history is the last H entries of (old entries ++ this batch's losses for t,
+// in batch order) — what the shift-left-and-append loop leaves behind. One warp per timestep: two ballot passes over the
+// batch (count the matches, then place match number q at slot cnt_old + q - shift), no serial walk.
+__global__ void __launch_bounds__(128)
+lt_history_kernel(const long long* __restrict__ ts, const double* __restrict__ loss, double* __restrict__ hist,
+                  long long* __restrict__ count, int B, int T, int H) {
+  __shared__ double rows[4][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int t = blockIdx.x * 4 + w;
+  if (t >= T) return;  // whole warps leave together; no block-wide barrier below
+  double* row = rows[w];
+  const int cnt_old = (int)count[t];
+  int n = 0;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int b = b0 + lane;
+    const bool match = b < B && ts[b] == (long long)t;
+    n += __popc(__ballot_sync(0xffffffffu, match));
   }
-  if (t < T) {
-    count[t] = cnt;
-    for (int j = 0; j < H; ++j) {
-      const int src = start + j;
-      grow[j] = lrow[src >= H ? src - H : src];
-    }
+  const int total = cnt_old + n;
+  const int shift = max(0, total - H);
+  if (lane < H) {
+    const int src = lane + shift;  // surviving old entries move down by `shift`; untouched slots keep their value
+    row[lane] = (src < cnt_old) ? hist[(long long)t * H + src] : hist[(long long)t * H + lane];
   }
+  __syncwarp();
+  int seen = 0;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int b = b0 + lane;
+    const bool match = b < B && ts[b] == (long long)t;
+    const unsigned m = __ballot_sync(0xffffffffu, match);
+    if (match) {
+      const int q = seen + __popc(m & ((1u << lane) - 1u));
+      const int pos = cnt_old + q - shift;
+      if (pos >= 0) row[pos] = loss[b];  // pos < H by construction; entries pushed out by later ones are dropped
+    }
+    seen += __popc(m);
+  }
+  __syncwarp();
+  if (lane < H) hist[(long long)t * H + lane] = row[lane];
+  if (lane == 0) count[t] = (long long)min(total, H);
 }
 
 // sample_timesteps(method="importance") of models/gaussian_diffusion.py:959-986 without leaving the device: while any
@@ -386,7 +383,7 @@ extern "C" int gdmcf_lt_history_update(const int64_t* ts, const double* loss, do
   }
   int rc = gdmcf_device_check();
   if (rc) return rc;
-  lt_history_kernel<<<(steps + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  lt_history_kernel<<<(steps + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(ts), loss, lt_history, reinterpret_cast<long long*>(lt_count), batch, steps, history);
   return cuda_check_launch("lt_history_kernel");
 }

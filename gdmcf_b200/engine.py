@@ -294,12 +294,13 @@ class StepEngine:
 
     def capture(self, warmup: int = 3) -> None:
         """Eager warm-up on whatever the static inputs hold (call load_* first), then capture. The warm-up allocates the
-        persistent operand buffers and optimizer state outside the graph pool and fills Lt_history."""
+        persistent operand buffers and optimizer state outside the graph pool and fills Lt_history; the first capture
+        needs at least one warm-up step (a re-capture of a warmed engine may pass 0)."""
         lib = _lib.load()
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):
+            for _ in range(warmup):
                 self._eager_step()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)

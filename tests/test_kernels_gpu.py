@@ -481,3 +481,24 @@ def test_mse_rows_ragged(K):
         got = K.mse_rows(a[:, :cols] if ld == cols else a, b[:, :cols] if ld == cols else b, rows, cols)
         ref = ((a[:, :cols].double() - b[:, :cols].double()) ** 2).mean(1)
         torch.testing.assert_close(got.double(), ref, rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("T,B,H", [(5, 400, 10), (100, 400, 10), (7, 33, 4), (3, 1000, 32)])
+def test_lt_history_kernel_matches_reference_loop(K, T, B, H):
+    """gdmcf_lt_history_update against the literal per-sample loop of gaussian_diffusion.py:935-949, several batches."""
+    g = torch.Generator().manual_seed(T * 1000 + B)
+    hist = torch.zeros(T, H, dtype=torch.float64)
+    count = torch.zeros(T, dtype=torch.int64)
+    hist_d, count_d = hist.cuda(), count.cuda()
+    for _ in range(4):
+        ts = torch.randint(0, T, (B,), generator=g)
+        loss = torch.rand(B, generator=g, dtype=torch.float64)
+        for t, l in zip(ts.tolist(), loss.tolist()):  # reference semantics
+            if count[t] == H:
+                hist[t, :-1] = hist[t, 1:].clone()
+                hist[t, -1] = l
+            else:
+                hist[t, count[t]] = l
+                count[t] += 1
+        K.lt_history_update(ts.cuda(), loss.cuda(), hist_d, count_d)
+        assert torch.equal(hist_d.cpu(), hist) and torch.equal(count_d.cpu(), count)
