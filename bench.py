@@ -198,7 +198,7 @@ def run_engine(args):
     import numpy as np
     import scipy.sparse as sp
     import torch
-    from gdmcf_b200 import _lib, data_utils, dist_utils, evaluate_utils
+    from gdmcf_b200 import _lib, data_utils, dist_utils
     from gdmcf_b200 import kernels as K
     from gdmcf_b200.lightGCN import LightGCN
     from gdmcf_b200.models import gaussian_diffusion as gd

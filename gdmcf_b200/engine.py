@@ -3,26 +3,25 @@
 The reference's loop body (main.py:331-351 train step, main.py:288-307 evaluate step) is ~150 kernel launches here;
 issued one by one from Python the step is bound by host enqueue time, not by the GPU. The engine captures
 
-    training_losses -> loss.mean().backward() -> [gradient all-reduce] -> FusedAdamW.step
-                    -> p_sample (reverse loop) -> history mask -> top-k -> Recall/NDCG sums
+    training_losses + backward -> p_sample (reverse loop) -> history mask -> top-k -> Recall/NDCG sums
+                               -> FusedAdamW update (+ refresh of the bf16 operands / tables derived from the weights)
 
 once, around *static* device inputs (the batch's CSR rows, ground-truth rows and user ids), and replays it per batch.
 Everything that changes from step to step lives on the device: the Philox epoch and AdamW step counters are advanced
 by kernels inside the graph, timesteps are drawn by gdmcf_sample_timesteps, bf16 weight operands are refreshed in place.
-With world_size > 1 the step is a chain of graph segments with NCCL between them: the backward pass hands over
-gradient groups as they become final (item table first), their all-reduces run asynchronously on NCCL's stream while the
-next segment computes, and AdamW updates each group as soon as its reduction has landed.
+With world_size > 1 the step is a chain of graph segments with eager NCCL between them: the backward pass hands over
+gradient groups as they become final (item table first); the big matrices are reduce-scattered by row blocks, a side
+stream runs AdamW on the rank's block and all-gathers the weights while the main stream denoises and ranks, and the
+derived tensors are recomputed from the gathered weights.
 
 The training half is `train_step.fused_train_stages` — the kernels and arithmetic of `diffusion.training_losses(...)
 ["loss"].mean().backward()` without the autograd bookkeeping; `optimizer.update`, `diffusion.rank` and
 `metrics_from_device` are the public calls. `graphs=False` runs the same program without capture (parity tests)."""
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Sequence
 
-import numpy as np
 import torch
-
 import torch.distributed as td
 
 from . import _lib, evaluate_utils
