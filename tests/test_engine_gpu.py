@@ -188,3 +188,40 @@ def test_adamw_row_coef_kernel():
     torch.testing.assert_close(m, m2, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(p, p2, rtol=0, atol=1e-5)
     assert torch.equal(op.hi, K.cast_bf16(p).hi)
+
+
+def test_engine_dnn_backbone_graph_equals_eager():
+    """The DiffRec-style DNN backbone (models/DNN.py:11-88) through the same engine: graph replays == eager program."""
+    from gdmcf_b200 import data_utils, dist_utils
+    from gdmcf_b200.engine import StepEngine
+    from gdmcf_b200.models import gaussian_diffusion as gd
+    from gdmcf_b200.models.DNN import DNN
+    from gdmcf_b200.optim import FusedAdamW
+    dev = torch.device("cuda")
+    tr, va, te = data_utils.synthetic_interactions(500, 1203, 15000, 7)
+    n_user, n_item = int(tr[:, 0].max()) + 1, int(tr[:, 1].max()) + 1
+    mk = lambda p: sp.csr_matrix((np.ones(len(p), dtype=np.float32), (p[:, 0], p[:, 1])), shape=(n_user, n_item))  # noqa: E731
+    train_sp, test_sp = mk(tr), mk(te)
+    train_dev, test_dev = data_utils.DeviceInteractions(train_sp, dev), data_utils.DeviceInteractions(test_sp, dev)
+    B, k = 64, 20
+    engines = []
+    for graphs in (True, False):
+        torch.manual_seed(4)
+        model = DNN([n_item, 64], [64, n_item], 10).to(dev)
+        diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, 5, dev, discrete=0.9995)
+        diff.seed = model.seed = 5
+        opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0, modules=[model], capturable=True)
+        eng = StepEngine(model, diff, opt, dist_utils.Dist(), batch_size=B, n_item=n_item, topk=k, topN=[10, k],
+                         cap_train_nnz=int(train_sp.nnz), cap_gt_nnz=int(test_sp.nnz), graphs=graphs)
+        eng.load_resident(train_dev, test_dev, 0, B)
+        eng.capture(warmup=2)
+        engines.append((model, eng))
+    for s in range(1, 4):
+        outs = []
+        for _, e in engines:
+            e.load_resident(train_dev, test_dev, s * B, (s + 1) * B)
+            outs.append(tuple(t.clone() for t in e.step()))
+        assert all(torch.equal(a, b) for a, b in zip(*outs))
+        assert torch.isfinite(outs[0][0])
+    for (n, pa), (_, pb) in zip(engines[0][0].named_parameters(), engines[1][0].named_parameters()):
+        assert torch.equal(pa, pb), n
