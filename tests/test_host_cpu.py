@@ -136,3 +136,41 @@ def test_bench_reference_arm_runs():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "users/s"
+
+
+def test_operand_cache_refreshes_in_place_and_adopts():
+    """_OperandCache (models/DNN.py): stale values are handed back to the builder (in-place refresh keeps addresses stable
+    for captured CUDA graphs); mark_fresh adopts a value refreshed by someone else (FusedAdamW's fused refresh)."""
+    import torch
+    from gdmcf_b200.models.DNN import _OperandCache
+    cache = _OperandCache()
+    p = torch.nn.Parameter(torch.zeros(3))
+    built = []
+
+    def build(prev):
+        built.append(prev)
+        out = prev if prev is not None else torch.empty(3)
+        out.copy_(p.detach() * 2)
+        return out
+
+    a = cache.get("x", [p], build)
+    assert built == [None] and cache.get("x", [p], build) is a and len(built) == 1  # hit
+    with torch.no_grad():
+        p.add_(1.0)                      # torch bumps the version counter
+    b = cache.get("x", [p], build)
+    assert b is a and built[-1] is a and torch.equal(a, torch.full((3,), 2.0))       # rebuilt in place
+    cache.epoch += 1                     # raw-pointer update (FusedAdamW): stale ...
+    assert cache.peek("x") is a
+    cache.mark_fresh("x", [p])           # ... unless the optimizer refreshed it itself
+    assert cache.get("x", [p], build) is a and len(built) == 2
+    cache.epoch += 1
+    cache.get("x", [p], build)
+    assert len(built) == 3
+
+
+def test_cli_engine_flags():
+    from gdmcf_b200.parse_args_util import parse_args
+    a = parse_args(["--dims=[64]", "--checkpoint_every", "2", "--resume", "ck.pt", "--synthetic", "600,500,15000"])
+    assert a.dims == [64] and a.checkpoint_every == 2 and a.resume == "ck.pt" and a.synthetic == "600,500,15000"
+    b = parse_args([])
+    assert b.checkpoint_every == 0 and b.resume == "" and b.dims == [1000]
