@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_graphs", action="store_true", help="launch the step kernel by kernel instead of replaying CUDA graphs")
+    ap.add_argument("--mode", default="train+rank", choices=["train+rank", "rank"],
+                    help="rank: denoise + mask + top-k + metrics only (BASELINE.json configs[2]); the default is the headline metric")
     ap.add_argument("--rank_after_update", action="store_true",
                     help="step order train -> AdamW -> rank (default: train -> rank -> AdamW, which hides the all-reduces)")
     ap.add_argument("--nccl_sms", type=int, default=32, help="SMs the contractions leave to NCCL while all-reduces are in flight (N > 1)")
@@ -62,7 +64,7 @@ def parse():
 
 def config_of(args, n_gpus):
     U, I, P, _ = WORKLOADS[args.workload]
-    return {"workload": f"{args.workload}-shape synthetic GDMCF train+denoise+rank", "n_user": U, "n_item": I,
+    return {"workload": f"{args.workload}-shape synthetic GDMCF " + ("train+denoise+rank" if args.mode == "train+rank" else "denoise+rank (inference only)"), "n_user": U, "n_item": I,
             "interactions": P, "backbone": "DNNOneHotEmbeddingGCN", "dims": [args.dims], "steps": args.diff_steps,
             "noise_scale": 0.01, "batch_size": args.batch, "top_k": args.topk, "users_per_step": args.batch * n_gpus,
             "parallelism": f"dp{n_gpus} (user batches; grad all-reduce)", "l2": "inputs larger than L2 (weights+state ~4 GB)",
@@ -252,7 +254,7 @@ def run_engine(args):
     eng = StepEngine(model, diffusion, opt, dist, batch_size=B, n_item=n_item, topk=k, topN=topN,
                      cap_train_nnz=window_nnz(train_sp), cap_gt_nnz=window_nnz(test_sp), reweight=True,
                      graphs=not args.no_graphs, rank_before_update=not args.rank_after_update, nccl_sms=args.nccl_sms,
-                     shard_optimizer=not args.replicated_optimizer)
+                     shard_optimizer=not args.replicated_optimizer, train=args.mode == "train+rank")
     eng.load_resident(train_dev, test_dev, *users_of(0))
     eng.capture(warmup=3)
 
@@ -440,7 +442,7 @@ def run_engine(args):
                 print(f"{e.device_time_total / 3e3:9.3f} ms/step  x{e.count / 3:6.1f}  {e.key[:100]}", file=sys.stderr)
 
     cpu = None
-    if rank == 0 and G == 1 and not args.no_cpu_baseline:
+    if rank == 0 and G == 1 and not args.no_cpu_baseline and args.mode == "train+rank":
         sd = {kk: v.detach().cpu() for kk, v in model.state_dict().items()}
         arm = CpuArm(args, sd)
         reps = max(1, args.cpu_sample_users // B)

@@ -34,10 +34,11 @@ class StepEngine:
     def __init__(self, model, diffusion, optimizer, dist, *, batch_size: int, n_item: int, topk: int, topN: Sequence[int],
                  cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
                  rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
-                 shard_min_bytes: int = 64 << 20):
+                 shard_min_bytes: int = 64 << 20, train: bool = True):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
+        self.train = train  # False: denoise + rank only (BASELINE.json configs[2]); no gradients, no collectives
         # the item table's norm-term gradient (-E_i * ri^2 * c_i) is applied inside the AdamW pass instead of the wgrad
         # contraction's epilogue (saves a 412 MB read of E per step at the Yelp shape)
         self.defer_item_norm = hasattr(model, "embedding_item")
@@ -68,7 +69,7 @@ class StepEngine:
         # only (1/G of the optimizer pass) and the updated blocks are all-gathered; the derived tensors are then refreshed
         # from the gathered weights. Same communication volume as an all-reduce, 1/G of the optimizer's HBM traffic.
         self._shards = {}
-        if G > 1 and shard_optimizer:
+        if G > 1 and shard_optimizer and train:
             self._setup_shards(shard_min_bytes)
         self.sparse_user_rows = G > 1 and hasattr(model, "embedding_user")
         if self.sparse_user_rows:
@@ -126,6 +127,13 @@ class StepEngine:
         all-reduce of a finished gradient group, ("wait", key) makes the stream wait for it. With one rank there are no
         yields and the whole step is a single graph."""
         model, diff, opt, G = self.model, self.diffusion, self.opt, self.dist.world_size
+        if not self.train:
+            model.eval()
+            batch = self._batch()
+            idx = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
+            sums = evaluate_utils.metrics_from_device(idx, batch.users, self.gt_rowptr, self.gt_col, self.topN)
+            self._result = (torch.zeros((), dtype=torch.float64, device=self.dev), idx, sums)
+            return
         model.train()
         opt.zero_grad(set_to_none=True)
         params = dict(model.named_parameters())
@@ -305,8 +313,9 @@ class StepEngine:
         torch.cuda.synchronize(self.dev)
         if not self.use_graphs:
             return
-        assert getattr(self.opt, "_capturable", False), "graph capture needs FusedAdamW(..., capturable=True)"
-        self.opt.zero_grad(set_to_none=True)
+        if self.train:
+            assert getattr(self.opt, "_capturable", False), "graph capture needs FusedAdamW(..., capturable=True)"
+            self.opt.zero_grad(set_to_none=True)
         n0 = lib.gdmcf_launch_count()
         self._segments = []
         pool = None
