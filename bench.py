@@ -399,13 +399,13 @@ def run_engine(args):
         _, col, val = lg.norm_adj_csr
         E0 = lg.E0.weight.detach()
         out = torch.empty_like(E0)
-        work = (torch.empty_like(E0), torch.empty_like(E0), torch.empty(max(lg.plan.n_slots, 1), 64, device=dev))
+        work = K.lightgcn_sym_work(lg.plan, E0)  # separable-normalisation form: pattern + D^-1/2, no value stream
         ts = []
         for it in range(13):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            K.lightgcn_propagate(lg.plan, col, val, E0, 3, out=out, work=work)
+            K.lightgcn_propagate(lg.plan, col, val, E0, 3, out=out, work=work, dinv=lg.dinv)
             e1.record()
             torch.cuda.synchronize()
             if it >= 3:
@@ -415,7 +415,7 @@ def run_engine(args):
         t_med = sorted(ts)[len(ts) // 2]
         gbs = bytes_alg / (t_med * 1e-3) / 1e9
         gather_bytes = 3 * nnz * 64 * 4  # rows the kernel must pull from L2 (the tables are L2 resident): nnz x d x 4 per layer
-        spmm = {"bound": "hbm", "kernel": "spmm_items_kernel + spmm_long_reduce_kernel x3 (lightgcn_propagate, K=3, d=64, fp32)",
+        spmm = {"bound": "hbm", "kernel": "spmm_items_kernel<binary> + spmm_long_reduce_kernel x3 (lightgcn_propagate_sym, K=3, d=64, fp32)",
                 "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "ms": t_med,
                 "algorithmic_bytes": bytes_alg, "N": N, "nnz": nnz, "l2": "flushed between iterations (256 MiB write)",
                 "l2_gather": {"bytes": gather_bytes, "achieved_tbs": gather_bytes / (t_med * 1e-3) / 1e12,

@@ -85,6 +85,8 @@ SIGNATURES = {
     "gdmcf_spmm_csr_f32": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _F, _F, _P]),
     "gdmcf_lightgcn_propagate_f32": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "gdmcf_build_norm_adj": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "gdmcf_lightgcn_propagate_sym_f32": (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "gdmcf_norm_adj_dinv": (_I, [_P, _P, _I, _I, _P, _P]),
     "gdmcf_gemm_auto_splits": (_I, [_I, _I, _I]),
     "gdmcf_gemm_set_sm_limit": (_I, [_I]),
     "gdmcf_gemm_workspace_bytes": (_SZ, [_I, _I, _I]),

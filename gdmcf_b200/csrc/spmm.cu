@@ -48,15 +48,24 @@ GD_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];"
 
 // The 32 lanes take the (col,val) pairs [base, base+n) of an item. Lanes past n hold a duplicate of the last column
 // with value 0, so the gather loop below needs no predicates (the duplicate row is an L1 hit).
-GD_DEV void load_pairs(const int* __restrict__ col, const float* __restrict__ val, int base, int n, int lane, int& c, float& v) {
+template <bool kWeighted>
+GD_DEV void load_pairs(const int* __restrict__ col, const float* __restrict__ val, int base, int n, int lane, int pad_col, int& c,
+                       float& v) {
   c = 0;
   v = 0.f;
-  if (n > 0) c = ld_stream_i32(col + base + min(lane, n - 1));
-  if (lane < n) v = ld_stream_f32(val + base + lane);
+  if (kWeighted) {
+    if (n > 0) c = ld_stream_i32(col + base + min(lane, n - 1));
+    if (lane < n) v = ld_stream_f32(val + base + lane);
+  } else {
+    // binary adjacency: no values; lanes past n point at the all-zero row `pad_col` of X, so the sums need no predicate
+    c = pad_col;
+    if (lane < n) c = ld_stream_i32(col + base + lane);
+  }
 }
 
 // acc += sum_j v_j * X[c_j, coff..coff+3]: the two half-warps take alternate non-zeros; each lane gathers a float4
 // (16 lanes x 16 B = one 256 B embedding row), 4 independent gathers per lane per trip; 8 instructions per 2 nnz.
+template <bool kWeighted>
 GD_DEV void gather_pairs(const float* __restrict__ Xs, long long ldx, int cc, float vv, int n, int half, float4& acc) {
   const int ng = (n + 7) & ~7;
 #pragma unroll 1
@@ -67,15 +76,26 @@ GD_DEV void gather_pairs(const float* __restrict__ Xs, long long ldx, int cc, fl
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + 2 * u + half;  // <= 31
       const int c = __shfl_sync(0xffffffffu, cc, j);
-      v[u] = __shfl_sync(0xffffffffu, vv, j);
-      x[u] = __ldg(reinterpret_cast<const float4*>(Xs + (long long)c * ldx));
+      if (kWeighted) {
+        v[u] = __shfl_sync(0xffffffffu, vv, j);
+        x[u] = __ldg(reinterpret_cast<const float4*>(Xs + (long long)c * ldx));
+      } else {
+        x[u] = __ldg(reinterpret_cast<const float4*>(Xs + (long long)c * ldx));  // padding lanes read the zero row
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      acc.x = fmaf(v[u], x[u].x, acc.x);
-      acc.y = fmaf(v[u], x[u].y, acc.y);
-      acc.z = fmaf(v[u], x[u].z, acc.z);
-      acc.w = fmaf(v[u], x[u].w, acc.w);
+      if (kWeighted) {
+        acc.x = fmaf(v[u], x[u].x, acc.x);
+        acc.y = fmaf(v[u], x[u].y, acc.y);
+        acc.z = fmaf(v[u], x[u].z, acc.z);
+        acc.w = fmaf(v[u], x[u].w, acc.w);
+      } else {
+        acc.x += x[u].x;
+        acc.y += x[u].y;
+        acc.z += x[u].z;
+        acc.w += x[u].w;
+      }
     }
   }
 }
@@ -83,10 +103,14 @@ GD_DEV void gather_pairs(const float* __restrict__ Xs, long long ldx, int cc, fl
 // One warp per work item, items dealt round-robin to the resident warps. The item descriptor two items ahead (L1 prefetch) and the
 // first 32 (col,val) pairs one item ahead are requested before the current item's gathers, so the dependent chain
 // descriptor -> pairs -> rows costs one L2 round trip per item instead of three.
+// kWeighted = false: binary adjacency (val unused); the per-row factor row_scale[r]^row_pow multiplies alpha in the epilogue
+// (the separable normalisation D^-1/2 A D^-1/2 of LightGCN, see gdmcf_lightgcn_propagate_sym_f32).
+template <bool kWeighted>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, const int4* __restrict__ items,
                   int n_items, const float* __restrict__ X, const float* __restrict__ Z, float* __restrict__ Y,
-                  float* __restrict__ scratch, int d, float alpha, float beta) {
+                  float* __restrict__ scratch, int d, float alpha, float beta, const float* __restrict__ row_scale,
+                  int row_pow, int pad_col) {
   const int lane = threadIdx.x & 31;
   const int half = lane >> 4, hl = lane & 15;
   const int slabs = d >> 6;
@@ -97,14 +121,14 @@ spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, co
   if (item + nwarps < n_items) prefetch_l1(&items[item + nwarps]);
   int my_c;
   float my_v;
-  load_pairs(col, val, it.y, min(32, it.z - it.y), lane, my_c, my_v);
+  load_pairs<kWeighted>(col, val, it.y, min(32, it.z - it.y), lane, pad_col, my_c, my_v);
   while (true) {
     const int item_n = item + nwarps;
     int c_n = 0;
     float v_n = 0.f;
     if (item_n < n_items) {
       const int4 nx = __ldg(&items[item_n]);  // L1 hit: prefetched one trip ago
-      load_pairs(col, val, nx.y, min(32, nx.z - nx.y), lane, c_n, v_n);
+      load_pairs<kWeighted>(col, val, nx.y, min(32, nx.z - nx.y), lane, pad_col, c_n, v_n);
       if (item_n + nwarps < n_items) prefetch_l1(&items[item_n + nwarps]);
     }
 
@@ -117,10 +141,10 @@ spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, co
       int cc = my_c;
       float vv = my_v;
       while (true) {
-        gather_pairs(Xs, d, cc, vv, min(32, it.z - base), half, acc);
+        gather_pairs<kWeighted>(Xs, d, cc, vv, min(32, it.z - base), half, acc);
         base += 32;
         if (base >= it.z) break;
-        load_pairs(col, val, base, min(32, it.z - base), lane, cc, vv);
+        load_pairs<kWeighted>(col, val, base, min(32, it.z - base), lane, pad_col, cc, vv);
       }
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
       acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
@@ -128,7 +152,12 @@ spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, co
       acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
       if (half == 0) {
         if (it.w < 0) {
-          float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+          float al = alpha;
+          if (row_scale) {
+            const float rsv = row_scale[it.x];
+            al *= (row_pow == 2) ? rsv * rsv : rsv;
+          }
+          float4 o = make_float4(al * acc.x, al * acc.y, al * acc.z, al * acc.w);
           if (Z) {
             const float4 z = ld_stream_f32x4(Z + (long long)it.x * d + coff);
             o.x = fmaf(beta, z.x, o.x);
@@ -155,7 +184,8 @@ spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, co
 // range order: a fixed summation tree (deterministic), ~n_slots/64 L2 round trips for a hub row instead of n_slots.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 spmm_long_reduce_kernel(const int* __restrict__ long_rows, int n_long, const float* __restrict__ scratch,
-                        const float* __restrict__ Z, float* __restrict__ Y, int d, float alpha, float beta) {
+                        const float* __restrict__ Z, float* __restrict__ Y, int d, float alpha, float beta,
+                        const float* __restrict__ row_scale, int row_pow) {
   __shared__ float2 part_sm[WARPS_PER_CTA][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slabs = d >> 6;
@@ -188,7 +218,12 @@ spmm_long_reduce_kernel(const int* __restrict__ long_rows, int n_long, const flo
         tot.x += part_sm[q][lane].x;
         tot.y += part_sm[q][lane].y;
       }
-      float2 o = make_float2(alpha * tot.x, alpha * tot.y);
+      float al = alpha;
+      if (row_scale) {
+        const float rsv = row_scale[row];
+        al *= (row_pow == 2) ? rsv * rsv : rsv;
+      }
+      float2 o = make_float2(al * tot.x, al * tot.y);
       if (Z) {
         const float2 z = *reinterpret_cast<const float2*>(Z + (long long)row * d + coff);
         o.x = fmaf(beta, z.x, o.x);
@@ -297,11 +332,10 @@ extern "C" int gdmcf_spmm_plan(const int32_t* rowptr, int n_rows, int chunk, int
   return GDMCF_OK;
 }
 
-extern "C" int gdmcf_spmm_csr_f32(const int32_t* col, const float* val, const int32_t* items, int n_items,
-                                  const int32_t* long_rows, int n_long, const float* X, const float* Z, float* Y,
-                                  float* scratch, int n_rows, int d, float alpha, float beta, gdmcf_stream_t stream) {
-  (void)n_rows;
-  if (!col || !val || !items || !X || !Y || n_items < 0 || d <= 0 || (d & 63)) {
+static int spmm_launch(const int32_t* col, const float* val, const int32_t* items, int n_items, const int32_t* long_rows,
+                       int n_long, const float* X, const float* Z, float* Y, float* scratch, int d, float alpha, float beta,
+                       const float* row_scale, int row_pow, int pad_col, gdmcf_stream_t stream) {
+  if (!col || (!val && !row_scale) || !items || !X || !Y || n_items < 0 || d <= 0 || (d & 63)) {
     set_error("spmm: need col/val/items/X/Y and d %% 64 == 0 (d=%d)", d);
     return GDMCF_EBADARG;
   }
@@ -315,15 +349,90 @@ extern "C" int gdmcf_spmm_csr_f32(const int32_t* col, const float* val, const in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int slabs = d >> 6;
   if (n_items > 0) {
-    spmm_items_kernel<<<grid_for_warps((long long)n_items * slabs), WARPS_PER_CTA * 32, 0, st>>>(
-        col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y, scratch, d, alpha, beta);
+    const int grid = grid_for_warps((long long)n_items * slabs);
+    if (val)
+      spmm_items_kernel<true><<<grid, WARPS_PER_CTA * 32, 0, st>>>(col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y,
+                                                                 scratch, d, alpha, beta, row_scale, row_pow, pad_col);
+    else
+      spmm_items_kernel<false><<<grid, WARPS_PER_CTA * 32, 0, st>>>(col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y,
+                                                                  scratch, d, alpha, beta, row_scale, row_pow, pad_col);
     if ((rc = cuda_check_launch("spmm_items_kernel"))) return rc;
   }
   if (n_long > 0) {
     const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
     spmm_long_reduce_kernel<<<(int)std::min<long long>((long long)n_long * slabs, (long long)sms * 8), WARPS_PER_CTA * 32, 0, st>>>(
-        long_rows, n_long, scratch, Z, Y, d, alpha, beta);
+        long_rows, n_long, scratch, Z, Y, d, alpha, beta, row_scale, row_pow);
     if ((rc = cuda_check_launch("spmm_long_reduce_kernel"))) return rc;
+  }
+  return GDMCF_OK;
+}
+
+extern "C" int gdmcf_spmm_csr_f32(const int32_t* col, const float* val, const int32_t* items, int n_items,
+                                  const int32_t* long_rows, int n_long, const float* X, const float* Z, float* Y,
+                                  float* scratch, int n_rows, int d, float alpha, float beta, gdmcf_stream_t stream) {
+  (void)n_rows;
+  if (!val) { set_error("spmm: val is required (use gdmcf_lightgcn_propagate_sym_f32 for a binary adjacency)"); return GDMCF_EBADARG; }
+  return spmm_launch(col, val, items, n_items, long_rows, n_long, X, Z, Y, scratch, d, alpha, beta, nullptr, 0, 0, stream);
+}
+
+// u0[r, :] = dinv[r] * E0[r, :]
+__global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y, long long n4, int d4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float sv = s[i / d4];
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= sv; v.y *= sv; v.z *= sv; v.w *= sv;
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
+// dinv[r] = (deg_r + 1e-9)^-1/2 for the bipartite graph [[0, R], [R^T, 0]] (lightGCN.py:160-166)
+__global__ void norm_adj_dinv_kernel(const int* __restrict__ r_rowptr, const int* __restrict__ rt_rowptr, int n_users, int n_items,
+                                     float* __restrict__ dinv) {
+  const int n = n_users + n_items;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const int deg = r < n_users ? r_rowptr[r + 1] - r_rowptr[r] : rt_rowptr[r - n_users + 1] - rt_rowptr[r - n_users];
+    dinv[r] = d_inv_of(deg);
+  }
+}
+
+extern "C" int gdmcf_norm_adj_dinv(const int32_t* r_rowptr, const int32_t* rt_rowptr, int n_users, int n_items, float* dinv,
+                                   gdmcf_stream_t stream) {
+  if (!r_rowptr || !rt_rowptr || !dinv || n_users <= 0 || n_items <= 0) { set_error("norm_adj_dinv: bad arguments"); return GDMCF_EBADARG; }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  norm_adj_dinv_kernel<<<(n_users + n_items + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(r_rowptr, rt_rowptr, n_users,
+                                                                                                      n_items, dinv);
+  return cuda_check_launch("norm_adj_dinv_kernel");
+}
+
+// mean_k (A~^k E0) for A~ = D^-1/2 A D^-1/2 with a BINARY A (pattern `col`) and dinv = diag(D^-1/2): iterate on
+// U_k = D^-1/2 T_k, for which the Horner step T <- A~ T + E0 becomes U <- D^-1 (A U) + U_0 with plain (unweighted) neighbour
+// sums — no value stream, no per-non-zero multiply; the last layer maps back: out = (dinv * (A U_{K-1}) + E0) / (K + 1).
+// u0 / tmp0 / tmp1 must have n + 1 rows with row n all zero (never written here): padding lanes of the gather read it.
+extern "C" int gdmcf_lightgcn_propagate_sym_f32(const int32_t* col, const float* dinv, const int32_t* items, int n_items,
+                                                const int32_t* long_rows, int n_long, const float* E0, float* u0, float* tmp0,
+                                                float* tmp1, float* out, float* scratch, int n, int d, int n_layers,
+                                                gdmcf_stream_t stream) {
+  if (n_layers < 1 || !E0 || !out || !dinv || !u0 || (n_layers > 1 && !tmp0) || (n_layers > 2 && !tmp1) || n <= 0 || d <= 0 || (d & 63)) {
+    set_error("lightgcn_propagate_sym: need n_layers >= 1, E0, dinv, u0, out and ping-pong buffers");
+    return GDMCF_EBADARG;
+  }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  const long long n4 = (long long)n * d / 4;
+  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  scale_rows_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)sms * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      E0, dinv, u0, n4, d / 4);
+  if ((rc = cuda_check_launch("scale_rows_kernel"))) return rc;
+  const float* src = u0;
+  for (int l = 0; l < n_layers; ++l) {
+    const bool last = (l == n_layers - 1);
+    float* dst = last ? out : ((l & 1) ? tmp1 : tmp0);
+    const float s = last ? 1.0f / (float)(n_layers + 1) : 1.0f;
+    rc = spmm_launch(col, nullptr, items, n_items, long_rows, n_long, src, last ? E0 : u0, dst, scratch, d, s, s, dinv, last ? 1 : 2,
+                     n, stream);
+    if (rc) return rc;
+    src = dst;
   }
   return GDMCF_OK;
 }

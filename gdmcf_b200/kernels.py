@@ -101,9 +101,11 @@ def spmm_csr(plan: SpmmPlan, col, val, X, Z=None, alpha: float = 1.0, beta: floa
     return out
 
 
-def lightgcn_propagate(plan: SpmmPlan, col, val, E0, n_layers: int, out=None, work=None):
-    """mean_{k<=K} A^k E0 (lightGCN.py:180-194). `work` = (tmp0, tmp1, scratch) to avoid reallocation."""
-    require_cuda(col, val, E0)
+def lightgcn_propagate(plan: SpmmPlan, col, val, E0, n_layers: int, out=None, work=None, dinv=None):
+    """mean_{k<=K} A^k E0 (lightGCN.py:180-194). `work` = (tmp0, tmp1, scratch[, u0]) to avoid reallocation.
+    dinv (= D^-1/2 of the binary adjacency, kernels.norm_adj_dinv): use the separable-normalisation form, which needs no
+    values (`val` is ignored) — same result up to fp32 rounding."""
+    require_cuda(col, val, E0, dinv)
     n, d = E0.shape
     assert n == plan.n_rows and E0.dtype == torch.float32 and E0.is_contiguous()
     if out is None:
@@ -111,11 +113,34 @@ def lightgcn_propagate(plan: SpmmPlan, col, val, E0, n_layers: int, out=None, wo
     if work is None:
         work = (torch.empty_like(E0), torch.empty_like(E0),
                 torch.empty(max(plan.n_slots, 1), d, dtype=torch.float32, device=E0.device))
-    tmp0, tmp1, scratch = work
+    if dinv is not None:
+        if len(work) < 4 or any(w.shape[0] != n + 1 for w in (work[0], work[1], work[3])):
+            work = lightgcn_sym_work(plan, E0)
+        tmp0, tmp1, scratch, u0 = work
+        check(load().gdmcf_lightgcn_propagate_sym_f32(ptr(col), ptr(dinv), ptr(plan.items), plan.n_items, ptr(plan.long_rows),
+                                                      plan.n_long, ptr(E0), ptr(u0), ptr(tmp0), ptr(tmp1), ptr(out),
+                                                      ptr(scratch), n, d, n_layers, stream()), "lightgcn_propagate_sym_f32")
+        return out
+    tmp0, tmp1, scratch = work[:3]
     check(load().gdmcf_lightgcn_propagate_f32(ptr(col), ptr(val), ptr(plan.items), plan.n_items, ptr(plan.long_rows),
                                               plan.n_long, ptr(E0), ptr(tmp0), ptr(tmp1), ptr(out), ptr(scratch), n, d,
                                               n_layers, stream()), "lightgcn_propagate_f32")
     return out
+
+
+def lightgcn_sym_work(plan: SpmmPlan, E0):
+    """(tmp0, tmp1, scratch, u0) for lightgcn_propagate(..., dinv=...): [n + 1, d] buffers whose last row is zero."""
+    n, d = E0.shape
+    mk = lambda: torch.zeros(n + 1, d, dtype=torch.float32, device=E0.device)  # noqa: E731
+    return (mk(), mk(), torch.empty(max(plan.n_slots, 1), d, dtype=torch.float32, device=E0.device), mk())
+
+
+def norm_adj_dinv(r_rowptr, rt_rowptr, n_users: int, n_items: int) -> torch.Tensor:
+    """dinv[r] = (deg_r + 1e-9)^-1/2 over users then items (lightGCN.py:160-166)."""
+    require_cuda(r_rowptr, rt_rowptr)
+    dinv = torch.empty(n_users + n_items, dtype=torch.float32, device=r_rowptr.device)
+    check(load().gdmcf_norm_adj_dinv(ptr(r_rowptr), ptr(rt_rowptr), n_users, n_items, ptr(dinv), stream()), "norm_adj_dinv")
+    return dinv
 
 
 def build_norm_adj(r_rowptr, r_col, rt_rowptr, rt_col, n_users: int, n_items: int):

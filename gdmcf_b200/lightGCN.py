@@ -40,7 +40,10 @@ class LightGCN(nn.Module):
         RT.sort_indices()
         dev = self.device
         t = lambda a: torch.from_numpy(a.astype(np.int32)).to(dev)  # noqa: E731
-        rowptr, col, val = K.build_norm_adj(t(R.indptr), t(R.indices), t(RT.indptr), t(RT.indices), self.n_users, self.n_items)
+        r_rp, rt_rp = t(R.indptr), t(RT.indptr)
+        rowptr, col, val = K.build_norm_adj(r_rp, t(R.indices), rt_rp, t(RT.indices), self.n_users, self.n_items)
+        # D^-1/2 of the interaction graph (pattern only, like build_norm_adj): the propagation uses the separable form
+        self.dinv = K.norm_adj_dinv(r_rp, rt_rp, self.n_users, self.n_items)
         self.plan = K.spmm_plan(rowptr.cpu(), chunk=self.chunk, device=dev)
         self.norm_adj_mat_sparse_tensor = (rowptr, col, val)  # reference attribute name; CSR triple here
         return rowptr, col, val
@@ -50,7 +53,7 @@ class LightGCN(nn.Module):
         """lightGCN.py:180-194: returns (final_user, final_item, initial_user, initial_item)."""
         _, col, val = self.norm_adj_csr
         E0 = self.E0.weight.detach()
-        mean = K.lightgcn_propagate(self.plan, col, val, E0, self.n_layers)
+        mean = K.lightgcn_propagate(self.plan, col, val, E0, self.n_layers, dinv=self.dinv)
         final_user, final_item = torch.split(mean, [self.n_users, self.n_items])
         initial_user, initial_item = torch.split(E0, [self.n_users, self.n_items])
         return final_user, final_item, initial_user, initial_item

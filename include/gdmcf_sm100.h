@@ -72,6 +72,18 @@ int gdmcf_lightgcn_propagate_f32(const int32_t* col, const float* val, const int
 /* get_A_tilda (lightGCN.py:145-178) on the device: given the user->item CSR of R (U x I) and its
  * transpose, writes the CSR of A~ = D^-1/2 [[0,R],[R^T,0]] D^-1/2 with d_inv = (rowsum + 1e-9)^-1/2.
  * rowptr_out int32[U+I+1], col_out int32[2 nnz], val_out fp32[2 nnz]. */
+/* The same propagation for the separable normalisation A~ = D^-1/2 A D^-1/2 of a BINARY adjacency (lightGCN.py:145-178):
+ * only the CSR pattern and dinv[n] = (deg + 1e-9)^-1/2 are needed. Iterates on U_k = D^-1/2 T_k, so neighbour sums are
+ * unweighted (no value stream, no per-non-zero multiply). u0, tmp0, tmp1: caller-provided [n + 1, d] buffers whose last row
+ * is zero (the kernels never write it; padding lanes of the gather read it). Same result as the value form up to fp32
+ * rounding. */
+int gdmcf_lightgcn_propagate_sym_f32(const int32_t* col, const float* dinv, const int32_t* items, int n_items,
+                                     const int32_t* long_rows, int n_long, const float* E0, float* u0, float* tmp0,
+                                     float* tmp1, float* out, float* scratch, int n, int d, int n_layers,
+                                     gdmcf_stream_t stream);
+/* dinv[r] = (deg_r + 1e-9)^-1/2 over the bipartite graph [[0, R], [R^T, 0]] (lightGCN.py:160-166). */
+int gdmcf_norm_adj_dinv(const int32_t* r_rowptr, const int32_t* rt_rowptr, int n_users, int n_items, float* dinv,
+                        gdmcf_stream_t stream);
 int gdmcf_build_norm_adj(const int32_t* r_rowptr, const int32_t* r_col, const int32_t* rt_rowptr,
                          const int32_t* rt_col, int n_users, int n_items, int32_t* rowptr_out,
                          int32_t* col_out, float* val_out, gdmcf_stream_t stream);

@@ -83,6 +83,12 @@ def test_yelp_shape_lightgcn_vs_torch_sparse_and_linearity(yelp):
     ref = ref / 4                                                         # mean over the K+1 layer outputs (:188-189)
     got = K.lightgcn_propagate(lg.plan, col, val, E0, 3)
     assert ((got - ref).norm() / ref.norm()).item() < 1e-5
+    # separable-normalisation form (pattern + D^-1/2, no value stream): same propagation
+    sym = K.lightgcn_propagate(lg.plan, col, None, E0, 3, dinv=lg.dinv)
+    assert ((sym - ref).norm() / ref.norm()).item() < 1e-5 and ((sym - got).abs().max() / got.abs().max()).item() < 1e-5
+    assert torch.equal(sym, K.lightgcn_propagate(lg.plan, col, None, E0, 3, dinv=lg.dinv))
+    fu, fi, _, _ = lg.propagate_through_layers()
+    assert torch.equal(torch.cat([fu, fi]), sym)
     X = torch.randn_like(E0)
     lin = K.lightgcn_propagate(lg.plan, col, val, 0.5 * E0 - 2.0 * X, 3)
     comb = 0.5 * got - 2.0 * K.lightgcn_propagate(lg.plan, col, val, X, 3)

@@ -209,6 +209,13 @@ def test_spmm_and_lightgcn(K, d):
     ref = torch.stack(layers).mean(0)
     torch.cuda.synchronize()
     assert (out - ref).abs().max().item() < 2e-5
+    # separable-normalisation form: pattern + D^-1/2 only (long rows and d = 128 slabs included)
+    dinv_dev = K.norm_adj_dinv(torch.from_numpy(r_rowptr).to(dev), torch.from_numpy(rt_rowptr).to(dev), U, I)
+    assert torch.allclose(dinv_dev.cpu().double(), dinv, rtol=1e-6)
+    sym = K.lightgcn_propagate(plan, col, None, E0, 3, dinv=dinv_dev)
+    assert (sym - ref).abs().max().item() < 2e-5
+    one = K.lightgcn_propagate(plan, col, None, E0, 1, dinv=dinv_dev)
+    assert (one - (E0 + An @ E0) / 2).abs().max().item() < 2e-5
 
 
 def test_spmm_empty_rows_and_beta(K):

@@ -24,21 +24,23 @@ def main():
     _, col, val = lg.norm_adj_csr
     E0 = lg.E0.weight.detach()
     out = torch.empty_like(E0)
-    work = (torch.empty_like(E0), torch.empty_like(E0), torch.empty(max(lg.plan.n_slots, 1), 64, device="cuda"))
+    sym = os.environ.get("SPMM_SYM", "1") != "0"
+    work = K.lightgcn_sym_work(lg.plan, E0) if sym else (torch.empty_like(E0), torch.empty_like(E0),
+                                                         torch.empty(max(lg.plan.n_slots, 1), 64, device="cuda"))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     ts = []
     for it in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        K.lightgcn_propagate(lg.plan, col, val, E0, layers, out=out, work=work)
+        K.lightgcn_propagate(lg.plan, col, val, E0, layers, out=out, work=work, dinv=lg.dinv if sym else None)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     N, nnz = n_user + n_item, col.numel()
     bytes_alg = layers * (nnz * 8 + (N + 1) * 4 + 2 * N * 64 * 4)
     t = sorted(ts[2:])[len(ts[2:]) // 2] if len(ts) > 2 else ts[-1]
-    print(f"spmm {wl}: N={N} nnz={nnz} items={lg.plan.n_items} long={lg.plan.n_long} ms={['%.3f' % x for x in ts]} "
+    print(f"spmm {wl} ({'separable' if sym else 'value'} form): N={N} nnz={nnz} items={lg.plan.n_items} long={lg.plan.n_long} ms={['%.3f' % x for x in ts]} "
           f"median {t:.3f} ms -> {bytes_alg / t / 1e6:.1f} GB/s algorithmic ({bytes_alg / 1e6:.1f} MB)")
 
 
