@@ -120,9 +120,11 @@ __global__ void qsample_dropout_kernel(const float* __restrict__ x0, long long l
                                        float* __restrict__ xt_f32, long long ld_xt,
                                        __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, long long ld_a,
                                        int rows, int cols) {
-  // Philox counter = offset0 + (epoch << 44) + element group: `epoch` is a device-resident step counter, so a
-  // captured CUDA graph draws fresh numbers on every replay
-  const uint64_t offset = offset0 + (epoch ? (epoch[0] << 44) : 0ull);
+  // Philox counter: low word = offset0 (call site << 40) + element group, high word = (epoch << 8) | sub-stream.
+  // `epoch` is a device-resident step counter, so a captured CUDA graph draws fresh numbers on every replay; it has
+  // 56 bits of its own and cannot run into the call-site or element fields however long the run is.
+  const uint64_t offset = offset0;
+  const uint64_t ep = epoch ? (epoch[0] << 8) : 0ull;
   const int groups = (int)(ld_a / 4);  // ld_a % 8 == 0
   const long long total = (long long)rows * groups;
   const Philox rng(seed);
@@ -136,11 +138,11 @@ __global__ void qsample_dropout_kernel(const float* __restrict__ x0, long long l
     float eps[4] = {0.f, 0.f, 0.f, 0.f};
     uint4 ur = make_uint4(0, 0, 0, 0);
     if (noisy && !noise) {
-      const uint4 g = rng(offset + (uint64_t)i, 0ull);
+      const uint4 g = rng(offset + (uint64_t)i, ep | 0ull);
       const float2 n0 = box_muller(g.x, g.y), n1 = box_muller(g.z, g.w);
       eps[0] = n0.x; eps[1] = n0.y; eps[2] = n1.x; eps[3] = n1.y;
     }
-    if (dropout_p > 0.f && !keep) ur = rng(offset + (uint64_t)i, 1ull);
+    if (dropout_p > 0.f && !keep) ur = rng(offset + (uint64_t)i, ep | 1ull);
     const uint32_t urr[4] = {ur.x, ur.y, ur.z, ur.w};
     __nv_bfloat16 h[4], l[4];
 #pragma unroll
@@ -185,7 +187,8 @@ __global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x
                                     const float* __restrict__ u_drop, uint64_t seed, uint64_t offset0,
                                     const uint64_t* __restrict__ epoch, __nv_bfloat16* __restrict__ out, long long ld_out,
                                     int rows, int cols) {
-  const uint64_t offset = offset0 + (epoch ? (epoch[0] << 44) : 0ull);
+  const uint64_t offset = offset0;
+  const uint64_t ep = epoch ? (epoch[0] << 8) : 0ull;  // high counter word = (epoch << 8) | sub-stream
   const int groups = (int)(ld_out / 8);  // 8 outputs = 4 items per thread
   const long long total = (long long)rows * groups;
   const Philox rng(seed);
@@ -199,8 +202,8 @@ __global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x
     const float q_one = a * 1.0f + (1.0f - a) * (1.0f - discrete);  // x0 == 1 keeps channel 1
     const float q_zero = a * 1.0f + (1.0f - a) * discrete;          // x0 == 0 keeps channel 0
     uint4 g0 = make_uint4(0, 0, 0, 0), g1 = make_uint4(0, 0, 0, 0);
-    if (!u_keep && ts) g0 = rng(offset + (uint64_t)i, 2ull);
-    if (!u_drop && dropout_p > 0.f) g1 = rng(offset + (uint64_t)i, 3ull);
+    if (!u_keep && ts) g0 = rng(offset + (uint64_t)i, ep | 2ull);
+    if (!u_drop && dropout_p > 0.f) g1 = rng(offset + (uint64_t)i, ep | 3ull);
     const uint32_t gk[4] = {g0.x, g0.y, g0.z, g0.w}, gd_[4] = {g1.x, g1.y, g1.z, g1.w};
     __nv_bfloat16 o[8];
 #pragma unroll

@@ -343,14 +343,15 @@ sample_timesteps_kernel(const double* __restrict__ hist, const long long* __rest
     }
   }
   __syncthreads();
-  const uint64_t offset = offset0 + (epoch ? (epoch[0] << 44) : 0ull);
+  const uint64_t offset = offset0;
+  const uint64_t ep = epoch ? (epoch[0] << 8) : 0ull;  // high counter word = (epoch << 8) | sub-stream
   const Philox rng(seed);
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     long long t;
     if (ts_in) {
       t = ts_in[b];
     } else {
-      const uint4 g = rng(offset + (uint64_t)b, 7ull);
+      const uint4 g = rng(offset + (uint64_t)b, ep | 7ull);
       const double u = ((double)(g.x >> 5) * 67108864.0 + (double)(g.y >> 6)) * (1.0 / 9007199254740992.0);  // [0,1), 53 bits
       if (ready) {
         const double target = u * s_cdf[T - 1];

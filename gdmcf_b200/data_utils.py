@@ -74,14 +74,53 @@ def synthetic_interactions(n_user: int, n_item: int, n_pairs: int, seed: int = 0
     rescaled to n_pairs total and clipped to [5, n_item/4]; items ~ Zipf(1.0) over a random permutation;
     de-duplicated; per-pair random 7:1:2 split. Returns (train, valid, test) int64 arrays [n, 2]."""
     rng = np.random.default_rng(seed)
+    lo_deg, hi_deg = min(5, n_item), max(min(5, n_item), n_item // 4)
     deg = rng.lognormal(0.0, 1.0, n_user)
-    deg = np.clip(deg * (n_pairs / deg.sum()), 5, max(5, n_item // 4)).astype(np.int64)
-    p = 1.0 / np.arange(1, n_item + 1)
-    p /= p.sum()
+    deg = np.clip(deg * (n_pairs / deg.sum()), lo_deg, hi_deg).astype(np.int64)
+    # the clip and the floor move the total: hand the difference out one interaction at a time over random users that
+    # still have room, so that exactly n_pairs DISTINCT pairs come out (when the bounds allow it at all)
+    n_pairs = int(min(max(n_pairs, n_user * lo_deg), n_user * hi_deg))
+    while deg.sum() != n_pairs:
+        diff = int(n_pairs - deg.sum())
+        room = np.flatnonzero(deg < hi_deg) if diff > 0 else np.flatnonzero(deg > lo_deg)
+        pick = rng.choice(room, size=min(abs(diff), room.shape[0]), replace=False)
+        deg[pick] += 1 if diff > 0 else -1
+    cdf = np.cumsum(1.0 / np.arange(1, n_item + 1))
+    cdf /= cdf[-1]
     perm = rng.permutation(n_item)
-    users = np.repeat(np.arange(n_user, dtype=np.int64), deg)
-    items = perm[rng.choice(n_item, size=users.shape[0], p=p)].astype(np.int64)
-    key = np.unique(users * n_item + items)
+    # draw with replacement, keep each user's first deg[u] distinct items in draw order; users that are still short are
+    # topped up with a doubling over-draw (only they are re-examined). One stable sort per round: draws are generated
+    # grouped by user, so "first deg[u] distinct, earlier rounds first" needs only a duplicate mask and running counts.
+    done = []
+    active = np.arange(n_user, dtype=np.int64)
+    old = np.empty(0, dtype=np.int64)                     # distinct pairs already held by the active users
+    have = np.zeros(n_user, dtype=np.int64)
+    mult = 1.25
+    while active.size:
+        need = deg[active] - have[active]
+        extra = (need * mult).astype(np.int64) + 2
+        users = np.repeat(active, extra)
+        new = users * n_item + perm[np.minimum(np.searchsorted(cdf, rng.random(users.shape[0])), n_item - 1)]
+        both = np.concatenate([old, new])
+        order = np.argsort(both, kind="stable")
+        srt = both[order]
+        fresh = np.ones(both.shape[0], dtype=bool)
+        fresh[order[1:][srt[1:] == srt[:-1]]] = False     # equal to an earlier entry (held pair or earlier draw)
+        fresh = fresh[old.shape[0]:]
+        seen = np.cumsum(fresh) - fresh                   # fresh draws before this one ...
+        begin = np.cumsum(extra) - extra                  # ... minus those of earlier users = rank within the user
+        rank = seen - np.repeat(seen[begin], extra)
+        keep = fresh & (have[users] + rank < deg[users])
+        new, users = new[keep], users[keep]
+        have[active] += np.bincount(np.searchsorted(active, users), minlength=active.size)
+        held = np.concatenate([old, new])
+        full = have[held // n_item] >= deg[held // n_item]
+        done.append(held[full])
+        old = held[~full]
+        active = active[have[active] < deg[active]]
+        mult *= 2.0
+    keys = np.concatenate(done)
+    key = np.sort(keys)
     users, items = key // n_item, key % n_item
     # every user and the largest ids must appear in train so that n_user/n_item derive like data_load does
     r = rng.random(users.shape[0])

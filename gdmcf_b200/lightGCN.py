@@ -48,16 +48,36 @@ class LightGCN(nn.Module):
         self.norm_adj_mat_sparse_tensor = (rowptr, col, val)  # reference attribute name; CSR triple here
         return rowptr, col, val
 
-    @torch.no_grad()
     def propagate_through_layers(self):
-        """lightGCN.py:180-194: returns (final_user, final_item, initial_user, initial_item)."""
-        _, col, val = self.norm_adj_csr
-        E0 = self.E0.weight.detach()
-        mean = K.lightgcn_propagate(self.plan, col, val, E0, self.n_layers, dinv=self.dinv)
+        """lightGCN.py:180-194: returns (final_user, final_item, initial_user, initial_item). Differentiable w.r.t. E0
+        like the reference's torch.sparse.mm chain (its BPR loop trains through it): Â is symmetric, so the backward of
+        mean_k Â^k is the same propagation applied to the incoming gradient."""
+        E0 = self.E0.weight
+        if torch.is_grad_enabled() and E0.requires_grad:
+            mean = _Propagate.apply(E0, self)
+        else:
+            mean = self._propagate(E0.detach())
         final_user, final_item = torch.split(mean, [self.n_users, self.n_items])
         initial_user, initial_item = torch.split(E0, [self.n_users, self.n_items])
         return final_user, final_item, initial_user, initial_item
 
+    def _propagate(self, X: torch.Tensor) -> torch.Tensor:
+        _, col, val = self.norm_adj_csr
+        return K.lightgcn_propagate(self.plan, col, val, X.contiguous(), self.n_layers, dinv=self.dinv)
+
     def forward(self, users, pos_items, neg_items):
         fu, fi, iu, ii = self.propagate_through_layers()
         return fu[users], fi[pos_items], fi[neg_items], iu[users], ii[pos_items], ii[neg_items]
+
+
+class _Propagate(torch.autograd.Function):
+    """mean_{k<=K} Â^k X with the hand-written SpMM in both directions (no torch.sparse path)."""
+
+    @staticmethod
+    def forward(ctx, E0, lg):
+        ctx.lg = lg
+        return lg._propagate(E0.detach())
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ctx.lg._propagate(grad), None

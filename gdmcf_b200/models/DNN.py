@@ -117,7 +117,7 @@ class _EngineModule(nn.Module):
 
     def _next_offset(self) -> int:
         self._rng_calls += 1
-        return self._rng_calls << 40  # disjoint Philox counter ranges per call
+        return (self._rng_calls & ((1 << 22) - 1)) << 40  # disjoint Philox counter ranges per call (bits 40-61)
 
     def _buf(self, key, make):
         b = self._bufs.get(key)

@@ -154,9 +154,10 @@ class GaussianDiffusionDiscrete(nn.Module):
         return res.expand(broadcast_shape)
 
     def _begin_step(self, dev) -> None:
-        """Advance the device-resident RNG epoch (one per training_losses / p_sample call). The Philox counter of every
-        in-kernel draw is (call site << 40) + (epoch << 44) + element, so a captured CUDA graph draws fresh numbers on
-        each replay without any host-side state."""
+        """Advance the device-resident RNG epoch (one per training_losses / p_sample call). The 128-bit Philox counter of
+        every in-kernel draw is low word = (call site << 40) + element, high word = (epoch << 8) | sub-stream, so a captured
+        CUDA graph draws fresh numbers on each replay without any host-side state and the epoch (56 bits) can never run
+        into the call-site field."""
         if self._epoch is None or self._epoch.device != torch.device(dev):
             self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         K.counter_add(self._epoch, 1)
@@ -164,6 +165,7 @@ class GaussianDiffusionDiscrete(nn.Module):
 
     def _offset(self) -> int:
         self._calls += 1
+        assert self._calls < (1 << 20), "more than 2^20 RNG call sites inside one step"
         return (self._calls << 40) | (1 << 62)
 
     # -- inputs ----------------------------------------------------------------------------------
@@ -342,7 +344,9 @@ class GaussianDiffusionDiscrete(nn.Module):
             out = model.reverse_loop(x_t, B, idx32, self.steps, c1, c2, x0_op=x_op, csr=csr, users=users, xu_op=xu_op)
         else:
             out = model.reverse_loop(x_t, B, None, self.steps, c1, c2, x0_op=x_op)
-        return out if _raw else out[:, :I]
+        # the loop's result lives in a cached ping-pong buffer that the next call overwrites: the public API hands back a
+        # fresh tensor like the reference; rank() consumes the buffer in place (_raw)
+        return out if _raw else out[:, :I].clone()
 
     @torch.no_grad()
     def rank(self, model, x_start, k, hist=None, hist2=None, steps=0, index=None, with_values=False):

@@ -2,7 +2,7 @@
 all-reduces must equal the same program run eagerly, ranks must stay bit-identical, and the sparse user-row exchange
 must equal a dense all-reduce of the user table's gradient, and the reduce-scatter + sharded AdamW + all-gather path
 must equal the all-reduce + replicated AdamW path.
-usage: torchrun --nproc-per-node N tools/engine_dist_check.py"""
+usage: torchrun --nproc-per-node N tests/_engine_dist_worker.py  (driven by tests/test_engine_gpu.py::test_engine_data_parallel_torchrun)"""
 import os
 import sys
 

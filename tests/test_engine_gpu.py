@@ -225,3 +225,25 @@ def test_engine_dnn_backbone_graph_equals_eager():
         assert torch.isfinite(outs[0][0])
     for (n, pa), (_, pb) in zip(engines[0][0].named_parameters(), engines[1][0].named_parameters()):
         assert torch.equal(pa, pb), n
+
+
+@pytest.mark.parametrize("world", [2])
+def test_engine_data_parallel_torchrun(world):
+    """The data-parallel engine under torchrun + NCCL (tests/_engine_dist_worker.py): graph segments with overlapped
+    collectives == the same program run eagerly (bit for bit); ranks stay bit-identical; sparse user-row exchange == dense
+    all-reduce; reduce-scatter + row-sharded AdamW + all-gather == all-reduce + replicated AdamW."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_engine_dist_worker.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), worker],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert f"engine_dist_check: world {world}" in res.stdout and "OK" in res.stdout, res.stdout[-2000:]

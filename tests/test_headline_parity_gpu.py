@@ -1,0 +1,169 @@
+"""Model-level parity with the oracle AT THE HEADLINE SHAPE (BASELINE.json configs[0]/[1]: Yelp shape, I = 34 395,
+d = 1000, B = 400, T = 5), in both precision modes, with injected draws: one training_losses loss vector
+(models/gaussian_diffusion.py:834-957), the p_sample scores (:668-768), the history-masked top-20 (main.py:299-301) and
+Recall/NDCG@{10,20} (evaluate_utils.py:6-52). The oracle needs ~10 s of CPU work per batch at this size.
+
+Tolerances held (normwise relative error against the fp32 CPU oracle), north_star quotes 1e-3 / 1e-5 as examples:
+    bf16 mode: loss, mse, scores <= 5e-3   (bf16 operands, fp32 accumulation; measured ~3e-3)
+    fp32 mode: loss, mse, scores <= 5e-5   (3-segment bf16 split; measured ~6e-6)
+Top-k: every position where engine and oracle disagree must be a near-tie of the ORACLE's scores (gap <= 4 * tol *
+max|score|, tol = 1e-3 / 1e-5); outside near-ties indices are identical, and Recall/NDCG computed from the two lists
+agree exactly on every row without a near-tie swap."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+pytestmark = pytest.mark.gpu
+
+U, I, P, SEED = 54574, 34395, 1402736, 0
+B, D, T, KTOP = 400, 1000, 5, 20
+TOL = {"bf16": (5e-3, 1e-3), "fp32": (5e-5, 1e-5)}
+
+
+@pytest.fixture(scope="module")
+def ref():
+    """Data, reference weights, injected draws and the oracle's outputs (computed once for both precisions)."""
+    from gdmcf_b200 import data_utils
+    from oracle import gdmcf_oracle as O
+    tr, va, te = data_utils.synthetic_interactions(U, I, P, SEED)
+    mk = lambda p: sp.csr_matrix((np.ones(len(p), dtype=np.float32), (p[:, 0], p[:, 1])), shape=(U, I))  # noqa: E731
+    train_sp, test_sp = mk(tr), mk(te)
+    torch.manual_seed(0)
+    oracle = O.OracleGDMCF([I, D], [D, I], 10, item_num=I, user_num=U)
+    with torch.no_grad():
+        oracle.sumW.fill_(0.8)  # a mix weight of exactly 1 would hide the GCN branch from the scores
+    od = O.OracleDiffusion(steps=T, noise_scale=0.01)
+    users = np.arange(2000, 2000 + B)
+    x0 = torch.from_numpy(np.asarray(train_sp[users].todense(), dtype=np.float32))
+    index = torch.from_numpy(users).long()
+    g = torch.Generator().manual_seed(11)
+    draws = dict(ts1=torch.randint(0, T, (B,), generator=g), ts=torch.randint(0, T, (B,), generator=g),
+                 noise=torch.randn(B, I, generator=g), u_keep=torch.rand(B, I, generator=g),
+                 kx=torch.rand(B, I, generator=g) >= 0.5, kxu=torch.rand(B, 2 * I, generator=g) >= 0.5)
+    with torch.no_grad():
+        oracle.train()
+        ot = od.training_losses(oracle, x0, index, draws["ts1"], draws["ts"], draws["noise"], draws["u_keep"], draws["kx"],
+                                draws["kxu"], reweight=True)
+        oracle.eval()
+        scores = od.p_sample(oracle, x0, 0, index=index)
+    hist = [train_sp.indices[train_sp.indptr[u]:train_sp.indptr[u + 1]] for u in users]
+    rv, ri = O.mask_topk(scores, hist, KTOP)
+    target = [test_sp.indices[test_sp.indptr[u]:test_sp.indptr[u + 1]].tolist() for u in users]
+    return dict(train_sp=train_sp, test_sp=test_sp, sd=oracle.state_dict(), users=users, draws=draws, ot=ot, scores=scores,
+                rv=rv, ri=ri, target=target, O=O)
+
+
+def _rel(a, b):
+    return float((a.double().cpu() - b.double()).norm() / b.double().norm())
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_yelp_shape_loss_scores_topk_metrics_vs_oracle(ref, precision):
+    from gdmcf_b200 import data_utils, evaluate_utils
+    from gdmcf_b200.models import gaussian_diffusion as gd
+    from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    O = ref["O"]
+    dev = torch.device("cuda")
+    model = DNNOneHotEmbeddingGCN([I, D], [D, I], 10, item_num=I, user_num=U, precision=precision)
+    model.load_state_dict(ref["sd"])
+    model.to(dev)
+    diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, T, dev, discrete=0.9995,
+                                        CatOneHot=True)
+    diff.indexIn = True
+    train_dev = data_utils.DeviceInteractions(ref["train_sp"], dev)
+    test_dev = data_utils.DeviceInteractions(ref["test_sp"], dev)
+    batch = train_dev.batch(ref["users"].astype(np.int32))
+    d = ref["draws"]
+    tol_norm, tol_tie = TOL[precision]
+    with torch.no_grad():
+        model.train()
+        et = diff.training_losses(model, batch, True, index=batch.users,
+                                  inject=dict(ts_discrete=d["ts1"].to(dev), ts=d["ts"].to(dev), noise=d["noise"].to(dev),
+                                              u_keep=d["u_keep"].to(dev), keep_x=d["kx"].to(dev), keep_xU=d["kxu"].to(dev)))
+    ot = ref["ot"]
+    e_loss, e_mse = _rel(et["loss"], ot["loss"]), _rel(et["mse"], ot["mse"])
+    e_out = _rel(et["model_output"], ot["model_output"])
+    e_closs = abs(float(et["closs"]) - float(ot["closs"])) / abs(float(ot["closs"]))
+    assert e_loss <= tol_norm and e_mse <= tol_norm and e_out <= tol_norm and e_closs <= tol_norm, (e_loss, e_mse, e_out, e_closs)
+    assert et["loss"].dtype == torch.float64  # the reference's loss is float64 (SNR weights are f64)
+
+    model.eval()
+    got = diff.p_sample(model, batch, 0, index=batch.users)
+    e_scores = _rel(got, ref["scores"])
+    assert e_scores <= tol_norm, e_scores
+    idx, val = diff.rank(model, batch, KTOP, hist=train_dev.csr, with_values=True)
+    idx = idx.cpu().long()
+    assert _rel(val, ref["rv"]) <= tol_norm
+    sc, ri = ref["scores"], ref["ri"]
+    band = 4.0 * tol_tie * float(sc.abs().max())
+    mism = idx != ri
+    gap = (sc.gather(1, idx) - sc.gather(1, ri)).abs()
+    assert not (mism & (gap > band)).any(), f"top-{KTOP} disagreement outside near-ties: {int((mism & (gap > band)).sum())}"
+    # Recall / NDCG: rows whose lists are identical must give identical per-user statistics; in aggregate the two runs may
+    # differ only through the near-tie rows
+    clean = ~mism.any(1)
+    assert clean.float().mean().item() > (0.5 if precision == "bf16" else 0.95), clean.float().mean().item()
+    rows = torch.nonzero(clean).flatten().tolist()
+    tgt = [ref["target"][r] for r in rows]
+    m_eng = O.computeTopNAccuracy(tgt, idx[rows].tolist(), [10, KTOP])
+    m_ref = O.computeTopNAccuracy(tgt, ri[rows].tolist(), [10, KTOP])
+    assert m_eng == m_ref
+    # and the device metric kernel on the engine's own lists equals the reference formula on them (all rows)
+    sums = evaluate_utils.metrics_from_device(idx.to(dev).int(), batch.users, test_dev.rowptr, test_dev.col, [10, KTOP])
+    got_m = evaluate_utils.finalize_metrics(sums, B)
+    want_m = O.computeTopNAccuracy(ref["target"], idx.tolist(), [10, KTOP])
+    assert [list(x) for x in got_m] == [list(x) for x in want_m]
+    full_ref = O.computeTopNAccuracy(ref["target"], ri.tolist(), [10, KTOP])
+    n_tie_rows = int((~clean).sum())
+    for a, b in zip(want_m[1] + want_m[2], full_ref[1] + full_ref[2]):  # Recall@10/20, NDCG@10/20
+        assert abs(a - b) <= n_tie_rows / B + 1e-4, (want_m, full_ref, n_tie_rows)
+    print(f"[{precision}] loss {e_loss:.2e} mse {e_mse:.2e} out {e_out:.2e} closs {e_closs:.2e} scores {e_scores:.2e} "
+          f"top-{KTOP} positions equal {(~mism).float().mean().item():.4f} rows identical {clean.float().mean().item():.3f} "
+          f"recall/ndcg engine {want_m[1]}/{want_m[2]} oracle {full_ref[1]}/{full_ref[2]}")
+
+
+def test_lightgcn_cuda_vs_reference_golden():
+    """gdmcf_b200.lightGCN.LightGCN (device Â build + CSR SpMM propagate) against tests/golden/lightgcn.npz, which
+    oracle/make_golden.py recorded from the UNMODIFIED reference class (lightGCN.py:145-194)."""
+    import os
+    from gdmcf_b200.lightGCN import LightGCN
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lightgcn.npz"))
+    nu, ni, K = int(g["n_users"]), int(g["n_items"]), int(g["n_layers"])
+    pairs = g["pairs"]
+    lg = LightGCN({"user_id_idx": pairs[:, 0], "item_id_idx": pairs[:, 1]}, nu, ni, K, 64, device="cuda")
+    with torch.no_grad():
+        lg.E0.weight.copy_(torch.from_numpy(g["E0"]).cuda())
+    rowptr, col, val = lg.norm_adj_csr
+    N = nu + ni
+    A = torch.sparse_csr_tensor(rowptr.long(), col.long(), val, size=(N, N)).to_dense().cpu()
+    A_ref = torch.sparse_coo_tensor(torch.from_numpy(g["A_indices"]), torch.from_numpy(g["A_values"]), (N, N)).to_dense()
+    np.testing.assert_allclose(A.numpy(), A_ref.numpy(), rtol=3e-7, atol=0)   # get_A_tilda, lightGCN.py:145-178
+    fu, fi, iu, ii = lg.propagate_through_layers()                              # lightGCN.py:180-194
+    np.testing.assert_allclose(fu.cpu().numpy(), g["final_user"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(fi.cpu().numpy(), g["final_item"], rtol=0, atol=2e-6)
+    assert torch.equal(torch.cat([iu, ii]).cpu(), torch.from_numpy(g["E0"]))
+    # the value-stream form of the same kernel (explicit Â entries) agrees too
+    from gdmcf_b200 import kernels as Kk
+    out = Kk.lightgcn_propagate(lg.plan, col, val, lg.E0.weight.detach(), K)
+    np.testing.assert_allclose(out.cpu().numpy(), np.concatenate([g["final_user"], g["final_item"]]), rtol=0, atol=2e-6)
+    # differentiable like the reference's torch.sparse.mm chain (its BPR loop trains E0 through forward())
+    lg.zero_grad()
+    users, pos, neg = torch.tensor([0, 3, 7]).cuda(), torch.tensor([1, 2, 5]).cuda(), torch.tensor([4, 0, 9]).cuda()
+    u, p, n, u0, p0, n0 = lg(users, pos, neg)
+    loss = torch.nn.functional.softplus((u * n).sum(1) - (u * p).sum(1)).mean() + 1e-3 * (u0.norm() ** 2 + p0.norm() ** 2 + n0.norm() ** 2)
+    loss.backward()
+    E = torch.from_numpy(g["E0"]).cuda().requires_grad_(True)
+    Ad = A_ref.cuda()
+    cur, acc = E, E
+    for _ in range(K):
+        cur = Ad @ cur
+        acc = acc + cur
+    mean = acc / (K + 1)
+    fu_r, fi_r = mean[:nu], mean[nu:]
+    iu_r, ii_r = E[:nu], E[nu:]
+    loss_r = torch.nn.functional.softplus((fu_r[users] * fi_r[neg]).sum(1) - (fu_r[users] * fi_r[pos]).sum(1)).mean() + \
+        1e-3 * (iu_r[users].norm() ** 2 + ii_r[pos].norm() ** 2 + ii_r[neg].norm() ** 2)
+    loss_r.backward()
+    assert abs(loss.item() - loss_r.item()) < 1e-6
+    assert ((lg.E0.weight.grad - E.grad).norm() / E.grad.norm()).item() < 1e-5

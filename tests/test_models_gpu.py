@@ -3,7 +3,7 @@
 
 Tolerances (normwise relative error ||got - ref|| / ||ref||, stated per north_star):
   fp32 mode (3-segment bf16 split, tensor-core fp32 accumulation): 5e-5 on scores, 2e-4 on gradients
-  bf16 mode: 1e-2 on scores after the 5-step reverse loop, 2e-2 on gradients
+  bf16 mode: 5e-3 on scores after the 5-step reverse loop (measured 3.7e-3), 3e-2 on gradients
 Top-K indices must be identical wherever the oracle's score gap to the K-th item exceeds the tolerance; metrics
 (4-dp rounded) must then be equal."""
 import os
@@ -19,7 +19,7 @@ B, I, U, D, E, T = 12, 150, 40, 32, 10, 5
 # sumW's gradient is a sum over [B, 3d] of terms that cancel ~50:1 (measured on the golden batch), and in bf16 mode
 # the relu mask of the 12-row golden batch flips for pre-activations within rounding of zero (conv1 gradients).
 GRAD_TOL_SCALE = {"sumW": 60.0, "gcn_model.conv1.bias": 2.0, "gcn_model.conv1.lin.weight": 2.0}
-TOL = {"fp32": dict(score=5e-5, grad=2e-4, loss=1e-4), "bf16": dict(score=1e-2, grad=3e-2, loss=2e-2)}
+TOL = {"fp32": dict(score=5e-5, grad=2e-4, loss=1e-4), "bf16": dict(score=5e-3, grad=3e-2, loss=2e-2)}
 
 
 @pytest.fixture(scope="module")
@@ -103,6 +103,8 @@ def test_gdmcf_backbone_golden(eng, precision):
     p2 = diff.p_sample(m, x0, 2, index=index, inject=dict(noise=torch.from_numpy(g["p_sample_s2.noise"]).cuda(),
                                                         u_keep=torch.from_numpy(g["p_sample_s2.u_keep"]).cuda()))
     assert rel(p2, g["p_sample_s2"]) < tol
+    # every p_sample call returns its own tensor (the reference does): later calls must not overwrite earlier results
+    assert rel(p0, g["p_sample_s0"]) < tol and rel(p0c, g["p_sample_s0"]) < tol and p0.data_ptr() != p0c.data_ptr()
     for steps in (10, 12):
         d2 = make_diffusion(eng, steps=steps)
         assert rel(d2.p_sample(m, batch, 0), g[f"p_sample_s0_T{steps}"]) < tol * (steps / 5)
