@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--rank_after_update", action="store_true",
                     help="step order train -> AdamW -> rank (default: train -> rank -> AdamW, which hides the all-reduces)")
     ap.add_argument("--nccl_sms", type=int, default=32, help="SMs the contractions leave to NCCL while all-reduces are in flight (N > 1)")
+    ap.add_argument("--overlap_sms", type=int, default=0,
+                    help="N = 1: SMs that run AdamW of the big matrices on a side stream while denoise+rank runs on the rest (0: serial; measured slower, see engine.py)")
     ap.add_argument("--replicated_optimizer", action="store_true",
                     help="N > 1: all-reduce + full AdamW on every rank instead of reduce-scatter + sharded AdamW + all-gather")
     ap.add_argument("--kernel_times", action="store_true", help="print a per-kernel device-time table (torch.profiler) to stderr")
@@ -71,7 +73,7 @@ def config_of(args, n_gpus):
             "parallelism": f"dp{n_gpus} (user batches; grad all-reduce)", "l2": "inputs larger than L2 (weights+state ~4 GB)",
             "precision": args.precision,
             "step_order": "train(fwd+bwd) -> AdamW -> denoise+rank" if args.rank_after_update else "train(fwd+bwd) -> denoise+rank -> AdamW",
-            "nccl_sms": args.nccl_sms,
+            "nccl_sms": args.nccl_sms, "overlap_sms": args.overlap_sms if n_gpus == 1 else 0,
             "optimizer": "replicated" if (args.replicated_optimizer or n_gpus == 1) else "row-sharded (reduce-scatter / all-gather)"}
 
 
@@ -304,7 +306,8 @@ def run_engine(args):
     eng = StepEngine(model, diffusion, opt, dist, batch_size=B, n_item=n_item, topk=k, topN=topN,
                      cap_train_nnz=window_nnz(train_sp), cap_gt_nnz=window_nnz(test_sp), reweight=True,
                      graphs=not args.no_graphs, rank_before_update=not args.rank_after_update, nccl_sms=args.nccl_sms,
-                     shard_optimizer=not args.replicated_optimizer, train=args.mode == "train+rank")
+                     shard_optimizer=not args.replicated_optimizer, train=args.mode == "train+rank",
+                     overlap_sms=args.overlap_sms)
     eng.load_resident(train_dev, test_dev, *users_of(0))
     eng.capture(warmup=3)
 

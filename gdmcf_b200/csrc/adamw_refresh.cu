@@ -253,6 +253,88 @@ adamw_flat_hi_kernel(const Args a) {
   }
 }
 
+// AdamW only (no derived tensors) by a FIXED set of SMs. Launched as `ctas` CTAs (clusters of 2 = whole TPCs) of 1024
+// threads that each reserve more than half of an SM's shared memory: exactly one CTA per SM, and no CTA of a tcgen05
+// contraction (227 KB) can share that SM. The optimizer pass is HBM-bound and the denoise + rank phase is tensor-bound;
+// with the contractions limited to the other SMs (gdmcf_gemm_set_sm_limit) the two run side by side on two streams
+// instead of back to back. Same element arithmetic as every other AdamW kernel here (adamw_update).
+constexpr int PART_THREADS = 1024;
+constexpr int PART_SMEM = 120 * 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PART_THREADS, 1)
+adamw_partition_kernel(const Args a) {
+  const AdamwCoef kc = adamw_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.bc1, a.bc2_sqrt, a.grad_scale, a.step_dev);
+  const long long total = (long long)a.rows * a.cols;
+  const long long groups = (total + 3) >> 2;
+  const bool g_flat = a.ld_g == a.cols && (((uintptr_t)a.g & 15) == 0);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < groups; i0 += 2 * stride) {
+    // two independent groups per trip: 8 x 16 B loads in flight per thread (128 KB per SM)
+    float pv[2][4], mv[2][4], vv[2][4], gv[2][4];
+    int rr[2][4];
+    bool live[2], full[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      live[u] = i < groups;
+      const long long idx = i << 2;
+      full[u] = live[u] && idx + 4 <= total;
+      if (full[u]) {
+        const float4 P = *reinterpret_cast<const float4*>(a.p + idx), M = *reinterpret_cast<const float4*>(a.m + idx);
+        const float4 V = *reinterpret_cast<const float4*>(a.v + idx);
+        pv[u][0] = P.x; pv[u][1] = P.y; pv[u][2] = P.z; pv[u][3] = P.w;
+        mv[u][0] = M.x; mv[u][1] = M.y; mv[u][2] = M.z; mv[u][3] = M.w;
+        vv[u][0] = V.x; vv[u][1] = V.y; vv[u][2] = V.z; vv[u][3] = V.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = live[u] && idx + j < total;
+          pv[u][j] = ok ? a.p[idx + j] : 0.f; mv[u][j] = ok ? a.m[idx + j] : 0.f; vv[u][j] = ok ? a.v[idx + j] : 0.f;
+        }
+      }
+      if (live[u]) {
+        int r = (int)(idx / a.cols);
+        int c = (int)(idx - (long long)r * a.cols);
+        if (g_flat && full[u]) {
+          const float4 G = *reinterpret_cast<const float4*>(a.g + idx);
+          gv[u][0] = G.x; gv[u][1] = G.y; gv[u][2] = G.z; gv[u][3] = G.w;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { rr[u][j] = r; if (++c == a.cols) { c = 0; ++r; } }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gv[u][j] = (idx + j < total) ? a.g[(long long)r * a.ld_g + c] : 0.f;
+            rr[u][j] = r;
+            if (++c == a.cols) { c = 0; ++r; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!live[u]) continue;
+      const long long idx = (i0 + u * stride) << 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (idx + j < total) {
+          float gr = gv[u][j];
+          if (a.row_coef) gr = fmaf(a.row_coef[rr[u][j]], pv[u][j], gr);
+          adamw_update(kc, pv[u][j], gr, mv[u][j], vv[u][j]);
+        }
+      }
+      if (full[u]) {
+        *reinterpret_cast<float4*>(a.p + idx) = make_float4(pv[u][0], pv[u][1], pv[u][2], pv[u][3]);
+        *reinterpret_cast<float4*>(a.m + idx) = make_float4(mv[u][0], mv[u][1], mv[u][2], mv[u][3]);
+        *reinterpret_cast<float4*>(a.v + idx) = make_float4(vv[u][0], vv[u][1], vv[u][2], vv[u][3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (idx + j < total) { a.p[idx + j] = pv[u][j]; a.m[idx + j] = mv[u][j]; a.v[idx + j] = vv[u][j]; }
+      }
+    }
+  }
+}
+
 // out[r] = finish(sum_s rowpart[s, r]) in split order; mode 0: 1/sqrt (row inverse norm), mode 1: plain sum (base).
 __global__ void adamw_row_finish_kernel(const float* __restrict__ rowpart, int splits, int rows, int mode, float* __restrict__ out) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
@@ -340,4 +422,34 @@ extern "C" int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float
     rc = cuda_check_launch("adamw_row_finish_kernel");
   }
   return rc;
+}
+
+extern "C" int gdmcf_adamw_partitioned(float* p, const float* g, int64_t ld_g, float* m, float* v, int rows, int cols, float lr,
+                                       float beta1, float beta2, float eps, float weight_decay, int step,
+                                       const int64_t* step_dev, float grad_scale, const float* row_coef, int n_ctas,
+                                       gdmcf_stream_t stream) {
+  if (!p || !g || !m || !v || rows <= 0 || cols <= 0 || ld_g < cols || (step < 1 && !step_dev) || n_ctas < 2 ||
+      ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) != 0)) {
+    set_error("adamw_partitioned: bad arguments (16 B aligned p/m/v, n_ctas >= 2)");
+    return GDMCF_EBADARG;
+  }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(adamw_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_SMEM);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(adamw_partition)");
+    attr_set = true;
+  }
+  Args a{};
+  a.p = p; a.g = g; a.m = m; a.v = v; a.rows = rows; a.cols = cols; a.ld_g = ld_g;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bc1 = (float)(1.0 - pow((double)beta1, (double)std::max(step, 1)));
+  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)std::max(step, 1)));
+  a.grad_scale = grad_scale; a.step_dev = reinterpret_cast<const long long*>(step_dev);
+  a.row_coef = row_coef;
+  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
+  const int ctas = std::max(2, std::min(n_ctas, sms) & ~1);
+  adamw_partition_kernel<<<ctas, PART_THREADS, PART_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return cuda_check_launch("adamw_partition_kernel");
 }

@@ -34,7 +34,7 @@ class StepEngine:
     def __init__(self, model, diffusion, optimizer, dist, *, batch_size: int, n_item: int, topk: int, topN: Sequence[int],
                  cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
                  rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
-                 shard_min_bytes: int = 64 << 20, train: bool = True):
+                 shard_min_bytes: int = 64 << 20, train: bool = True, overlap_sms: int = 0):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
@@ -46,6 +46,12 @@ class StepEngine:
         # before the ranking (False: the batch is ranked with the weights that already include its own gradient)
         self.rank_before_update = rank_before_update
         self.nccl_sms = nccl_sms  # SMs the contractions leave free while all-reduces are in flight (world_size > 1)
+        # world_size == 1: SMs (whole TPCs) that run the AdamW pass of the big matrices on a side stream WHILE the
+        # tensor-bound denoise + rank phase runs on the others (0: optimizer after the ranking, on the same stream).
+        # Measured on B200 (profiles/r2_overlap_sweep.txt): a loss at every split — the exact-rounding AdamW arithmetic
+        # needs ~80 instructions per element, so confined to 40-72 SMs the pass is issue-bound at ~43 GB/s per SM
+        # (6.07 / 4.95 / 4.30 ms per step at 40 / 56 / 72 SMs against 4.17 serial). Off by default.
+        self.overlap_sms = overlap_sms & ~1
         dev = torch.device(device) if device is not None else next(model.parameters()).device
         self.dev = dev
         i32 = dict(dtype=torch.int32, device=dev)
@@ -199,6 +205,40 @@ class StepEngine:
             return mine
 
         side_opt = bool(self._shards) and self.rank_before_update
+        if G == 1 and self.rank_before_update and self.overlap_sms > 0:
+            # One rank: fork inside the step (one CUDA graph with two branches). Side stream: AdamW of the big matrices on
+            # `overlap_sms` SMs, fp32 masters / moments only. Main stream: denoise + rank on the remaining SMs — it reads
+            # only the bf16 operands and tables derived from the PRE-update weights, plus the user rows staged before the
+            # fork — then AdamW of the small tensors. After the join one pass re-derives the operands from the new weights.
+            opt.begin_step()
+            n_sms = _lib.load().gdmcf_num_sms()
+            specs = model.refresh_specs()
+            every = [p for plist in groups for p in plist]
+            side_params = [p for p in every if p.dim() == 2 and p.numel() >= (1 << 20)]
+            side_ids = {id(p) for p in side_params}
+            if hasattr(model, "stage_user_rows"):
+                model.stage_user_rows(self.B, self.users)
+            main, side = torch.cuda.current_stream(self.dev), self._opt_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                opt.update(side_params, row_coef=row_coef, partition_ctas=self.overlap_sms)
+            K.gemm_set_sm_limit(max(2, n_sms - self.overlap_sms))
+            try:
+                idx, sums = rank_and_metrics()
+            finally:
+                K.gemm_set_sm_limit(0)
+            opt.update([p for p in every if id(p) not in side_ids], row_coef=row_coef)
+            main.wait_stream(side)
+            for p_ in side_params:
+                spec = specs.get(id(p_))
+                if spec is not None:
+                    K.refresh_derived(p_.data, **spec[0])
+                    refreshed.append((p_, spec[1]))
+            opt.end_step()
+            for p_, names_ in refreshed:
+                model.adopt_refreshed(p_, names_)
+            self._result = (loss, idx, sums)
+            return
         if side_opt:
             # Sharded optimizer on a side stream: as each reduce-scatter lands, this rank's row block is updated and the
             # all-gather of the weights starts, all concurrently with the denoise + rank phase on the main stream (which

@@ -412,6 +412,24 @@ def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.9
                                    ptr(step_dev), grad_scale, stream()), "adamw_fused")
 
 
+def adamw_partitioned(p, g, m, v, *, n_ctas: int, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                      weight_decay: float = 0.0, step: int = 1, step_dev=None, grad_scale: float = 1.0, row_coef=None) -> None:
+    """AdamW (no derived tensors) confined to n_ctas SMs (gdmcf_adamw_partitioned): runs next to SM-limited contractions
+    on another stream. p/m/v contiguous; g may be a [rows, cols] view with a padded leading dimension."""
+    require_cuda(p, g, m, v, row_coef)
+    assert p.is_contiguous() and m.is_contiguous() and v.is_contiguous() and g.shape == p.shape
+    if p.dim() == 2:
+        rows, cols = p.shape
+        assert g.stride(1) == 1
+        ld_g = g.stride(0)
+    else:
+        rows, cols, ld_g = 1, p.numel(), p.numel()
+        assert g.is_contiguous()
+    check(load().gdmcf_adamw_partitioned(ptr(p), ptr(g), ld_g, ptr(m), ptr(v), rows, cols, lr, beta1, beta2, eps, weight_decay,
+                                         step, ptr(step_dev), grad_scale, ptr(row_coef), int(n_ctas), stream()),
+          "adamw_partitioned")
+
+
 def adamw_refresh(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
                   weight_decay: float = 0.0, step: int = 1, step_dev=None, grad_scale: float = 1.0, cols_used: int = 0,
                   op: Optional[Bf16Mat] = None, op_t: Optional[Bf16Mat] = None, inv_norm=None, delta=None, base=None,

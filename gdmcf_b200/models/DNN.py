@@ -464,6 +464,15 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
                  out_f32=out_f32, out_bf16=out_op.hi if out_op is not None else None,
                  out_bf16_lo=out_op.lo if out_op is not None else None, **post)
 
+    @torch.no_grad()
+    def stage_user_rows(self, B: int, index) -> None:
+        """Gather embedding_user[index] into the user-tower buffer ahead of the next reverse_loop call (which then skips
+        its own gather). engine.StepEngine uses it to update the user table on another stream while the loop runs."""
+        bufs = self._hc_buffers(B, index.device)
+        f32, hi, lo = self._seg(bufs, 2)
+        K.gather_rows(self.embedding_user.weight.detach(), _as_i32(index), B, self.hidden, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+        self._user_rows_staged = True
+
     # -- reference call surface ----------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, timesteps, x_U, index=None, graph=None, RCloss=False):
@@ -511,8 +520,11 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         else:
             base, delta = self._onehot_tables()
             K.encode_onehot_gather(csr[0], csr[1], users, B, base, delta, d, bufs["S"])
-        f32, hi, lo = self._seg(bufs, 2)
-        K.gather_rows(self.embedding_user.weight.detach(), index, B, d, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+        if getattr(self, "_user_rows_staged", False):
+            self._user_rows_staged = False  # gathered ahead of the loop by stage_user_rows()
+        else:
+            f32, hi, lo = self._seg(bufs, 2)
+            K.gather_rows(self.embedding_user.weight.detach(), index, B, d, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
         x_op = x0_op
         if x_op is None:
             x_op = bufs["xop"]

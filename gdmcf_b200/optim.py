@@ -43,9 +43,11 @@ class FusedAdamW(torch.optim.Optimizer):
             K.counter_add(self._step_dev, 1)
 
     @torch.no_grad()
-    def update(self, params=None, grad_scale: float = 1.0, row_coef=None) -> None:
+    def update(self, params=None, grad_scale: float = 1.0, row_coef=None, partition_ctas: int = 0) -> None:
         """AdamW on `params` (default: every parameter with a gradient). row_coef: {id(param): coef [rows]} — the
-        parameter's effective gradient is grad + coef[r] * param[r, :] (deferred norm term of the cosine scorer)."""
+        parameter's effective gradient is grad + coef[r] * param[r, :] (deferred norm term of the cosine scorer).
+        partition_ctas > 0: update only (derived tensors are NOT refreshed — the caller runs kernels.refresh_derived
+        afterwards) with gdmcf_adamw_partitioned on that many SMs, so that the pass can overlap SM-limited contractions."""
         row_coef = row_coef or {}
         only = None if params is None else {id(p) for p in params}
         # weights whose derived tensors (bf16 operands, transposes, norms, one-hot tables) are refreshed by the same pass
@@ -69,7 +71,10 @@ class FusedAdamW(torch.optim.Optimizer):
                              step=st["step"], step_dev=self._step_dev if self._capturable else None, grad_scale=grad_scale)
                 spec = specs.get(id(p))
                 rc = row_coef.get(id(p))
-                if spec is not None and p.dim() == 2 and p.is_contiguous() and p.grad.stride(1) == 1:
+                if partition_ctas > 0:
+                    g = p.grad if (p.dim() == 2 and p.grad.stride(1) == 1) or p.grad.is_contiguous() else p.grad.contiguous()
+                    K.adamw_partitioned(p.data, g, st["exp_avg"], st["exp_avg_sq"], n_ctas=partition_ctas, **hyper, row_coef=rc)
+                elif spec is not None and p.dim() == 2 and p.is_contiguous() and p.grad.stride(1) == 1:
                     K.adamw_refresh(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], **hyper, **spec[0], row_coef=rc)
                     self._adopted.append((spec[2], p, spec[1]))
                 else:

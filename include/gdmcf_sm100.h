@@ -297,8 +297,15 @@ int gdmcf_adamw_refresh_splits(int rows, int cols);
 int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float* m, float* v, int rows, int cols, float lr,
                         float beta1, float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
                         float grad_scale, const gdmcf_refresh* out, gdmcf_stream_t stream);
+/* AdamW only (no derived tensors) confined to `n_ctas` SMs: n_ctas CTAs (clusters of 2, one CTA per SM, each reserving
+ * more than half of the SM's shared memory so that no tcgen05 contraction CTA can share it). Lets the HBM-bound optimizer
+ * pass (main.py:351) run on a side stream next to the tensor-bound denoise + rank phase whose contractions were limited to
+ * the other SMs with gdmcf_gemm_set_sm_limit. Same arithmetic and row_coef meaning as gdmcf_adamw_refresh. */
+int gdmcf_adamw_partitioned(float* p, const float* g, int64_t ld_g, float* m, float* v, int rows, int cols, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
+                            float grad_scale, const float* row_coef, int n_ctas, gdmcf_stream_t stream);
 /* counter_dev[0] += inc on the stream: the device-resident step / RNG-epoch counters that keep captured CUDA graphs
- * advancing (Philox counter = offset + (epoch << 44); AdamW bias corrections from *step_dev when non-NULL). */
+ * advancing (Philox counter high word = (epoch << 8) | sub-stream; AdamW bias corrections from *step_dev when non-NULL). */
 int gdmcf_counter_add(uint64_t* counter_dev, uint64_t inc, gdmcf_stream_t stream);
 
 /* Backward of the weighted MSE (models/gaussian_diffusion.py:902,932,951) in one pass over out [rows, cols]:
@@ -336,7 +343,7 @@ int gdmcf_lt_history_update(const int64_t* ts, const double* loss, double* lt_hi
 /* sample_timesteps(method="importance") (models/gaussian_diffusion.py:959-986) on the device, no host sync:
  * uniform draws with pt = 1 until every lt_count[t] == history, then t ~ Categorical(p), p = sqrt(mean(Lt_history^2))
  * normalised and mixed with uniform_prob, pt = p[t] * steps. ts_in != NULL: only pt for the given timesteps.
- * ts int64 [batch], pt fp64 [batch]; Philox counter = offset + (epoch_dev[0] << 44) + row. */
+ * ts int64 [batch], pt fp64 [batch]; Philox counter = (offset + row, (epoch_dev[0] << 8) | 7). */
 int gdmcf_sample_timesteps(const double* lt_history, const int64_t* lt_count, int steps, int history, int batch,
                            double uniform_prob, uint64_t seed, uint64_t offset, const uint64_t* epoch_dev,
                            const int64_t* ts_in, int64_t* ts_out, double* pt_out, gdmcf_stream_t stream);

@@ -22,7 +22,7 @@ def _setup(seed_model=0, U=700, I=1203, D=64, B=64, T=5, k=20):
     train_sp, test_sp = mk(tr), mk(te)
     train_dev, test_dev = data_utils.DeviceInteractions(train_sp, dev), data_utils.DeviceInteractions(test_sp, dev)
 
-    def make(graphs):
+    def make(graphs, **engine_kw):
         torch.manual_seed(seed_model)
         model = DNNOneHotEmbeddingGCN([n_item, D], [D, n_item], 10, item_num=n_item, user_num=n_user).to(dev)
         diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, T, dev,
@@ -31,7 +31,7 @@ def _setup(seed_model=0, U=700, I=1203, D=64, B=64, T=5, k=20):
         diff.seed = model.seed = 77
         opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0, modules=[model], capturable=True)
         eng = StepEngine(model, diff, opt, dist_utils.Dist(), batch_size=B, n_item=n_item, topk=k, topN=[10, k],
-                         cap_train_nnz=int(train_sp.nnz), cap_gt_nnz=int(test_sp.nnz), graphs=graphs)
+                         cap_train_nnz=int(train_sp.nnz), cap_gt_nnz=int(test_sp.nnz), graphs=graphs, **engine_kw)
         return model, diff, eng
 
     return make, train_dev, test_dev, train_sp, test_sp, B, n_user
@@ -247,3 +247,26 @@ def test_engine_data_parallel_torchrun(world):
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert f"engine_dist_check: world {world}" in res.stdout and "OK" in res.stdout, res.stdout[-2000:]
+
+
+def test_overlapped_optimizer_equals_serial():
+    """world_size 1 with overlap_sms > 0 (AdamW of the big matrices on a side stream, confined to a set of SMs by
+    gdmcf_adamw_partitioned, + one refresh-only pass) must produce the same weights, operands and results as the serial
+    fused update, bit for bit."""
+    make, train_dev, test_dev, _, _, B, n_user = _setup()
+    outs = []
+    for ov in (0, 8):
+        model, diff, eng = make(True, overlap_sms=ov)
+        eng.load_resident(train_dev, test_dev, 0, B)
+        eng.capture(warmup=2)
+        res = []
+        for s in range(1, 4):
+            eng.load_resident(train_dev, test_dev, s * B, (s + 1) * B)
+            loss, idx, sums = eng.step()
+            res.append((loss.clone(), idx.clone(), sums.clone()))
+        torch.cuda.synchronize()
+        outs.append((res, [p.detach().clone() for p in model.parameters()]))
+    for (l0, i0, s0), (l1, i1, s1) in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(l0, l1) and torch.equal(i0, i1) and torch.equal(s0, s1)
+    for p0, p1 in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(p0, p1)
