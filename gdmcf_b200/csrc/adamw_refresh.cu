@@ -49,6 +49,7 @@ GD_DEV uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 template <int VEC, bool UPDATE>
 __global__ void __launch_bounds__(THREADS)
 adamw_refresh_kernel(const Args a) {
+  pdl_entry();
   __shared__ float tile[TR][TC + 1];
   const AdamwCoef kc = adamw_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.bc1, a.bc2_sqrt, a.grad_scale, a.step_dev);
   auto update = [&](float& param, float gr, float& mi, float& vi) { adamw_update(kc, param, gr, mi, vi); };
@@ -200,6 +201,7 @@ adamw_refresh_kernel(const Args a) {
 // (2-byte stores; neighbouring threads fill the sectors). Operand padding columns are never touched (zero since built).
 __global__ void __launch_bounds__(THREADS)
 adamw_flat_hi_kernel(const Args a) {
+  pdl_entry();
   const AdamwCoef kc = adamw_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.bc1, a.bc2_sqrt, a.grad_scale, a.step_dev);
   const long long total = (long long)a.rows * a.cols;
   const long long groups = (total + 3) >> 2;
@@ -263,6 +265,7 @@ constexpr int PART_SMEM = 120 * 1024;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PART_THREADS, 1)
 adamw_partition_kernel(const Args a) {
+  pdl_entry();
   const AdamwCoef kc = adamw_coef(a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.bc1, a.bc2_sqrt, a.grad_scale, a.step_dev);
   const long long total = (long long)a.rows * a.cols;
   const long long groups = (total + 3) >> 2;
@@ -337,6 +340,7 @@ adamw_partition_kernel(const Args a) {
 
 // out[r] = finish(sum_s rowpart[s, r]) in split order; mode 0: 1/sqrt (row inverse norm), mode 1: plain sum (base).
 __global__ void adamw_row_finish_kernel(const float* __restrict__ rowpart, int splits, int rows, int mode, float* __restrict__ out) {
+  pdl_entry();
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int q = 0; q < splits; ++q) s += rowpart[(long long)q * rows + r];
@@ -404,21 +408,21 @@ extern "C" int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float
   if (ctas > 0x7fffffffLL) { set_error("adamw_refresh: too many tiles"); return GDMCF_EBADARG; }
   const bool flat_ok = g && !vec && !a.t_hi && !a.delta && !a.rowpart && ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   if (!g) {
-    if (vec) adamw_refresh_kernel<4, false><<<(int)ctas, THREADS, 0, st>>>(a);
-    else adamw_refresh_kernel<1, false><<<(int)ctas, THREADS, 0, st>>>(a);
+    if (vec) launch_kernel(adamw_refresh_kernel<4, false>, (int)ctas, THREADS, 0, st, a);
+    else launch_kernel(adamw_refresh_kernel<1, false>, (int)ctas, THREADS, 0, st, a);
   } else if (vec) {
-    adamw_refresh_kernel<4, true><<<(int)ctas, THREADS, 0, st>>>(a);
+    launch_kernel(adamw_refresh_kernel<4, true>, (int)ctas, THREADS, 0, st, a);
   } else if (flat_ok) {
     const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
     const long long groups = ((long long)rows * cols + 3) / 4;
-    adamw_flat_hi_kernel<<<(int)std::min<long long>((groups + THREADS - 1) / THREADS, (long long)sms * 8), THREADS, 0, st>>>(a);
+    launch_kernel(adamw_flat_hi_kernel, (int)std::min<long long>((groups + THREADS - 1) / THREADS, (long long)sms * 8), THREADS, 0, st, a);
   } else {
-    adamw_refresh_kernel<1, true><<<(int)ctas, THREADS, 0, st>>>(a);
+    launch_kernel(adamw_refresh_kernel<1, true>, (int)ctas, THREADS, 0, st, a);
   }
   if ((rc = cuda_check_launch("adamw_refresh_kernel"))) return rc;
   if (a.rowpart) {
     float* dst = o.inv_norm ? o.inv_norm : o.base;
-    adamw_row_finish_kernel<<<(rows + 255) / 256, 256, 0, st>>>(a.rowpart, a.col_splits, rows, o.inv_norm ? 0 : 1, dst);
+    launch_kernel(adamw_row_finish_kernel, (rows + 255) / 256, 256, 0, st, a.rowpart, a.col_splits, rows, o.inv_norm ? 0 : 1, dst);
     rc = cuda_check_launch("adamw_row_finish_kernel");
   }
   return rc;
@@ -450,6 +454,6 @@ extern "C" int gdmcf_adamw_partitioned(float* p, const float* g, int64_t ld_g, f
   a.row_coef = row_coef;
   const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
   const int ctas = std::max(2, std::min(n_ctas, sms) & ~1);
-  adamw_partition_kernel<<<ctas, PART_THREADS, PART_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  launch_kernel(adamw_partition_kernel, ctas, PART_THREADS, PART_SMEM, reinterpret_cast<cudaStream_t>(stream), a);
   return cuda_check_launch("adamw_partition_kernel");
 }

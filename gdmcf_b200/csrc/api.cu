@@ -1,4 +1,5 @@
 // Error plumbing and device queries of the C ABI (include/gdmcf_sm100.h).
+#include <cstdlib>
 #include "api_internal.h"
 
 namespace gd {
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t err, const char* what) {
   set_error("%s: %s (%s)", what, cudaGetErrorName(err), cudaGetErrorString(err));
   return GDMCF_ECUDA;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GDMCF_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 static unsigned long long g_launches = 0;

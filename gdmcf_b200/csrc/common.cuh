@@ -18,6 +18,16 @@ GD_DEV uint64_t globaltimer_ns() {
   return t;
 }
 
+// Programmatic dependent launch (see api_internal.h): let the next kernel's CTAs be scheduled now, then wait until
+// every kernel this one depends on has completed and its writes are visible. Both are no-ops for a kernel that was
+// launched without the attribute / has no programmatic dependents.
+GD_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+GD_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+GD_DEV void pdl_entry() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 GD_DEV bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

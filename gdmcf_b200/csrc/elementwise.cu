@@ -28,6 +28,7 @@ GD_DEV void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ hi,
                                  __nv_bfloat16* __restrict__ lo, long long ld_out, int rows, int cols) {
+  pdl_entry();
   // one thread per 8 output columns: eight coalesced scalar loads (the fp32 rows of nn.Linear weights are not
   // 16 B aligned: ld_in = n_item + emb_size), one 16 B store per output
   const int groups = (int)(ld_out >> 3);  // ld_out % 8 == 0 (checked on the host)
@@ -56,6 +57,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, long long ld_in, 
 // out[c, r] = in[r, c]; 32x32 tiles through shared memory, both sides coalesced.
 __global__ void cast_bf16_transpose_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ hi,
                                            __nv_bfloat16* __restrict__ lo, long long ld_out, int rows, int cols) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int tiles_c = (cols + 31) / 32;
   const int tiles_r = (int)((ld_out + 31) / 32);  // output columns (= input rows) incl. padding
@@ -87,6 +89,7 @@ __global__ void cast_bf16_transpose_kernel(const float* __restrict__ in, long lo
 __global__ void densify_rows_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                                     const int* __restrict__ users, int n_rows, int n_items, float* __restrict__ out_f32,
                                     long long ld_f32, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16) {
+  pdl_entry();
   for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
     if (out_f32) {
       float4* p = reinterpret_cast<float4*>(out_f32 + (long long)r * ld_f32);
@@ -120,6 +123,7 @@ __global__ void qsample_dropout_kernel(const float* __restrict__ x0, long long l
                                        float* __restrict__ xt_f32, long long ld_xt,
                                        __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, long long ld_a,
                                        int rows, int cols) {
+  pdl_entry();
   // Philox counter: low word = offset0 (call site << 40) + element group, high word = (epoch << 8) | sub-stream.
   // `epoch` is a device-resident step counter, so a captured CUDA graph draws fresh numbers on every replay; it has
   // 56 bits of its own and cannot run into the call-site or element fields however long the run is.
@@ -187,6 +191,7 @@ __global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x
                                     const float* __restrict__ u_drop, uint64_t seed, uint64_t offset0,
                                     const uint64_t* __restrict__ epoch, __nv_bfloat16* __restrict__ out, long long ld_out,
                                     int rows, int cols) {
+  pdl_entry();
   const uint64_t offset = offset0;
   const uint64_t ep = epoch ? (epoch[0] << 8) : 0ull;  // high counter word = (epoch << 8) | sub-stream
   const int groups = (int)(ld_out / 8);  // 8 outputs = 4 items per thread
@@ -240,6 +245,7 @@ __global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x
 // delta[i,k] = W2[k,2i+1] - W2[k,2i] via 32x32 transposing tiles; base accumulated separately.
 __global__ void onehot_delta_kernel(const float* __restrict__ w2, long long ld_w, int d, int n_items,
                                     float* __restrict__ delta, long long ld_delta) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int tiles_i = (n_items + 31) / 32, tiles_k = (d + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -264,6 +270,7 @@ __global__ void onehot_delta_kernel(const float* __restrict__ w2, long long ld_w
 }
 // base[k] = sum_i W2[k, 2i]  (fp64 accumulation, one CTA per k)
 __global__ void onehot_base_kernel(const float* __restrict__ w2, long long ld_w, int d, int n_items, float* __restrict__ base) {
+  pdl_entry();
   __shared__ double red[TPB / 32];
   for (int k = blockIdx.x; k < d; k += gridDim.x) {
     double s = 0.0;
@@ -285,6 +292,7 @@ __global__ void encode_onehot_gather_kernel(const int* __restrict__ rowptr, cons
                                             const int* __restrict__ users, int n_rows, const float* __restrict__ base,
                                             const float* __restrict__ delta, long long ld_delta, int d,
                                             float* __restrict__ out, long long ld_out) {
+  pdl_entry();
   // the row's item ids are staged in shared memory so that the delta-row gathers (coalesced over k) are independent
   // loads, 8 in flight per thread, instead of a chain id -> gather -> id -> gather
   constexpr int SLAB = 512;
@@ -344,6 +352,7 @@ __global__ void mix_rownorm_kernel(const float* __restrict__ hc, long long ld_hc
                                    long long ld_g, const float* __restrict__ sumw, float* __restrict__ out_f32,
                                    long long ld_of, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
                                    long long ld_ob, float* __restrict__ inv_norm, int rows, int cols) {
+  pdl_entry();
   __shared__ float red[TPB / 32];
   const float w = (g && sumw) ? sumw[0] : 1.0f;
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
@@ -370,6 +379,7 @@ __global__ void mix_rownorm_kernel(const float* __restrict__ hc, long long ld_hc
 }
 
 __global__ void row_inv_norm_kernel(const float* __restrict__ x, long long ld, float* __restrict__ inv_norm, int rows, int cols) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -389,6 +399,7 @@ __global__ void row_inv_norm_kernel(const float* __restrict__ x, long long ld, f
 __global__ void __launch_bounds__(512)
 mse_rows_kernel(const float* __restrict__ out, long long ld_out, const float* __restrict__ x0, long long ld_x0, int rows,
                 int cols, float* __restrict__ mse) {
+  pdl_entry();
   __shared__ float red[16];
   const bool vec = (((ld_out | ld_x0) & 3) == 0) && ((((uintptr_t)out | (uintptr_t)x0) & 15) == 0);
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
@@ -424,6 +435,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                              float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
                              float weight_decay, float bc1, float bc2_sqrt, float grad_scale,
                              const long long* __restrict__ step_dev) {
+  pdl_entry();
   const AdamwCoef kc = adamw_coef(lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, step_dev);
   auto update = [&](float& param, float gr, float& mi, float& vi) { adamw_update(kc, param, gr, mi, vi); };
   // 128-bit streams (all four tensors are 16 B aligned: checked on the host), scalar tail
@@ -449,6 +461,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 }
 
 __global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) {
+  pdl_entry();
   if (blockIdx.x == 0 && threadIdx.x == 0) ctr[0] += inc;
 }
 
@@ -471,7 +484,7 @@ extern "C" int gdmcf_cast_bf16(const float* in, int64_t ld_in, void* out_hi, voi
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  cast_bf16_kernel<<<grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st>>>(in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
+  launch_kernel(cast_bf16_kernel, grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st, in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
   return cuda_check_launch("cast_bf16_kernel");
 }
 
@@ -480,7 +493,7 @@ extern "C" int gdmcf_cast_bf16_transpose(const float* in, int64_t ld_in, void* o
   if (!in || !out_hi || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < rows) { set_error("cast_bf16_transpose: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
   const long long ntiles = (long long)((cols + 31) / 32) * ((ld_out + 31) / 32);
-  cast_bf16_transpose_kernel<<<grid_1d(ntiles, 1), TPB, 0, st>>>(in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
+  launch_kernel(cast_bf16_transpose_kernel, grid_1d(ntiles, 1), TPB, 0, st, in, ld_in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ld_out, rows, cols);
   return cuda_check_launch("cast_bf16_transpose_kernel");
 }
 
@@ -494,7 +507,7 @@ extern "C" int gdmcf_densify_rows(const int32_t* rowptr, const int32_t* col, con
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  densify_rows_kernel<<<grid_1d(n_rows, 1), TPB, 0, st>>>(rowptr, col, users, n_rows, n_items, out_f32, ld_f32, (__nv_bfloat16*)out_bf16, ld_bf16);
+  launch_kernel(densify_rows_kernel, grid_1d(n_rows, 1), TPB, 0, st, rowptr, col, users, n_rows, n_items, out_f32, ld_f32, (__nv_bfloat16*)out_bf16, ld_bf16);
   return cuda_check_launch("densify_rows_kernel");
 }
 
@@ -509,7 +522,7 @@ extern "C" int gdmcf_qsample_dropout(const float* x0, int64_t ld_x0, const int32
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  qsample_dropout_kernel<<<grid_1d((long long)rows * (ld_a / 4)), TPB, 0, st>>>(
+  launch_kernel(qsample_dropout_kernel, grid_1d((long long)rows * (ld_a / 4)), TPB, 0, st, 
       x0, ld_x0, row_t, t_const, sqrt_ab, sqrt_1mab, noise, keep, dropout_p, seed, offset, epoch_dev, xt_f32, ld_xt,
       (__nv_bfloat16*)a_bf16, (__nv_bfloat16*)a_lo, ld_a, rows, cols);
   return cuda_check_launch("qsample_dropout_kernel");
@@ -525,7 +538,7 @@ extern "C" int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t*
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  onehot_noise_kernel<<<grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st>>>(
+  launch_kernel(onehot_noise_kernel, grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st, 
       x0, ld_x0, ts, discrete, dropout_p, u_keep, u_drop, seed, offset, epoch_dev, (__nv_bfloat16*)out_bf16, ld_out, rows, cols);
   return cuda_check_launch("onehot_noise_kernel");
 }
@@ -538,9 +551,9 @@ extern "C" int gdmcf_onehot_tables(const float* w2, int64_t ld_w, int d, int n_i
   }
   GD_PRE();
   const long long ntiles = (long long)((n_items + 31) / 32) * ((d + 31) / 32);
-  onehot_delta_kernel<<<grid_1d(ntiles, 1), TPB, 0, st>>>(w2, ld_w, d, n_items, delta, ld_delta);
+  launch_kernel(onehot_delta_kernel, grid_1d(ntiles, 1), TPB, 0, st, w2, ld_w, d, n_items, delta, ld_delta);
   if ((rc = cuda_check_launch("onehot_delta_kernel"))) return rc;
-  onehot_base_kernel<<<grid_1d(d, 1), TPB, 0, st>>>(w2, ld_w, d, n_items, base);
+  launch_kernel(onehot_base_kernel, grid_1d(d, 1), TPB, 0, st, w2, ld_w, d, n_items, base);
   return cuda_check_launch("onehot_base_kernel");
 }
 
@@ -552,7 +565,7 @@ extern "C" int gdmcf_encode_onehot_gather(const int32_t* rowptr, const int32_t* 
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  encode_onehot_gather_kernel<<<grid_1d(n_rows, 1), TPB, 0, st>>>(rowptr, col, users, n_rows, base, delta, ld_delta, d, out, ld_out);
+  launch_kernel(encode_onehot_gather_kernel, grid_1d(n_rows, 1), TPB, 0, st, rowptr, col, users, n_rows, base, delta, ld_delta, d, out, ld_out);
   return cuda_check_launch("encode_onehot_gather_kernel");
 }
 
@@ -566,7 +579,7 @@ extern "C" int gdmcf_mix_rownorm(const float* hc, int64_t ld_hc, const float* g,
   }
   GD_PRE();
   if (!out_bf16) ld_ob = cols;
-  mix_rownorm_kernel<<<grid_1d(rows, 1), TPB, 0, st>>>(hc, ld_hc, g, ld_g, sumw, out_f32, ld_of, (__nv_bfloat16*)out_bf16,
+  launch_kernel(mix_rownorm_kernel, grid_1d(rows, 1), TPB, 0, st, hc, ld_hc, g, ld_g, sumw, out_f32, ld_of, (__nv_bfloat16*)out_bf16,
                                                        (__nv_bfloat16*)out_lo, ld_ob, inv_norm, rows, cols);
   return cuda_check_launch("mix_rownorm_kernel");
 }
@@ -574,7 +587,7 @@ extern "C" int gdmcf_mix_rownorm(const float* hc, int64_t ld_hc, const float* g,
 extern "C" int gdmcf_row_inv_norm(const float* x, int64_t ld, float* inv_norm, int rows, int cols, gdmcf_stream_t stream) {
   if (!x || !inv_norm || rows <= 0 || cols <= 0 || ld < cols) { set_error("row_inv_norm: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
-  row_inv_norm_kernel<<<grid_1d((long long)rows * 32), TPB, 0, st>>>(x, ld, inv_norm, rows, cols);
+  launch_kernel(row_inv_norm_kernel, grid_1d((long long)rows * 32), TPB, 0, st, x, ld, inv_norm, rows, cols);
   return cuda_check_launch("row_inv_norm_kernel");
 }
 
@@ -582,7 +595,7 @@ extern "C" int gdmcf_mse_rows(const float* out, int64_t ld_out, const float* x0,
                               float* mse, gdmcf_stream_t stream) {
   if (!out || !x0 || !mse || rows <= 0 || cols <= 0 || ld_out < cols || ld_x0 < cols) { set_error("mse_rows: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
-  mse_rows_kernel<<<grid_1d(rows, 1), 512, 0, st>>>(out, ld_out, x0, ld_x0, rows, cols, mse);
+  launch_kernel(mse_rows_kernel, grid_1d(rows, 1), 512, 0, st, out, ld_out, x0, ld_x0, rows, cols, mse);
   return cuda_check_launch("mse_rows_kernel");
 }
 
@@ -597,13 +610,13 @@ extern "C" int gdmcf_adamw_fused(float* p, const float* g, float* m, float* v, i
   GD_PRE();
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adamw_kernel<<<grid_1d(n), TPB, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, reinterpret_cast<const long long*>(step_dev));
+  launch_kernel(adamw_kernel, grid_1d(n), TPB, 0, st, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, reinterpret_cast<const long long*>(step_dev));
   return cuda_check_launch("adamw_kernel");
 }
 
 extern "C" int gdmcf_counter_add(uint64_t* counter_dev, uint64_t inc, gdmcf_stream_t stream) {
   if (!counter_dev) { set_error("counter_add: null pointer"); return GDMCF_EBADARG; }
   GD_PRE();
-  counter_add_kernel<<<1, 32, 0, st>>>(reinterpret_cast<unsigned long long*>(counter_dev), inc);
+  launch_kernel(counter_add_kernel, 1, 32, 0, st, reinterpret_cast<unsigned long long*>(counter_dev), inc);
   return cuda_check_launch("counter_add_kernel");
 }

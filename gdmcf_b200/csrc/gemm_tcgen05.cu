@@ -383,6 +383,7 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, const gdmcf_epilogue epi) {
   using C = Cfg<BN>;
+  pdl_launch_dependents();  // the next kernel may be scheduled; it waits for this grid's completion before touching data
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need 1024 B alignment
   uint8_t* tiles = smem;
@@ -421,6 +422,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptors are set up: everything above overlapped the previous kernel's tail; operands,
+  // epilogue vectors and outputs are only touched once the kernels this one depends on have completed
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -562,6 +566,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, const Shape shape, const gdmcf_epilogue epi) {
   using C = Cfg2;
   constexpr int BN = C::BN;
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* tiles = smem;
@@ -604,6 +609,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, const Shape shape
   cluster_sync_all();  // both CTAs' barriers and TMEM exist before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, TMEM and descriptors are set up: everything above overlapped the previous kernel's tail; operands,
+  // epilogue vectors and outputs are only touched once the kernels this one depends on have completed
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
@@ -702,6 +710,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ TmaMaps maps, const Shape shape
 
 // Sum split-K slabs in fixed order and apply the epilogue. One thread per 8 columns.
 __global__ void splitk_reduce_kernel(const Shape shape, const gdmcf_epilogue epi) {
+  pdl_entry();
   const int groups = (shape.n + 7) / 8;
   const long long total = (long long)shape.m * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -771,7 +780,7 @@ static int launch(const TmaMaps& maps, const Shape& shape, const gdmcf_epilogue&
     if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(gemm)");
     attr_set = true;
   }
-  gemm_bf16_tn_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps, shape, epi);
+  launch_kernel(gemm_bf16_tn_kernel<BN>, grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st, maps, shape, epi);
   return cuda_check_launch("gemm_bf16_tn_kernel");
 }
 
@@ -782,7 +791,7 @@ static int launch_2cta(const TmaMaps& maps, const Shape& shape, const gdmcf_epil
     if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(gemm 2cta)");
     attr_set = true;
   }
-  gemm_bf16_tn_2cta_kernel<<<2 * clusters, NUM_THREADS, Cfg2::SMEM_BYTES, st>>>(maps, shape, epi);
+  launch_kernel(gemm_bf16_tn_2cta_kernel, 2 * clusters, NUM_THREADS, Cfg2::SMEM_BYTES, st, maps, shape, epi);
   return cuda_check_launch("gemm_bf16_tn_2cta_kernel");
 }
 
@@ -927,7 +936,7 @@ extern "C" int gdmcf_gemm_bf16_tn(const gdmcf_gemm_desc* g, const gdmcf_epilogue
     const long long total = (long long)g->m * ((g->n + 7) / 8);
     const int threads = 256;
     const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)(sms > 0 ? sms : 148) * 8);
-    splitk_reduce_kernel<<<blocks, threads, 0, st>>>(shape, *e);
+    launch_kernel(splitk_reduce_kernel, blocks, threads, 0, st, shape, *e);
     rc = cuda_check_launch("splitk_reduce_kernel");
   }
   return rc;

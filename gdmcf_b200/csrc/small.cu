@@ -28,6 +28,7 @@ GD_DEV float temb_at(int t, int j, int e) {
 // emb_table[t, i] = b_emb[i] + sum_j w_emb[i, j] * temb(t)[j]        (emb_layer, models/DNN.py:24/1122)
 __global__ void time_emb_table_kernel(const float* __restrict__ w_emb, const float* __restrict__ b_emb, int T, int e,
                                       float* __restrict__ emb_table) {
+  pdl_entry();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T * e; i += gridDim.x * blockDim.x) {
     const int t = i / e, r = i % e;
     float s = b_emb[r];
@@ -38,6 +39,7 @@ __global__ void time_emb_table_kernel(const float* __restrict__ w_emb, const flo
 // bias_table[t, k] = b[k] + sum_j w_time[k, j] * emb_table[t, j]   (the `cat([x, emb])` columns of the first layer)
 __global__ void time_bias_table_kernel(const float* __restrict__ emb_table, const float* __restrict__ w_time, long long ld_w,
                                        const float* __restrict__ b, int T, int e, int d, float* __restrict__ out, long long ld_out) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)T * d; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i / d), k = (int)(i % d);
     float s = b ? b[k] : 0.f;
@@ -56,6 +58,7 @@ __global__ void bias_act_rows_kernel(const float* __restrict__ in, long long ld_
                                      long long ld_bias, const int* __restrict__ row_t, int t_const, int act,
                                      float* __restrict__ out_f32, long long ld_of, __nv_bfloat16* __restrict__ out_hi,
                                      __nv_bfloat16* __restrict__ out_lo, long long ld_ob, int rows, int cols) {
+  pdl_entry();
   const long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -77,6 +80,7 @@ __global__ void bias_act_rows_kernel(const float* __restrict__ in, long long ld_
 __global__ void gather_rows_kernel(const float* __restrict__ table, long long ld_t, const int* __restrict__ idx,
                                    float* __restrict__ out_f32, long long ld_of, __nv_bfloat16* __restrict__ out_hi,
                                    __nv_bfloat16* __restrict__ out_lo, long long ld_ob, int rows, int cols) {
+  pdl_entry();
   const long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -96,6 +100,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, long long ld
 __global__ void sgemm_small_kernel(const float* __restrict__ A, long long lda, int ta, const float* __restrict__ B,
                                    long long ldb, int tb, float* __restrict__ C, long long ldc, int M, int N, int K,
                                    float alpha, float beta) {
+  pdl_entry();
   __shared__ float sa[32][33], sb[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int tiles_n = (N + 31) / 32;
@@ -137,6 +142,7 @@ __global__ void sgemm_small_kernel(const float* __restrict__ A, long long lda, i
 // out[c] = sum_r x[r, c]: 32 columns x 8 row-slices per CTA, fixed summation order (deterministic).
 __global__ void __launch_bounds__(256)
 colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ out) {
+  pdl_entry();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int c0 = blockIdx.x * 32; c0 < cols; c0 += gridDim.x * 32) {
@@ -162,6 +168,7 @@ template <int NMAX>
 __global__ void __launch_bounds__(256)
 skinny_nn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, int tb,
                  float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, float beta) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -192,6 +199,7 @@ template <int NMAX>
 __global__ void __launch_bounds__(256)
 skinny_tn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb, int tb,
                  float* __restrict__ C, long long ldc, int M, int N, int K, float alpha, float beta, int stage_b) {
+  pdl_entry();
   __shared__ float red[8][NMAX][33];
   extern __shared__ float sB[];  // [K][N] when stage_b
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -273,9 +281,9 @@ extern "C" int gdmcf_time_bias_table(const float* w_emb, const float* b_emb, con
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  time_emb_table_kernel<<<grid_1d(T * e), TPB, 0, st>>>(w_emb, b_emb, T, e, emb_table);
+  launch_kernel(time_emb_table_kernel, grid_1d(T * e), TPB, 0, st, w_emb, b_emb, T, e, emb_table);
   if ((rc = cuda_check_launch("time_emb_table_kernel"))) return rc;
-  time_bias_table_kernel<<<grid_1d((long long)T * d), TPB, 0, st>>>(emb_table, w_time, ld_w, b, T, e, d, out, ld_out);
+  launch_kernel(time_bias_table_kernel, grid_1d((long long)T * d), TPB, 0, st, emb_table, w_time, ld_w, b, T, e, d, out, ld_out);
   return cuda_check_launch("time_bias_table_kernel");
 }
 
@@ -288,7 +296,7 @@ extern "C" int gdmcf_bias_act_rows(const float* in, int64_t ld_in, const float* 
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  bias_act_rows_kernel<<<grid_1d((long long)rows * cols), TPB, 0, st>>>(in, ld_in, bias, ld_bias, row_t, t_const, act, out_f32, ld_of,
+  launch_kernel(bias_act_rows_kernel, grid_1d((long long)rows * cols), TPB, 0, st, in, ld_in, bias, ld_bias, row_t, t_const, act, out_f32, ld_of,
                                                                         (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_lo, ld_ob, rows, cols);
   return cuda_check_launch("bias_act_rows_kernel");
 }
@@ -301,7 +309,7 @@ extern "C" int gdmcf_gather_rows(const float* table, int64_t ld_t, const int32_t
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  gather_rows_kernel<<<grid_1d((long long)rows * cols), TPB, 0, st>>>(table, ld_t, idx, out_f32, ld_of, (__nv_bfloat16*)out_bf16,
+  launch_kernel(gather_rows_kernel, grid_1d((long long)rows * cols), TPB, 0, st, table, ld_t, idx, out_f32, ld_of, (__nv_bfloat16*)out_bf16,
                                                                       (__nv_bfloat16*)out_lo, ld_ob, rows, cols);
   return cuda_check_launch("gather_rows_kernel");
 }
@@ -314,21 +322,21 @@ extern "C" int gdmcf_sgemm_small(const float* A, int64_t lda, int trans_a, const
     if (trans_a) {
       const size_t sb_bytes = (size_t)k * n * sizeof(float);
       const int stage_b = sb_bytes <= 28 * 1024 ? 1 : 0;  // + 16.9 KB static: stays under the 48 KB default limit
-      skinny_tn_kernel<16><<<grid_1d((m + 31) / 32, 1), 256, stage_b ? sb_bytes : 0, st>>>(A, lda, B, ldb, trans_b, C, ldc, m, n, k,
+      launch_kernel(skinny_tn_kernel<16>, grid_1d((m + 31) / 32, 1), 256, stage_b ? sb_bytes : 0, st, A, lda, B, ldb, trans_b, C, ldc, m, n, k,
                                                                                         alpha, beta, stage_b);
       return cuda_check_launch("skinny_tn_kernel");
     }
-    skinny_nn_kernel<16><<<grid_1d((long long)m * 32), 256, 0, st>>>(A, lda, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
+    launch_kernel(skinny_nn_kernel<16>, grid_1d((long long)m * 32), 256, 0, st, A, lda, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
     return cuda_check_launch("skinny_nn_kernel");
   }
   const int ntiles = ((m + 31) / 32) * ((n + 31) / 32);
-  sgemm_small_kernel<<<grid_1d(ntiles, 1), TPB, 0, st>>>(A, lda, trans_a, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
+  launch_kernel(sgemm_small_kernel, grid_1d(ntiles, 1), TPB, 0, st, A, lda, trans_a, B, ldb, trans_b, C, ldc, m, n, k, alpha, beta);
   return cuda_check_launch("sgemm_small_kernel");
 }
 
 extern "C" int gdmcf_colsum_f32(const float* x, int64_t ld, int rows, int cols, float* out, gdmcf_stream_t stream) {
   if (!x || !out || rows <= 0 || cols <= 0 || ld < cols) { set_error("colsum_f32: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
-  colsum_f32_kernel<<<grid_1d((cols + 31) / 32, 1), 256, 0, st>>>(x, ld, rows, cols, out);
+  launch_kernel(colsum_f32_kernel, grid_1d((cols + 31) / 32, 1), 256, 0, st, x, ld, rows, cols, out);
   return cuda_check_launch("colsum_f32_kernel");
 }

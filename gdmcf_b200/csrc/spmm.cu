@@ -111,6 +111,7 @@ spmm_items_kernel(const int* __restrict__ col, const float* __restrict__ val, co
                   int n_items, const float* __restrict__ X, const float* __restrict__ Z, float* __restrict__ Y,
                   float* __restrict__ scratch, int d, float alpha, float beta, const float* __restrict__ row_scale,
                   int row_pow, int pad_col) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int half = lane >> 4, hl = lane & 15;
   const int slabs = d >> 6;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 spmm_long_reduce_kernel(const int* __restrict__ long_rows, int n_long, const float* __restrict__ scratch,
                         const float* __restrict__ Z, float* __restrict__ Y, int d, float alpha, float beta,
                         const float* __restrict__ row_scale, int row_pow) {
+  pdl_entry();
   __shared__ float2 part_sm[WARPS_PER_CTA][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slabs = d >> 6;
@@ -238,6 +240,7 @@ spmm_long_reduce_kernel(const int* __restrict__ long_rows, int n_long, const flo
 // A~ = D^-1/2 [[0,R],[R^T,0]] D^-1/2, d_inv = (rowsum + 1e-9)^-1/2 (lightGCN.py:145-178). One thread per row.
 __global__ void norm_adj_rowptr_kernel(const int* __restrict__ r_rowptr, const int* __restrict__ rt_rowptr,
                                        int n_users, int n_items, int* __restrict__ rowptr_out) {
+  pdl_entry();
   const int n = n_users + n_items;
   const int nnz = r_rowptr[n_users];
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x)
@@ -247,6 +250,7 @@ GD_DEV float d_inv_of(int deg) { return 1.0f / sqrtf((float)deg + 1e-9f); }
 __global__ void norm_adj_fill_kernel(const int* __restrict__ r_rowptr, const int* __restrict__ r_col,
                                      const int* __restrict__ rt_rowptr, const int* __restrict__ rt_col, int n_users,
                                      int n_items, int* __restrict__ col_out, float* __restrict__ val_out) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int n = n_users + n_items;
   const int nnz = r_rowptr[n_users];
@@ -351,16 +355,16 @@ static int spmm_launch(const int32_t* col, const float* val, const int32_t* item
   if (n_items > 0) {
     const int grid = grid_for_warps((long long)n_items * slabs);
     if (val)
-      spmm_items_kernel<true><<<grid, WARPS_PER_CTA * 32, 0, st>>>(col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y,
+      launch_kernel(spmm_items_kernel<true>, grid, WARPS_PER_CTA * 32, 0, st, col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y,
                                                                  scratch, d, alpha, beta, row_scale, row_pow, pad_col);
     else
-      spmm_items_kernel<false><<<grid, WARPS_PER_CTA * 32, 0, st>>>(col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y,
+      launch_kernel(spmm_items_kernel<false>, grid, WARPS_PER_CTA * 32, 0, st, col, val, reinterpret_cast<const int4*>(items), n_items, X, Z, Y,
                                                                   scratch, d, alpha, beta, row_scale, row_pow, pad_col);
     if ((rc = cuda_check_launch("spmm_items_kernel"))) return rc;
   }
   if (n_long > 0) {
     const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
-    spmm_long_reduce_kernel<<<(int)std::min<long long>((long long)n_long * slabs, (long long)sms * 8), WARPS_PER_CTA * 32, 0, st>>>(
+    launch_kernel(spmm_long_reduce_kernel, (int)std::min<long long>((long long)n_long * slabs, (long long)sms * 8), WARPS_PER_CTA * 32, 0, st, 
         long_rows, n_long, scratch, Z, Y, d, alpha, beta, row_scale, row_pow);
     if ((rc = cuda_check_launch("spmm_long_reduce_kernel"))) return rc;
   }
@@ -377,6 +381,7 @@ extern "C" int gdmcf_spmm_csr_f32(const int32_t* col, const float* val, const in
 
 // u0[r, :] = dinv[r] * E0[r, :]
 __global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y, long long n4, int d4) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float sv = s[i / d4];
     float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -388,6 +393,7 @@ __global__ void scale_rows_kernel(const float* __restrict__ x, const float* __re
 // dinv[r] = (deg_r + 1e-9)^-1/2 for the bipartite graph [[0, R], [R^T, 0]] (lightGCN.py:160-166)
 __global__ void norm_adj_dinv_kernel(const int* __restrict__ r_rowptr, const int* __restrict__ rt_rowptr, int n_users, int n_items,
                                      float* __restrict__ dinv) {
+  pdl_entry();
   const int n = n_users + n_items;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     const int deg = r < n_users ? r_rowptr[r + 1] - r_rowptr[r] : rt_rowptr[r - n_users + 1] - rt_rowptr[r - n_users];
@@ -400,7 +406,7 @@ extern "C" int gdmcf_norm_adj_dinv(const int32_t* r_rowptr, const int32_t* rt_ro
   if (!r_rowptr || !rt_rowptr || !dinv || n_users <= 0 || n_items <= 0) { set_error("norm_adj_dinv: bad arguments"); return GDMCF_EBADARG; }
   int rc = gdmcf_device_check();
   if (rc) return rc;
-  norm_adj_dinv_kernel<<<(n_users + n_items + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(r_rowptr, rt_rowptr, n_users,
+  launch_kernel(norm_adj_dinv_kernel, (n_users + n_items + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream), r_rowptr, rt_rowptr, n_users,
                                                                                                       n_items, dinv);
   return cuda_check_launch("norm_adj_dinv_kernel");
 }
@@ -421,7 +427,7 @@ extern "C" int gdmcf_lightgcn_propagate_sym_f32(const int32_t* col, const float*
   if (rc) return rc;
   const long long n4 = (long long)n * d / 4;
   const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
-  scale_rows_kernel<<<(int)std::min<long long>((n4 + 255) / 256, (long long)sms * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(scale_rows_kernel, (int)std::min<long long>((n4 + 255) / 256, (long long)sms * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       E0, dinv, u0, n4, d / 4);
   if ((rc = cuda_check_launch("scale_rows_kernel"))) return rc;
   const float* src = u0;
@@ -469,8 +475,8 @@ extern "C" int gdmcf_build_norm_adj(const int32_t* r_rowptr, const int32_t* r_co
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n = n_users + n_items;
-  norm_adj_rowptr_kernel<<<std::min(1024, ceil_div(n + 1, 256)), 256, 0, st>>>(r_rowptr, rt_rowptr, n_users, n_items, rowptr_out);
+  launch_kernel(norm_adj_rowptr_kernel, std::min(1024, ceil_div(n + 1, 256)), 256, 0, st, r_rowptr, rt_rowptr, n_users, n_items, rowptr_out);
   if ((rc = cuda_check_launch("norm_adj_rowptr_kernel"))) return rc;
-  norm_adj_fill_kernel<<<std::min(148 * 16, ceil_div(n, 8)), 256, 0, st>>>(r_rowptr, r_col, rt_rowptr, rt_col, n_users, n_items, col_out, val_out);
+  launch_kernel(norm_adj_fill_kernel, std::min(148 * 16, ceil_div(n, 8)), 256, 0, st, r_rowptr, r_col, rt_rowptr, rt_col, n_users, n_items, col_out, val_out);
   return cuda_check_launch("norm_adj_fill_kernel");
 }

@@ -71,6 +71,7 @@ mask_topk_kernel(const float* __restrict__ scores, long long ld, int n_rows, int
                  const int* __restrict__ h_rowptr, const int* __restrict__ h_col, const int* __restrict__ h_rowptr2,
                  const int* __restrict__ h_col2, int k, int kpad, int stage_keys, int* __restrict__ out_idx,
                  float* __restrict__ out_val) {
+  pdl_entry();
   extern __shared__ uint32_t sm[];
   // layout: hist[256] | ctrl[8] | scan[TPB] | scan_idx[TPB] | cand_key[CAND_CAP] | cand_idx[CAND_CAP] | bitmap[words] | keys[n_items]?
   uint32_t* hist = sm;
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(MW * 32)
 topn_metrics_kernel(const int* __restrict__ topk_idx, int ld_idx, int n_rows, const int* __restrict__ users,
                     const int* __restrict__ gt_rowptr, const int* __restrict__ gt_col, const int* __restrict__ topn,
                     int n_topn, int max_n, double* __restrict__ stats) {
+  pdl_entry();
   extern __shared__ double smd[];
   double* inv_log = smd;                                                  // [max_n] 1/log2(j+2)
   uint32_t* hitbits = reinterpret_cast<uint32_t*>(inv_log + max_n);        // [MW][ceil(max_n/32)]
@@ -304,6 +306,7 @@ topn_metrics_kernel(const int* __restrict__ topk_idx, int ld_idx, int n_rows, co
 
 // out[c] = sum_r x[r, c], sequential per thread then fixed-shape tree: deterministic for fixed (rows, cols).
 __global__ void colsum_f64_kernel(const double* __restrict__ x, int rows, int cols, double* __restrict__ out) {
+  pdl_entry();
   __shared__ double red[256];
   for (int c = blockIdx.x; c < cols; c += gridDim.x) {
     double s = 0.0;
@@ -355,7 +358,7 @@ extern "C" int gdmcf_mask_topk(const float* scores, int64_t ld, int n_rows, int 
   }
   const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
   const int grid = std::min(n_rows, sms * 4);
-  mask_topk_kernel<<<grid, TPB, smem, st>>>(scores, ld, n_rows, n_items, users, hist_rowptr, hist_col, hist_rowptr2,
+  launch_kernel(mask_topk_kernel, grid, TPB, smem, st, scores, ld, n_rows, n_items, users, hist_rowptr, hist_col, hist_rowptr2,
                                             hist_col2, k, kpad, stage, out_idx, out_val);
   return cuda_check_launch("mask_topk_kernel");
 }
@@ -364,7 +367,7 @@ extern "C" int gdmcf_colsum_f64(const double* x, int rows, int cols, double* out
   if (!x || !out || rows <= 0 || cols <= 0) { set_error("colsum_f64: bad arguments"); return GDMCF_EBADARG; }
   int rc = gdmcf_device_check();
   if (rc) return rc;
-  colsum_f64_kernel<<<std::min(cols, 1024), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, rows, cols, out);
+  launch_kernel(colsum_f64_kernel, std::min(cols, 1024), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, rows, cols, out);
   return cuda_check_launch("colsum_f64_kernel");
 }
 
@@ -384,7 +387,7 @@ extern "C" int gdmcf_topn_metrics(const int32_t* topk_idx, int ld_idx, int n_row
   const size_t smem = (size_t)max_n * 8 + (size_t)MW * ((max_n + 31) / 32) * 4;
   const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
   const int grid = std::min((n_rows + MW - 1) / MW, sms * 8);
-  topn_metrics_kernel<<<grid, MW * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(topk_idx, ld_idx, n_rows, users, gt_rowptr,
+  launch_kernel(topn_metrics_kernel, grid, MW * 32, smem, reinterpret_cast<cudaStream_t>(stream), topk_idx, ld_idx, n_rows, users, gt_rowptr,
                                                                                      gt_col, topn, n_topn, max_n, stats);
   return cuda_check_launch("topn_metrics_kernel");
 }

@@ -36,6 +36,7 @@ loss_grad_kernel(const float* __restrict__ out, long long ld_out, const float* _
                  __nv_bfloat16* __restrict__ G, __nv_bfloat16* __restrict__ G_lo, long long ld_g,
                  __nv_bfloat16* __restrict__ GT, __nv_bfloat16* __restrict__ GT_lo, long long ld_gt,
                  float* __restrict__ colsum, float* __restrict__ rowpart, int B, int I) {
+  pdl_entry();
   __shared__ float tile[32][33];
   __shared__ float colred[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -96,6 +97,7 @@ loss_grad_kernel(const float* __restrict__ out, long long ld_out, const float* _
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out, long long ld_out,
                       int rows, int cols) {
+  pdl_entry();
   __shared__ __nv_bfloat16 tile[32][34];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int tr = (rows + 31) / 32, tc = (cols + 31) / 32;
@@ -119,6 +121,7 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __n
 __global__ void __launch_bounds__(256)
 transpose_bf16_vec_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
                           long long ld_out, int rows, int cols) {
+  pdl_entry();
   __shared__ uint32_t tile[64][33];  // 64 rows x 64 bf16 (32 words) + 1 pad word
   const int tid = threadIdx.x;
   const int tr = (rows + 63) / 64, tc = (cols + 63) / 64;
@@ -158,6 +161,7 @@ __global__ void ew_binary_kernel(int op, const float* __restrict__ a, long long 
                                  float alpha, float beta, float* __restrict__ out_f32, long long ld_of,
                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_ob, int rows,
                                  int cols) {
+  pdl_entry();
   const long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(TPB)
 mix_backward_kernel(const float* __restrict__ d_hcp, long long ld_d, const float* __restrict__ hc, long long ld_hc,
                     const float* __restrict__ g2, long long ld_g, const float* __restrict__ sumw, float* __restrict__ d_hc,
                     long long ld_dh, float* __restrict__ d_g2, long long ld_dg, float* __restrict__ dw_rows, int rows, int cols) {
+  pdl_entry();
   __shared__ float red[TPB / 32];
   const float w = sumw[0];
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
@@ -210,6 +215,7 @@ mix_backward_kernel(const float* __restrict__ d_hcp, long long ld_d, const float
 __global__ void __launch_bounds__(TPB)
 ntxent_rows_kernel(const float* __restrict__ S, long long ld_s, int n, float tau, float eps, const float* __restrict__ dscale,
                    float* __restrict__ loss_rows, float* __restrict__ dS, long long ld_ds) {
+  pdl_entry();
   __shared__ float red[TPB / 32];
   __shared__ float bc;
   const float inv_tau = 1.0f / tau;
@@ -260,6 +266,7 @@ ntxent_rows_kernel(const float* __restrict__ S, long long ld_s, int n, float tau
 // grad[idx[r], :] += v[r, :]   (dense embedding gradient rows; atomics make duplicate ids safe)
 __global__ void scatter_rows_add_kernel(const float* __restrict__ v, long long ld_v, const int* __restrict__ idx,
                                         float* __restrict__ grad, long long ld_g, int rows, int cols) {
+  pdl_entry();
   const long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -274,6 +281,7 @@ __global__ void scatter_rows_add_kernel(const float* __restrict__ v, long long l
 __global__ void __launch_bounds__(128)
 lt_history_kernel(const long long* __restrict__ ts, const double* __restrict__ loss, double* __restrict__ hist,
                   long long* __restrict__ count, int B, int T, int H) {
+  pdl_entry();
   __shared__ double rows[4][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int t = blockIdx.x * 4 + w;
@@ -318,6 +326,7 @@ __global__ void __launch_bounds__(256)
 sample_timesteps_kernel(const double* __restrict__ hist, const long long* __restrict__ count, int T, int H, int B,
                         double uniform_prob, uint64_t seed, uint64_t offset0, const uint64_t* __restrict__ epoch,
                         const long long* __restrict__ ts_in, long long* __restrict__ ts, double* __restrict__ pt) {
+  pdl_entry();
   __shared__ double s_p[1024];
   __shared__ double s_cdf[1024];
   int full = 1;
@@ -384,7 +393,7 @@ extern "C" int gdmcf_lt_history_update(const int64_t* ts, const double* loss, do
   }
   int rc = gdmcf_device_check();
   if (rc) return rc;
-  lt_history_kernel<<<(steps + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(lt_history_kernel, (steps + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(ts), loss, lt_history, reinterpret_cast<long long*>(lt_count), batch, steps, history);
   return cuda_check_launch("lt_history_kernel");
 }
@@ -398,7 +407,7 @@ extern "C" int gdmcf_sample_timesteps(const double* lt_history, const int64_t* l
   }
   int rc = gdmcf_device_check();
   if (rc) return rc;
-  sample_timesteps_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(sample_timesteps_kernel, 1, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       lt_history, reinterpret_cast<const long long*>(lt_count), steps, history, batch, uniform_prob, seed, offset, epoch_dev,
       reinterpret_cast<const long long*>(ts_in), reinterpret_cast<long long*>(ts_out), pt_out);
   return cuda_check_launch("sample_timesteps_kernel");
@@ -420,7 +429,7 @@ extern "C" int gdmcf_loss_grad(const float* out, int64_t ld_out, const float* x0
   }
   GD_PRE();
   const int n_cb = (cols + 31) / 32;
-  loss_grad_kernel<<<std::min(n_cb, sm_count() * 8), 256, 0, st>>>(out, ld_out, x0, ld_x0, gs, row_scale, col_scale, with_out,
+  launch_kernel(loss_grad_kernel, std::min(n_cb, sm_count() * 8), 256, 0, st, out, ld_out, x0, ld_x0, gs, row_scale, col_scale, with_out,
                                                                    (__nv_bfloat16*)g_bf16, (__nv_bfloat16*)g_lo, ld_g,
                                                                    (__nv_bfloat16*)gt_bf16, (__nv_bfloat16*)gt_lo, ld_gt,
                                                                    colsum, rowpart, rows, cols);
@@ -433,11 +442,11 @@ extern "C" int gdmcf_transpose_bf16(const void* in, int64_t ld_in, void* out, in
   GD_PRE();
   if ((ld_in & 7) == 0 && (ld_out & 7) == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
     const long long nt = (long long)((rows + 63) / 64) * ((cols + 63) / 64);
-    transpose_bf16_vec_kernel<<<grid_1d(nt, 1), 256, 0, st>>>((const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, ld_out, rows, cols);
+    launch_kernel(transpose_bf16_vec_kernel, grid_1d(nt, 1), 256, 0, st, (const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, ld_out, rows, cols);
     return cuda_check_launch("transpose_bf16_vec_kernel");
   }
   const long long nt = (long long)((rows + 31) / 32) * ((cols + 31) / 32);
-  transpose_bf16_kernel<<<grid_1d(nt, 1), 256, 0, st>>>((const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, ld_out, rows, cols);
+  launch_kernel(transpose_bf16_kernel, grid_1d(nt, 1), 256, 0, st, (const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, ld_out, rows, cols);
   return cuda_check_launch("transpose_bf16_kernel");
 }
 
@@ -450,7 +459,7 @@ extern "C" int gdmcf_ew_binary(int op, const float* a, int64_t ld_a, const float
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  ew_binary_kernel<<<grid_1d((long long)rows * cols), TPB, 0, st>>>(op, a, ld_a, b, ld_b, alpha, beta, out_f32, ld_of,
+  launch_kernel(ew_binary_kernel, grid_1d((long long)rows * cols), TPB, 0, st, op, a, ld_a, b, ld_b, alpha, beta, out_f32, ld_of,
                                                                     (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_lo, ld_ob, rows, cols);
   return cuda_check_launch("ew_binary_kernel");
 }
@@ -464,7 +473,7 @@ extern "C" int gdmcf_mix_backward(const float* d_hcp, int64_t ld_d, const float*
     return GDMCF_EBADARG;
   }
   GD_PRE();
-  mix_backward_kernel<<<grid_1d(rows, 1), TPB, 0, st>>>(d_hcp, ld_d, hc, ld_hc, g2, ld_g, sumw, d_hc, ld_dh, d_g2, ld_dg, dw_rows, rows, cols);
+  launch_kernel(mix_backward_kernel, grid_1d(rows, 1), TPB, 0, st, d_hcp, ld_d, hc, ld_hc, g2, ld_g, sumw, d_hc, ld_dh, d_g2, ld_dg, dw_rows, rows, cols);
   return cuda_check_launch("mix_backward_kernel");
 }
 
@@ -472,7 +481,7 @@ extern "C" int gdmcf_ntxent_rows(const float* S, int64_t ld_s, int n, float tau,
                                  float* loss_rows, float* dS, int64_t ld_ds, gdmcf_stream_t stream) {
   if (!S || n <= 1 || ld_s < n || tau <= 0.f || (!loss_rows && !dS) || (dS && ld_ds < n)) { set_error("ntxent_rows: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
-  ntxent_rows_kernel<<<grid_1d(n, 1), TPB, 0, st>>>(S, ld_s, n, tau, eps, dscale, loss_rows, dS, ld_ds);
+  launch_kernel(ntxent_rows_kernel, grid_1d(n, 1), TPB, 0, st, S, ld_s, n, tau, eps, dscale, loss_rows, dS, ld_ds);
   return cuda_check_launch("ntxent_rows_kernel");
 }
 
@@ -480,6 +489,6 @@ extern "C" int gdmcf_scatter_rows_add(const float* v, int64_t ld_v, const int32_
                                       int cols, gdmcf_stream_t stream) {
   if (!v || !idx || !grad || rows <= 0 || cols <= 0 || ld_v < cols || ld_g < cols) { set_error("scatter_rows_add: bad arguments"); return GDMCF_EBADARG; }
   GD_PRE();
-  scatter_rows_add_kernel<<<grid_1d((long long)rows * cols), TPB, 0, st>>>(v, ld_v, idx, grad, ld_g, rows, cols);
+  launch_kernel(scatter_rows_add_kernel, grid_1d((long long)rows * cols), TPB, 0, st, v, ld_v, idx, grad, ld_g, rows, cols);
   return cuda_check_launch("scatter_rows_add_kernel");
 }

@@ -142,7 +142,8 @@ def test_lightgcn_cuda_vs_reference_golden():
     A = torch.sparse_csr_tensor(rowptr.long(), col.long(), val, size=(N, N)).to_dense().cpu()
     A_ref = torch.sparse_coo_tensor(torch.from_numpy(g["A_indices"]), torch.from_numpy(g["A_values"]), (N, N)).to_dense()
     np.testing.assert_allclose(A.numpy(), A_ref.numpy(), rtol=3e-7, atol=0)   # get_A_tilda, lightGCN.py:145-178
-    fu, fi, iu, ii = lg.propagate_through_layers()                              # lightGCN.py:180-194
+    with torch.no_grad():
+        fu, fi, iu, ii = lg.propagate_through_layers()                          # lightGCN.py:180-194
     np.testing.assert_allclose(fu.cpu().numpy(), g["final_user"], rtol=0, atol=2e-6)
     np.testing.assert_allclose(fi.cpu().numpy(), g["final_item"], rtol=0, atol=2e-6)
     assert torch.equal(torch.cat([iu, ii]).cpu(), torch.from_numpy(g["E0"]))
