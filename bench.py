@@ -506,6 +506,7 @@ def run_engine(args):
 
     cpu, parity = None, None
     if rank == 0 and G == 1 and not args.no_cpu_baseline and args.mode == "train+rank":
+        eng.flush()  # the user table is updated row-sparsely with exact catch-up: bring every row up to date before export
         sd = {kk: v.detach().cpu() for kk, v in model.state_dict().items()}
         arm = CpuArm(args, sd)
         # parity first: the oracle still holds exactly the engine's weights (arm.step() trains the oracle's copy)

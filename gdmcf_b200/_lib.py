@@ -111,6 +111,10 @@ SIGNATURES = {
     "gdmcf_mse_rows": (_I, [_P, _L, _P, _L, _I, _I, _P, _P]),
     "gdmcf_adamw_fused": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
     "gdmcf_counter_add": (_I, [_P, _U64, _P]),
+    "gdmcf_user_tower_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "gdmcf_user_tower": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _P, _I, _I, _I, _I, _P, _L, _P, _P, _P, _L, _P, _L, _P, _SZ,
+                              _P, _I, _P]),
+    "gdmcf_adamw_rows_lazy": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _F, _F, _F, _F, _I, _P, _F, _P]),
     "gdmcf_adamw_partitioned": (_I, [_P, _P, _L, _P, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _F, _P, _I, _P]),
     "gdmcf_adamw_refresh_splits": (_I, [_I, _I]),
     "gdmcf_adamw_refresh": (_I, [_P, _P, _L, _P, _P, _I, _I, _F, _F, _F, _F, _F, _I, _P, _F, C.POINTER(Refresh), _P]),

@@ -34,7 +34,8 @@ class StepEngine:
     def __init__(self, model, diffusion, optimizer, dist, *, batch_size: int, n_item: int, topk: int, topN: Sequence[int],
                  cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
                  rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
-                 shard_min_bytes: int = 64 << 20, train: bool = True, overlap_sms: int = 0):
+                 shard_min_bytes: int = 64 << 20, train: bool = True, overlap_sms: int = 0,
+                 lazy_user_rows: bool = True):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
@@ -78,6 +79,11 @@ class StepEngine:
         if G > 1 and shard_optimizer and train:
             self._setup_shards(shard_min_bytes)
         self.sparse_user_rows = G > 1 and hasattr(model, "embedding_user")
+        # The user table's gradient has B non-zero rows per rank. lazy_user_rows: AdamW touches only those rows; the
+        # zero-gradient updates every other row would have received (decaying moments still move the weights) are replayed
+        # exactly when a row is next used (optim.FusedAdamW.update_rows_lazy; call flush() before reading the table
+        # outside step()). Saves a 28 B/element pass over the [n_user, d] table and its dense gradient every step.
+        self.lazy_user_rows = bool(lazy_user_rows) and train and hasattr(model, "embedding_user")
         if self.sparse_user_rows:
             d = model.embedding_user.weight.shape[1]
             self._send_idx = torch.zeros(batch_size, **i32)
@@ -143,12 +149,19 @@ class StepEngine:
         model.train()
         opt.zero_grad(set_to_none=True)
         params = dict(model.named_parameters())
+        lazy = self.lazy_user_rows
+        if lazy:  # the forward pass reads these users' rows: bring them up to the last completed optimizer step first
+            opt.catch_up_rows(params["embedding_user.weight"], self.users, self.B)
         stages = fused_train_stages(diff, model, self._batch(), self.reweight, index=self.users,
-                                    defer_item_norm=self.defer_item_norm)
+                                    defer_item_norm=self.defer_item_norm, sparse_user_grad=lazy)
         _, loss = next(stages)
         groups, row_coef = [], {}
-        for _, grads in stages:
+        user_gi = None
+        for si, (_, grads) in enumerate(stages):
             names = list(grads)
+            has_user = "embedding_user.weight" in grads or (lazy and si == 1)
+            if has_user:
+                user_gi = len(groups)
             for n in names:
                 sh = self._shards.get(n)
                 if sh is not None and grads[n].data_ptr() != sh["gview"].data_ptr():
@@ -166,7 +179,7 @@ class StepEngine:
                 if not rs and sum(t.numel() * t.element_size() for t in dense) < (64 << 20):
                     self._small_keys.add(len(groups) - 1)
                 dense = (dense, rs)
-                if self.sparse_user_rows and "embedding_user.weight" in grads:
+                if self.sparse_user_rows and has_user:
                     # only B rows of the user table carry a gradient: exchange (ids, rows) instead of the dense table
                     idx, rows = model._user_grad_rows
                     self._send_idx.copy_(idx)
@@ -190,8 +203,16 @@ class StepEngine:
 
         def finish_group(gi, sharded_rows: bool, replicated: bool):
             plist = groups[gi]
+            if replicated and lazy and gi == user_gi:
+                pU = params["embedding_user.weight"]
+                if G == 1:
+                    idx_, rows_ = model._user_grad_rows
+                    opt.update_rows_lazy(pU, idx_, rows_, self.B)
+                else:  # one row set per rank (distinct users: the ranks hold different batches), identical on every rank
+                    for r in range(G):
+                        opt.update_rows_lazy(pU, self._recv_idx[r], self._recv_rows[r], self.B, grad_scale=1.0 / G, first=r == 0)
             if replicated:
-                if self.sparse_user_rows and any(p is params.get("embedding_user.weight") for p in plist):
+                if not lazy and self.sparse_user_rows and any(p is params.get("embedding_user.weight") for p in plist):
                     gU = params["embedding_user.weight"].grad
                     d = gU.shape[1]
                     for r in range(G):
@@ -228,6 +249,8 @@ class StepEngine:
             finally:
                 K.gemm_set_sm_limit(0)
             opt.update([p for p in every if id(p) not in side_ids], row_coef=row_coef)
+            if lazy:
+                opt.update_rows_lazy(params["embedding_user.weight"], *model._user_grad_rows, self.B)
             main.wait_stream(side)
             for p_ in side_params:
                 spec = specs.get(id(p_))
@@ -329,6 +352,13 @@ class StepEngine:
             works.append(td.all_gather_into_tensor(self._recv_idx.view(-1), self._send_idx, group=group, async_op=True))
             works.append(td.all_gather_into_tensor(self._recv_rows.view(-1), self._send_rows.view(-1), group=group, async_op=True))
         self._works[key], self._after[key] = works, after
+
+    def flush(self) -> None:
+        """Bring lazily updated tables (lazy_user_rows) up to the current optimizer step. Call before the parameters are
+        read outside step(): evaluation of other users, state_dict(), checkpoints, comparisons."""
+        if self.train:
+            self.opt.flush_lazy()
+            self.model.weights_updated()
 
     def _eager_step(self):
         self._main_stream = torch.cuda.current_stream(self.dev)

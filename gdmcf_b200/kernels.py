@@ -170,9 +170,14 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+_sm_limit = 0
+
+
 def gemm_set_sm_limit(sms: int) -> None:
     """Upper bound on the SMs the contraction kernels occupy from now on (0 = all). See gdmcf_gemm_set_sm_limit."""
+    global _sm_limit
     check(load().gdmcf_gemm_set_sm_limit(int(sms)), "gemm_set_sm_limit")
+    _sm_limit = int(sms)
 
 
 def gemm(a: Sequence[torch.Tensor], b: Sequence[torch.Tensor], m: int, n: int, k: Sequence[int], *,
@@ -213,6 +218,32 @@ def gemm(a: Sequence[torch.Tensor], b: Sequence[torch.Tensor], m: int, n: int, k
         ws_bytes = lib.gdmcf_gemm_workspace_bytes(m, n, splits)
         ws = _workspace(ws_bytes, a[0].device)
     check(lib.gdmcf_gemm_bf16_tn(C.byref(g), C.byref(e), splits, ptr(ws), ws_bytes, stream()), "gemm_bf16_tn")
+
+
+_tower_ws: dict = {}
+
+
+def user_tower(hc: Bf16Mat, hc_f32, w1: Bf16Mat, b1, w2: Bf16Mat, b2, sumw, rows: int, *, out: Bf16Mat, inv_u,
+               g1_f32=None, g2_f32=None, hcp_f32=None, max_ctas: Optional[int] = None) -> None:
+    """conv1 + relu + conv2 + sumW mix + user norms of the GDMCF tower in one launch (gdmcf_user_tower, bf16 mode).
+    max_ctas defaults to the SM limit currently imposed on the contractions (gemm_set_sm_limit)."""
+    if max_ctas is None:
+        max_ctas = _sm_limit
+    require_cuda(hc.hi, hc_f32, w1.hi, b1, w2.hi, b2, sumw, out.hi, inv_u, g1_f32, g2_f32, hcp_f32)
+    k1, hidden, n = hc.cols, w1.rows, w2.rows
+    assert w1.cols == k1 and w2.cols == hidden and out.cols == n and hc_f32.stride(1) == 1
+    lib = load()
+    key = (str(hc.hi.device), torch.cuda.current_stream().cuda_stream, rows, k1, hidden, n)
+    ws = _tower_ws.get(key)
+    if ws is None:
+        nbytes = lib.gdmcf_user_tower_workspace_bytes(rows, k1, hidden, n)
+        ws = (torch.empty(nbytes, dtype=torch.uint8, device=hc.hi.device), torch.zeros(16, dtype=torch.int32, device=hc.hi.device))
+        _tower_ws[key] = ws
+    check(lib.gdmcf_user_tower(ptr(hc.hi), hc.ld, ptr(hc_f32), hc_f32.stride(0), ptr(w1.hi), w1.ld, ptr(b1), ptr(w2.hi), w2.ld,
+                               ptr(b2), ptr(sumw), rows, k1, hidden, n, ptr(out.hi), out.ld, ptr(inv_u), ptr(g1_f32), ptr(g2_f32),
+                               g2_f32.stride(0) if g2_f32 is not None else 0, ptr(hcp_f32),
+                               hcp_f32.stride(0) if hcp_f32 is not None else 0, ptr(ws[0]), ws[0].numel(), ptr(ws[1]), max_ctas,
+                               stream()), "user_tower")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -410,6 +441,24 @@ def adamw_fused(p, g, m, v, *, lr: float, beta1: float = 0.9, beta2: float = 0.9
     assert p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
     check(load().gdmcf_adamw_fused(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
                                    ptr(step_dev), grad_scale, stream()), "adamw_fused")
+
+
+def adamw_rows_lazy(p, m, v, last_step, *, idx=None, grad_rows=None, n_sel: int = 0, lr: float, beta1: float = 0.9,
+                    beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0, step: int = 1, step_dev=None,
+                    grad_scale: float = 1.0) -> None:
+    """Row-sparse AdamW with exact catch-up of the skipped steps (gdmcf_adamw_rows_lazy). idx=None: flush all rows."""
+    require_cuda(p, m, v, last_step, idx, grad_rows)
+    assert p.dim() == 2 and p.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    assert last_step.dtype == torch.int32 and last_step.numel() == p.shape[0]
+    ld_g = 0
+    if idx is not None:
+        assert idx.dtype == torch.int32 and idx.is_contiguous() and n_sel > 0
+    if grad_rows is not None:
+        assert idx is not None and grad_rows.stride(1) == 1 and grad_rows.shape[1] == p.shape[1]
+        ld_g = grad_rows.stride(0)
+    check(load().gdmcf_adamw_rows_lazy(ptr(p), ptr(m), ptr(v), ptr(last_step), ptr(idx), ptr(grad_rows), ld_g, n_sel, p.shape[0],
+                                       p.shape[1], lr, beta1, beta2, eps, weight_decay, step, ptr(step_dev), grad_scale, stream()),
+          "adamw_rows_lazy")
 
 
 def adamw_partitioned(p, g, m, v, *, n_ctas: int, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,

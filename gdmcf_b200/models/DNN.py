@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import copy
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -29,6 +30,10 @@ from .. import kernels as K
 from ..kernels import Bf16Mat
 
 _MAX_T_TABLE = 1024
+
+
+def c_ok(hidden_channels: int) -> bool:
+    return hidden_channels % 64 == 0
 
 
 def _as_i32(t: torch.Tensor) -> torch.Tensor:
@@ -452,10 +457,19 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         c1, c2 = self.gcn_model.conv1, self.gcn_model.conv2
         wc1 = self._weight_operand("gcn1", c1.lin.weight)
         wc2 = self._weight_operand("gcn2", c2.lin.weight)
+        if self._fused_tower():
+            # both linears, the mix and the norms in one launch (csrc/tower.cu)
+            K.user_tower(bufs["hc"], bufs["hc_f32"], wc1, c1.bias.detach(), wc2, c2.bias.detach(), self.sumW.detach(), B,
+                         out=bufs["hcp"], inv_u=bufs["inv_u"])
+            return
         g1 = bufs["g1"]
         self._mm(bufs["hc"], wc1, B, 512, d3, act=K.ACT_RELU, bias=c1.bias.detach(), out_bf16=g1.hi, out_bf16_lo=g1.lo)
         self._mm(g1, wc2, B, d3, 512, bias=c2.bias.detach(), out_f32=bufs["g2"])
         K.mix_rownorm(bufs["hc_f32"], B, d3, g=bufs["g2"], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
+
+    def _fused_tower(self) -> bool:
+        """bf16 mode uses the one-launch tower kernel (GDMCF_FUSED_TOWER=0: the two contractions + mix kernels)."""
+        return not self._lo and os.environ.get("GDMCF_FUSED_TOWER", "1") != "0" and c_ok(self.gcn_model.conv1.lin.weight.shape[0])
 
     def _score(self, bufs, B: int, out_f32, out_op: Optional[Bf16Mat] = None, **post):
         """cosine_similarity_cuda (models/DNN.py:1304-1327) with the norms applied in the GEMM epilogue."""

@@ -22,6 +22,7 @@ class FusedAdamW(torch.optim.Optimizer):
         # fuse_refresh: 2-D weights of `modules` are updated by gdmcf_adamw_refresh, which also rewrites the tensors the
         # contractions derive from them (same update arithmetic; False keeps one flat pass per parameter)
         self._fuse_refresh = fuse_refresh
+        self._lazy = {}  # id(param) -> row-sparse parameters updated with exact catch-up (update_rows_lazy)
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -104,6 +105,56 @@ class FusedAdamW(torch.optim.Optimizer):
                         beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"], step=st["step"],
                         step_dev=self._step_dev if self._capturable else None, grad_scale=grad_scale,
                         row_coef=row_coef[r0:r1] if row_coef is not None else None)
+
+    # -- row-sparse parameters (embedding_user: only the batch's rows carry a gradient) ---------------------------------
+    def _lazy_state(self, p):
+        st = self.state[p]
+        if "exp_avg" not in st:
+            st["step"] = 0
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        if "last_step" not in st:
+            # rows are up to date with every step taken so far (they were updated densely, or never)
+            st["last_step"] = torch.full((p.shape[0],), int(st["step"]), dtype=torch.int32, device=p.device)
+            if self._capturable and self._step_dev is not None:
+                st["last_step"] += (self._step_dev.to(torch.int32) - int(st["step"]))
+        self._lazy[id(p)] = p
+        group = next(g for g in self.param_groups if any(q is p for q in g["params"]))
+        b1, b2 = group["betas"]
+        return st, dict(lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"],
+                        step_dev=self._step_dev if self._capturable else None)
+
+    @torch.no_grad()
+    def catch_up_rows(self, p, idx, n_sel: int) -> None:
+        """Bring rows idx of a lazily updated table up to the last completed step (call BEFORE a forward pass reads them)."""
+        if self._capturable and self._step_dev is None:
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=p.device)
+        st, hyper = self._lazy_state(p)
+        if st["step"] == 0 and not self._capturable:
+            return
+        K.adamw_rows_lazy(p.data, st["exp_avg"], st["exp_avg_sq"], st["last_step"], idx=idx, n_sel=n_sel, step=max(st["step"], 1),
+                          **hyper)
+
+    @torch.no_grad()
+    def update_rows_lazy(self, p, idx, grad_rows, n_sel: int, grad_scale: float = 1.0, first: bool = True) -> None:
+        """AdamW step on a table whose gradient is non-zero on rows idx only (distinct), grad_rows [n_sel, cols]: the other
+        rows are NOT touched now; their zero-gradient updates are replayed exactly when they are next selected, caught up
+        or flushed (gdmcf_adamw_rows_lazy). Call between begin_step() and end_step(); `first=False` for further row sets of
+        the same step (data parallel: one set per rank)."""
+        st, hyper = self._lazy_state(p)
+        if first:
+            st["step"] += 1
+        K.adamw_rows_lazy(p.data, st["exp_avg"], st["exp_avg_sq"], st["last_step"], idx=idx, grad_rows=grad_rows, n_sel=n_sel,
+                          step=st["step"], grad_scale=grad_scale, **hyper)
+
+    @torch.no_grad()
+    def flush_lazy(self) -> None:
+        """Replay the pending zero-gradient steps of every lazily updated table. Required before such a table is read
+        outside the training step (evaluation of other users, state_dict, checkpoint)."""
+        for p in self._lazy.values():
+            st, hyper = self._lazy_state(p)
+            if st["step"] > 0 or self._capturable:
+                K.adamw_rows_lazy(p.data, st["exp_avg"], st["exp_avg_sq"], st["last_step"], step=max(st["step"], 1), **hyper)
 
     @torch.no_grad()
     def end_step(self) -> None:

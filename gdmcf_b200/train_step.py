@@ -155,17 +155,23 @@ def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc,
     g = model.gcn_model
     wc1 = model._weight_operand("gcn1", g.conv1.lin.weight)
     wc2 = model._weight_operand("gcn2", g.conv2.lin.weight)
-    c.g1_f32 = torch.empty(B, 512, dtype=torch.float32, device=dev)
-    c.g1 = Bf16Mat.empty(B, 512, dev, model._lo)
-    hc_in = c.hc if model._lo else Bf16Mat(c.hc.hi, None, B, 3 * d)
-    _mm_auto(model, hc_in, wc1, B, 512, 3 * d, act=K.ACT_RELU, bias=g.conv1.bias.detach(), out_f32=c.g1_f32,
-             out_bf16=c.g1.hi, out_bf16_lo=c.g1.lo)
+    H = g.conv1.lin.weight.shape[0]
+    c.g1_f32 = torch.empty(B, H, dtype=torch.float32, device=dev)
     c.g2 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
-    _mm_auto(model, c.g1, wc2, B, 3 * d, 512, bias=g.conv2.bias.detach(), out_f32=c.g2)
     c.hcp_f32 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
     c.hcp = Bf16Mat.empty(B, 3 * d, dev, model._lo)
     c.inv_u = torch.empty(B, dtype=torch.float32, device=dev)
-    K.mix_rownorm(c.hc_f32, B, 3 * d, g=c.g2, sumw=model.sumW.detach(), out_f32=c.hcp_f32, out=c.hcp, inv_norm=c.inv_u)
+    hc_in = c.hc if model._lo else Bf16Mat(c.hc.hi, None, B, 3 * d)
+    if model._fused_tower():
+        # one launch for both linears, the mix and the norms; the fp32 copies feed the backward pass
+        K.user_tower(hc_in, c.hc_f32, wc1, g.conv1.bias.detach(), wc2, g.conv2.bias.detach(), model.sumW.detach(), B,
+                     out=c.hcp, inv_u=c.inv_u, g1_f32=c.g1_f32, g2_f32=c.g2, hcp_f32=c.hcp_f32)
+    else:
+        c.g1 = Bf16Mat.empty(B, H, dev, model._lo)
+        _mm_auto(model, hc_in, wc1, B, H, 3 * d, act=K.ACT_RELU, bias=g.conv1.bias.detach(), out_f32=c.g1_f32,
+                 out_bf16=c.g1.hi, out_bf16_lo=c.g1.lo)
+        _mm_auto(model, c.g1, wc2, B, 3 * d, H, bias=g.conv2.bias.detach(), out_f32=c.g2)
+        K.mix_rownorm(c.hc_f32, B, 3 * d, g=c.g2, sumw=model.sumW.detach(), out_f32=c.hcp_f32, out=c.hcp, inv_norm=c.inv_u)
     # cosine scorer (DNN.py:1304-1327) and per-row MSE (gaussian_diffusion.py:902)
     e_op, c.inv_i = model._item_operands()
     c.out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
@@ -182,7 +188,7 @@ def _gdmcf_backward(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Te
 
 
 def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: torch.Tensor, g_closs: torch.Tensor,
-                           defer_item_norm: bool = False):
+                           defer_item_norm: bool = False, sparse_user_grad: bool = False):
     """Generator over the backward pass: yields {parameter name: gradient} as soon as a group is final, so that a
     data-parallel caller can start its all-reduce while the rest of the backward runs. Stage 1: the item table
     (412 MB at the Yelp shape, needs only dL/d(out) and the user tower); stage 2: sumW, GCN linears, user table;
@@ -254,11 +260,12 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     d_hc_tot = torch.empty(B, d3, dtype=torch.float32, device=dev)
     _mm_auto(model, d_pre1_op, wc1T, B, d3, 512, out_f32=d_hc_tot, c1=ones1, c2=ones1, xt=d_hc, t_const=0)
     # ---- user embedding rows
-    gU = torch.zeros_like(P["embedding_user.weight"])
-    K.scatter_rows_add(d_hc_tot[:, 2 * d:], c.idx32, gU, B, d)
-    grads["embedding_user.weight"] = gU
-    # the rows of the user table that received a gradient (for a sparse exchange instead of a dense all-reduce)
+    # the rows of the user table that received a gradient (sparse exchange / row-sparse optimizer instead of a dense table)
     model._user_grad_rows = (c.idx32, d_hc_tot[:, 2 * d:])
+    if not sparse_user_grad:
+        gU = torch.zeros_like(P["embedding_user.weight"])
+        K.scatter_rows_add(d_hc_tot[:, 2 * d:], c.idx32, gU, B, d)
+        grads["embedding_user.weight"] = gU
     yield grads  # stage 2: sumW, the GCN linears, the user table — small messages, final before the two big wgrads
     grads = {}
     # ---- nt_xent backward (DNN.py:479-508) into h and h_U
@@ -473,7 +480,7 @@ def training_losses(diff, model, x_start, reweight=False, index=None, inject: Op
 
 @torch.no_grad()
 def fused_train_stages(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None,
-                       defer_item_norm: bool = False):
+                       defer_item_norm: bool = False, sparse_user_grad: bool = False):
     """`training_losses(...)["loss"].mean().backward()` without autograd, as a generator (used by engine.StepEngine):
     yields ("loss", mean loss [] f64) after the forward and loss bookkeeping, then ("grads", {parameter name: gradient})
     once per backward stage, in the order the gradients become final — a data-parallel caller starts the all-reduce of a
@@ -499,7 +506,9 @@ def fused_train_stages(diff, model, x_start, reweight=False, index=None, inject:
     g_mse = (weight / pt / B).float()
     if gdmcf:
         g_closs = torch.full((), 0.1, dtype=torch.float32, device=dev)
-        for stage in _gdmcf_backward_stages(model, diff, c, g_mse, g_closs, defer_item_norm):
+        # sparse_user_grad: the user table's gradient is NOT materialised as a dense [n_user, d] tensor; the caller
+        # consumes model._user_grad_rows = (user ids [B], gradient rows [B, d]) after the second stage
+        for stage in _gdmcf_backward_stages(model, diff, c, g_mse, g_closs, defer_item_norm, sparse_user_grad):
             yield "grads", stage
     else:
         yield "grads", _dnn_backward(model, diff, c, g_mse)

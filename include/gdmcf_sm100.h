@@ -297,6 +297,20 @@ int gdmcf_adamw_refresh_splits(int rows, int cols);
 int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float* m, float* v, int rows, int cols, float lr,
                         float beta1, float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
                         float grad_scale, const gdmcf_refresh* out, gdmcf_stream_t stream);
+/* User tower of DNNOneHotEmbeddingGCN in one launch (bf16 mode): LayerGCN on the user rows (models/DNN.py:1093-1100,
+ * GCNConv with self loops only = two linears), the sumW mix (:1288) and the user norms of the cosine scorer (:1320):
+ *   g1 = relu(hc W1^T + b1) [rows, hidden];  g2 = g1 W2^T + b2 [rows, n];  hc' = hc*sumW + g2*(1 - sumW);  inv_u = 1/||hc'||
+ * hc_bf16 [rows, ld_hcb] / hc_f32 [rows, ld_hc]: the concatenated tower input (k1 = n columns); w1_bf16 [hidden, ld_w1],
+ * w2_bf16 [n, ld_w2] K-major bf16 operands. Outputs: hcp_bf16 [rows, ld_hcp] (columns [n, ld_hcp) zeroed), inv_u [rows],
+ * optional fp32 copies g1_f32 [rows, hidden], g2_f32, hcp_f32 (training keeps them for the backward pass). workspace:
+ * gdmcf_user_tower_workspace_bytes(); sync_block: 64 zero-initialised bytes that the kernel leaves zeroed (grid barriers of
+ * one resident wave of CTAs; max_ctas > 0 bounds the wave, 0 = one CTA per SM). Deterministic. */
+size_t gdmcf_user_tower_workspace_bytes(int rows, int k1, int hidden, int n);
+int gdmcf_user_tower(const void* hc_bf16, int64_t ld_hcb, const float* hc_f32, int64_t ld_hc, const void* w1_bf16,
+                     int64_t ld_w1, const float* b1, const void* w2_bf16, int64_t ld_w2, const float* b2, const float* sumw,
+                     int rows, int k1, int hidden, int n, void* hcp_bf16, int64_t ld_hcp, float* inv_u, float* g1_f32,
+                     float* g2_f32, int64_t ld_g2, float* hcp_f32, int64_t ld_hcp32, void* workspace, size_t workspace_bytes,
+                     uint32_t* sync_block, int max_ctas, gdmcf_stream_t stream);
 /* AdamW only (no derived tensors) confined to `n_ctas` SMs: n_ctas CTAs (clusters of 2, one CTA per SM, each reserving
  * more than half of the SM's shared memory so that no tcgen05 contraction CTA can share it). Lets the HBM-bound optimizer
  * pass (main.py:351) run on a side stream next to the tensor-bound denoise + rank phase whose contractions were limited to
@@ -304,6 +318,16 @@ int gdmcf_adamw_refresh(float* p, const float* g, int64_t ld_g, float* m, float*
 int gdmcf_adamw_partitioned(float* p, const float* g, int64_t ld_g, float* m, float* v, int rows, int cols, float lr,
                             float beta1, float beta2, float eps, float weight_decay, int step, const int64_t* step_dev,
                             float grad_scale, const float* row_coef, int n_ctas, gdmcf_stream_t stream);
+/* AdamW (torch.optim.AdamW semantics, main.py:258,351) on a [n_rows, cols] embedding table whose gradient is non-zero on
+ * n_sel rows only: idx int32 [n_sel] (distinct rows), grad_rows [n_sel, ld_g]. last_step int32 [n_rows] (zero-initialised)
+ * records the optimizer step each row is up to date with; a row that receives a gradient first replays the steps it
+ * missed with a zero gradient (decaying moments keep moving the weights, exactly as the dense pass would), then takes the
+ * real update — results are bit-identical to gdmcf_adamw_fused on the dense gradient. grad_rows == NULL: the rows idx (the
+ * rows the next forward pass will read) or, with idx == NULL, all rows (flush: required before the table is read outside
+ * the training step, saved or evaluated) are brought up to the current step with zero gradients. */
+int gdmcf_adamw_rows_lazy(float* p, float* m, float* v, int32_t* last_step, const int32_t* idx, const float* grad_rows,
+                          int64_t ld_g, int n_sel, int n_rows, int cols, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, const int64_t* step_dev, float grad_scale, gdmcf_stream_t stream);
 /* counter_dev[0] += inc on the stream: the device-resident step / RNG-epoch counters that keep captured CUDA graphs
  * advancing (Philox counter high word = (epoch << 8) | sub-stream; AdamW bias corrections from *step_dev when non-NULL). */
 int gdmcf_counter_add(uint64_t* counter_dev, uint64_t inc, gdmcf_stream_t stream);

@@ -1,6 +1,6 @@
 """Data-parallel check of engine.StepEngine under torchrun (N >= 2, NCCL): the graph-segment engine with overlapped
 all-reduces must equal the same program run eagerly, ranks must stay bit-identical, and the sparse user-row exchange
-must equal a dense all-reduce of the user table's gradient, and the reduce-scatter + sharded AdamW + all-gather path
++ row-sparse AdamW with exact catch-up must equal a dense all-reduce of the user table's gradient + dense AdamW, and the reduce-scatter + sharded AdamW + all-gather path
 must equal the all-reduce + replicated AdamW path.
 usage: torchrun --nproc-per-node N tests/_engine_dist_worker.py  (driven by tests/test_engine_gpu.py::test_engine_data_parallel_torchrun)"""
 import os
@@ -42,7 +42,7 @@ def main():
         opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0, modules=[model], capturable=True)
         eng = StepEngine(model, diff, opt, dist, batch_size=B, n_item=n_item, topk=k, topN=[10, k],
                          cap_train_nnz=int(train_sp.nnz), cap_gt_nnz=int(test_sp.nnz), graphs=graphs, nccl_sms=32,
-                         shard_optimizer=shard, shard_min_bytes=1 << 16)
+                         shard_optimizer=shard, shard_min_bytes=1 << 16, lazy_user_rows=sparse)
         eng.sparse_user_rows = eng.sparse_user_rows and sparse
         return model, diff, eng
 
@@ -64,6 +64,8 @@ def main():
             if not same:
                 print(f"rank {rank} step {s}: engine 0 vs {j}: loss {outs[0][0].item():.9f} vs {o[0].item():.9f}, "
                       f"top-k index agreement {(outs[0][1] == o[1]).float().mean().item():.4f}", flush=True)
+    for _, _, e in engines:
+        e.flush()  # row-sparse user-table updates: replay the pending zero-gradient steps before comparing weights
     torch.cuda.synchronize()
     ok = True
     for (n, pg), (_, pe), (_, pd) in zip(*[m.named_parameters() for m, _, _ in engines]):

@@ -270,3 +270,31 @@ def test_overlapped_optimizer_equals_serial():
         assert torch.equal(l0, l1) and torch.equal(i0, i1) and torch.equal(s0, s1)
     for p0, p1 in zip(outs[0][1], outs[1][1]):
         assert torch.equal(p0, p1)
+
+
+def test_lazy_user_rows_equal_dense_adamw():
+    """The user table's gradient has B non-zero rows per step. The engine's row-sparse AdamW (replay of the skipped
+    zero-gradient steps when a row is next used, gdmcf_adamw_rows_lazy) must equal the dense torch.optim.AdamW-style pass
+    over the whole table bit for bit: per-step results while training, and every parameter after flush()."""
+    make, train_dev, test_dev, _, _, B, n_user = _setup()
+    runs = []
+    for lazy in (True, False):
+        model, diff, eng = make(True, lazy_user_rows=lazy)
+        eng.load_resident(train_dev, test_dev, 0, B)
+        eng.capture(warmup=2)
+        res = []
+        for s in (1, 3, 1, 5, 2, 3, 7):  # users come back after different numbers of skipped steps
+            lo = (s * B) % (n_user - B)
+            eng.load_resident(train_dev, test_dev, lo, lo + B)
+            loss, idx, sums = eng.step()
+            res.append((loss.clone(), idx.clone(), sums.clone()))
+        if lazy:
+            stale = model.embedding_user.weight.detach().clone()
+        eng.flush()
+        torch.cuda.synchronize()
+        runs.append((res, {n: p.detach().clone() for n, p in model.named_parameters()}))
+    for (l0, i0, s0), (l1, i1, s1) in zip(runs[0][0], runs[1][0]):
+        assert torch.equal(l0, l1) and torch.equal(i0, i1) and torch.equal(s0, s1)
+    for n in runs[0][1]:
+        assert torch.equal(runs[0][1][n], runs[1][1][n]), n
+    assert not torch.equal(stale, runs[0][1]["embedding_user.weight"])  # the flush really had pending steps to replay

@@ -509,3 +509,47 @@ def test_lt_history_kernel_matches_reference_loop(K, T, B, H):
                 count[t] += 1
         K.lt_history_update(ts.cuda(), loss.cuda(), hist_d, count_d)
         assert torch.equal(hist_d.cpu(), hist) and torch.equal(count_d.cpu(), count)
+
+
+@pytest.mark.parametrize("rows,d,hidden", [(400, 1000, 512), (12, 32, 512), (70, 64, 128), (513, 104, 64)])
+def test_user_tower_vs_torch(K, rows, d, hidden):
+    """gdmcf_user_tower (conv1 + relu + conv2 + sumW mix + user norms in one launch, models/DNN.py:1093-1100,1288,1320)
+    against plain torch fp32 on the same bf16 operands; also: the counter block is left zeroed, a second launch on the
+    same workspace reproduces the first bit for bit, and a reduced CTA budget gives the same values."""
+    from gdmcf_b200.kernels import Bf16Mat
+    d3 = 3 * d
+    g = torch.Generator(device="cuda").manual_seed(5)
+    hc_f32 = torch.randn(rows, d3, generator=g, device="cuda") * 0.3
+    hc = K.cast_bf16(hc_f32)
+    w1 = Bf16Mat(_bf16_operand(hidden, d3, 21, 0.05), None, hidden, d3)
+    w2 = Bf16Mat(_bf16_operand(d3, hidden, 22, 0.05), None, d3, hidden)
+    b1 = torch.randn(hidden, generator=g, device="cuda") * 0.1
+    b2 = torch.randn(d3, generator=g, device="cuda") * 0.1
+    sumw = torch.tensor(0.7, device="cuda")
+    outs = []
+    for budget in (None, None, 37):
+        out = Bf16Mat.empty(rows, d3, "cuda", zero=False)
+        out.hi.fill_(float("nan"))
+        inv_u = torch.empty(rows, device="cuda")
+        g1 = torch.empty(rows, hidden, device="cuda")
+        g2 = torch.empty(rows, d3, device="cuda")
+        hcp = torch.empty(rows, d3, device="cuda")
+        K.user_tower(hc, hc_f32, w1, b1, w2, b2, sumw, rows, out=out, inv_u=inv_u, g1_f32=g1, g2_f32=g2, hcp_f32=hcp,
+                     max_ctas=budget)
+        torch.cuda.synchronize()
+        outs.append((out.hi.clone(), inv_u, g1, g2, hcp))
+    r_g1 = torch.relu(hc.hi[:, :d3].float() @ w1.hi[:, :d3].float().t() + b1)
+    r_g2 = r_g1.to(torch.bfloat16).float() @ w2.hi[:, :hidden].float().t() + b2
+    r_hcp = hc_f32 * 0.7 + r_g2 * (1.0 - sumw)
+    out_hi, inv_u, g1, g2, hcp = outs[0]
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()  # noqa: E731
+    assert rel(g1, r_g1) < 1e-5 and rel(g2, r_g2) < 2e-3 and rel(hcp, r_hcp) < 2e-3  # g2 sees bf16(g1) rounding flips
+    # the mix and the norm from the kernel's own g2 are exact fp32 arithmetic
+    assert torch.allclose(hcp, hc_f32 * sumw + g2 * (1.0 - sumw), rtol=1e-6, atol=1e-7)
+    assert rel(inv_u, 1.0 / hcp.norm(dim=1)) < 1e-6
+    assert torch.equal(out_hi[:, :d3], hcp.to(torch.bfloat16)) and (out_hi[:, d3:] == 0).all()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+    ws = [v for k, v in K._tower_ws.items() if k[2:] == (rows, d3, hidden, d3)][0]
+    assert int(ws[1][:12].abs().sum()) == 0  # counters zeroed again ([12:16] hold phase timestamps of CTA 0)
