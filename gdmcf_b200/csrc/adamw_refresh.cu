@@ -379,7 +379,13 @@ adamw_rows_lazy_kernel(float* __restrict__ p, float* __restrict__ m, float* __re
         const bool ok = c < cols;
         pv[j] = ok ? pr[c] : 0.f; mv[j] = ok ? mr[c] : 0.f; vv[j] = ok ? vr[c] : 0.f;
       }
-      for (int s0 = last + 1; s0 <= replay_end; s0 += LAZY_CHUNK) {
+      // a row that never received a gradient has zero moments: its zero-gradient steps change nothing (without weight
+      // decay), so the replay is skipped for the whole CTA when no thread holds a non-zero moment
+      bool live = weight_decay != 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) live = live || mv[j] != 0.f || vv[j] != 0.f;
+      const bool replay = __syncthreads_or(live ? 1 : 0) != 0;
+      for (int s0 = last + 1; replay && s0 <= replay_end; s0 += LAZY_CHUNK) {
         const int n = min(LAZY_CHUNK, replay_end - s0 + 1);
         __syncthreads();
         if (threadIdx.x < n) {  // bias corrections of step s0 + t, same double arithmetic as adamw_coef

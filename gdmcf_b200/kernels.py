@@ -319,10 +319,21 @@ def onehot_tables(w2: torch.Tensor, d: int, n_items: int, out=None):
     return base, delta
 
 
+_gather_ws: dict = {}
+
+
 def encode_onehot_gather(rowptr, col, users, n_rows: int, base, delta, d: int, out: torch.Tensor) -> None:
     require_cuda(rowptr, col, users, base, delta, out)
-    check(load().gdmcf_encode_onehot_gather(ptr(rowptr), ptr(col), ptr(users), n_rows, ptr(base), ptr(delta),
-                                            delta.stride(0), d, ptr(out), out.stride(0), stream()), "encode_onehot_gather")
+    lib = load()
+    key = (str(out.device), torch.cuda.current_stream().cuda_stream, n_rows, d)
+    ws = _gather_ws.get(key)
+    if ws is None:  # partial sums of the heavy users' row slices + per-row completion counters (left zeroed by the kernel)
+        ws = (torch.empty(lib.gdmcf_encode_onehot_gather_workspace_bytes(n_rows, d) // 4, dtype=torch.float32, device=out.device),
+              torch.zeros(n_rows, dtype=torch.int32, device=out.device))
+        _gather_ws[key] = ws
+    check(lib.gdmcf_encode_onehot_gather(ptr(rowptr), ptr(col), ptr(users), n_rows, ptr(base), ptr(delta), delta.stride(0), d,
+                                         ptr(out), out.stride(0), ptr(ws[0]), ws[0].numel() * 4, ptr(ws[1]), stream()),
+          "encode_onehot_gather")
 
 
 def time_bias_table(w_emb, b_emb, w_layer: torch.Tensor, n_in: int, bias, T: int, out=None):

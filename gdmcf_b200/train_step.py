@@ -79,13 +79,24 @@ def _mm3(a: Bf16Mat, b: Bf16Mat, m, n, k, **epi):
     K.gemm([a.hi, a.hi, a.lo], [b.hi, b.lo, b.hi], m, n, [k, k, k], **epi)
 
 
-def _bf16_T(x: Bf16Mat, rows, cols, dev) -> Bf16Mat:
-    """Transpose a bf16 operand [rows, cols] -> [cols, rows] (hi and lo)."""
-    out = Bf16Mat.empty(cols, rows, dev, x.lo is not None, zero=False)
+def _bf16_T(x: Bf16Mat, rows, cols, dev, extra_rows: int = 0) -> Bf16Mat:
+    """Transpose a bf16 operand [rows, cols] -> [cols (+ extra_rows), rows] (hi and lo); the extra rows are left for
+    the caller to fill (the time-embedding rows appended to a first layer's wgrad operand)."""
+    out = Bf16Mat.empty(cols + extra_rows, rows, dev, x.lo is not None, zero=False)
     K.transpose_bf16(x.hi, rows, cols, out.hi)
     if x.lo is not None:
         K.transpose_bf16(x.lo, rows, cols, out.lo)
     return out
+
+
+def _input_T_with_time_rows(model, A: Bf16Mat, emb_rows, B, n_in, e, dev) -> Bf16Mat:
+    """[n_in + e, B] wgrad operand of a first layer: the transposed (noised, dropped-out) input rows followed by the
+    transposed time-embedding rows emb(t_b) — `cat([x, emb])` of models/DNN.py:79/1240/1250 seen from the weight gradient.
+    One contraction then yields all n_in + e gradient columns (the e time columns used to be a separate 23 us kernel)."""
+    AT = _bf16_T(A, B, n_in, dev, extra_rows=e)
+    tail = Bf16Mat(AT.hi[n_in:], AT.lo[n_in:] if AT.lo is not None else None, e, B)
+    K.cast_bf16_transpose(emb_rows, with_lo=AT.lo is not None, out=tail)
+    return AT
 
 
 def _hand_over(model, grads: Dict[str, torch.Tensor], names):
@@ -286,21 +297,26 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     K.ew_binary(K.EW_TANH_BWD, dhU_tot, c.hc_f32[:, d:2 * d], B, d, out_f32=dhU_pre)
     dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)     # [d, B]
     dhU_preT = K.cast_bf16_transpose(dhU_pre, with_lo=lo)
-    A1T = _bf16_T(c.A1, B, I, dev)                          # [I, B]
-    A2T = _bf16_T(Bf16Mat(c.A2, None, B, 2 * I), B, 2 * I, dev)
     emb_table = K.time_bias_table(model.emb_layer.weight.detach(), model.emb_layer.bias.detach(),
                                   model.in_layers[0].weight.detach(), I, None, T)[1]   # [T, e]
     emb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
     temb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
     K.gather_rows(emb_table, c.ts, B, e, out_f32=emb_rows)
     K.gather_rows(_temb_table(model, T, dev), c.ts, B, e, out_f32=temb_rows)
+    A1T = _input_T_with_time_rows(model, c.A1, emb_rows, B, I, e, dev)                                    # [I + e, B]
+    A2T = _input_T_with_time_rows(model, Bf16Mat(c.A2, None, B, 2 * I), emb_rows, B, 2 * I, e, dev)       # [2I + e, B]
     d_emb = torch.empty(B, e, dtype=torch.float32, device=dev)
     for name, dpre, dpreT, AT, n_in, first in (("in_layers.0", dh_pre, dh_preT, A1T, I, True),
                                               ("in_layers2.0", dhU_pre, dhU_preT, A2T, 2 * I, False)):
         W = P[name + ".weight"]
         gW = _grad_buffer(W, model, name + ".weight")
-        _mm_auto(model, dpreT, AT, d, n_in, B, out_f32=gW)                                   # columns [0, n_in)
-        K.sgemm_small(dpre, emb_rows, gW[:, n_in:], d, e, B, trans_a=True)                   # time-embedding columns
+        if lo and AT.lo is None:
+            # fp32 mode, one-hot operand (exact in bf16, no lo part): its time rows would be rounded to bf16, so the e
+            # time-embedding columns keep their own fp32 product
+            _mm_auto(model, dpreT, AT, d, n_in, B, out_f32=gW)
+            K.sgemm_small(dpre, emb_rows, gW[:, n_in:], d, e, B, trans_a=True)
+        else:
+            _mm_auto(model, dpreT, AT, d, n_in + e, B, out_f32=gW)    # all columns: inputs [0, n_in) + time embedding
         grads[name + ".weight"] = gW
         grads[name + ".bias"] = K.colsum_f32(dpre, B, d)
         K.sgemm_small(dpre, _time_cols(model, name, W, n_in), d_emb, B, e, d, beta=0.0 if first else 1.0)
@@ -378,16 +394,15 @@ def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
     dh_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
     K.ew_binary(K.EW_TANH_BWD, dh, c.h_f32, B, d, out_f32=dh_pre)
     dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)
-    A1T = _bf16_T(c.A1, B, I, dev)
     W = P["in_layers.0.weight"]
     gW = _grad_buffer(W)
-    _mm_auto(model, dh_preT, A1T, d, I, B, out_f32=gW)
     emb_table = K.time_bias_table(model.emb_layer.weight.detach(), model.emb_layer.bias.detach(), W.detach(), I, None, T)[1]
     emb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
     temb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
     K.gather_rows(emb_table, c.ts, B, e, out_f32=emb_rows)
     K.gather_rows(_temb_table(model, T, dev), c.ts, B, e, out_f32=temb_rows)
-    K.sgemm_small(dh_pre, emb_rows, gW[:, I:], d, e, B, trans_a=True)
+    A1T = _input_T_with_time_rows(model, c.A1, emb_rows, B, I, e, dev)
+    _mm_auto(model, dh_preT, A1T, d, I + e, B, out_f32=gW)
     grads["in_layers.0.weight"] = gW
     grads["in_layers.0.bias"] = K.colsum_f32(dh_pre, B, d)
     d_emb = torch.empty(B, e, dtype=torch.float32, device=dev)

@@ -195,9 +195,13 @@ int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t* ts, float 
 /* Inference form of the one-hot encoder (models/DNN.py:1249-1251 with x_tU = one_hot(x0)):
  * S[r,:] = base[:] + sum_{i in row users[r]} delta[i,:], where base = sum_i W2[:,2i] and
  * delta[i,:] = W2[:,2i+1] - W2[:,2i] are fp32 tables prepared from in_layers2.0.weight. */
+/* workspace (gdmcf_encode_onehot_gather_workspace_bytes) + counters (int32 [n_rows], zero-initialised, left zeroed):
+ * optional; with them the rows of heavy users are gathered by several CTAs (deterministic slice-order reduction). */
+size_t gdmcf_encode_onehot_gather_workspace_bytes(int n_rows, int d);
 int gdmcf_encode_onehot_gather(const int32_t* rowptr, const int32_t* col, const int32_t* users, int n_rows,
                                const float* base, const float* delta, int64_t ld_delta, int d, float* out,
-                               int64_t ld_out, gdmcf_stream_t stream);
+                               int64_t ld_out, float* workspace, size_t workspace_bytes, int32_t* counters,
+                               gdmcf_stream_t stream);
 /* Builds base/delta from W2 fp32 [d, ld_w] (columns 2i, 2i+1 interleaved; models/DNN.py:1224). */
 int gdmcf_onehot_tables(const float* w2, int64_t ld_w, int d, int n_items, float* base, float* delta,
                         int64_t ld_delta, gdmcf_stream_t stream);

@@ -553,3 +553,29 @@ def test_user_tower_vs_torch(K, rows, d, hidden):
             assert torch.equal(a, b)
     ws = [v for k, v in K._tower_ws.items() if k[2:] == (rows, d3, hidden, d3)][0]
     assert int(ws[1][:12].abs().sum()) == 0  # counters zeroed again ([12:16] hold phase timestamps of CTA 0)
+
+
+def test_onehot_gather_heavy_rows(K):
+    """Rows of heavy users are gathered by several CTAs (slice partial sums + ordered reduction): values must match the
+    dense product, be reproducible bit for bit, and leave the completion counters zeroed."""
+    n_users, n_items, d = 40, 5000, 1000
+    rng = np.random.default_rng(3)
+    deg = np.array([3, 70, 64, 65, 1200, 0, 129, 2500] + [int(x) for x in rng.integers(1, 200, n_users - 8)])
+    rows = np.repeat(np.arange(n_users), deg)
+    cols = np.concatenate([np.sort(rng.choice(n_items, size=k, replace=False)) for k in deg] + [np.zeros(0, np.int64)])
+    rowptr = np.zeros(n_users + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum(deg)
+    rp, cl = torch.from_numpy(rowptr).cuda(), torch.from_numpy(cols.astype(np.int32)).cuda()
+    users = torch.arange(n_users, dtype=torch.int32, device="cuda")
+    W2 = torch.randn(d, 2 * n_items + 10, device="cuda") * 0.05
+    base, delta = K.onehot_tables(W2, d, n_items)
+    S1, S2 = torch.empty(n_users, d, device="cuda"), torch.empty(n_users, d, device="cuda")
+    K.encode_onehot_gather(rp, cl, users, n_users, base, delta, d, S1)
+    K.encode_onehot_gather(rp, cl, users, n_users, base, delta, d, S2)
+    dense = torch.zeros(n_users, n_items, device="cuda")
+    dense[torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()] = 1.0
+    x_U = torch.nn.functional.one_hot(dense.long(), 2).double().reshape(n_users, -1)
+    ref = (x_U @ W2[:, : 2 * n_items].double().t()).float()
+    assert ((S1 - ref).norm() / ref.norm()).item() < 1e-5 and torch.equal(S1, S2)
+    ws = [v for k, v in K._gather_ws.items() if k[2:] == (n_users, d)][0]
+    assert int(ws[1].abs().sum()) == 0
