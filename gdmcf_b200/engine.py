@@ -35,11 +35,14 @@ class StepEngine:
                  cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
                  rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
                  shard_min_bytes: int = 64 << 20, train: bool = True, overlap_sms: int = 0,
-                 lazy_user_rows: bool = True):
+                 lazy_user_rows: bool = True, rank: bool = True, sampling_steps: int = 0):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
         self.train = train  # False: denoise + rank only (BASELINE.json configs[2]); no gradients, no collectives
+        self.do_rank = rank or not train  # False: training step only (main.py's epoch loop, main.py:331-351)
+        self.sampling_steps = sampling_steps  # forward-process steps before the reverse loop (--sampling_steps, main.py:288)
+        self._res = None  # device-resident interaction matrices bound with bind_resident()
         # the item table's norm-term gradient (-E_i * ri^2 * c_i) is applied inside the AdamW pass instead of the wgrad
         # contraction's epilogue (saves a 412 MB read of E per step at the Yelp shape)
         self.defer_item_norm = hasattr(model, "embedding_item")
@@ -121,6 +124,20 @@ class StepEngine:
             if e > b:
                 cl[: e - b].copy_(src.col[b:e])
 
+    def bind_resident(self, x_dev, gt_dev=None, hist_dev=None, hist2_dev=None) -> None:
+        """Resident mode (call before capture): the step reads the batch's rows straight from device-resident interaction
+        matrices (data_utils.DeviceInteractions) through the user ids — x_dev: the model input rows (main.py:153-156),
+        gt_dev: ground truth of the metrics, hist_dev / hist2_dev: rows masked before top-k (main.py:299; default x_dev).
+        Per step only the B user ids change (load_users); nothing is copied or re-indexed."""
+        h1 = hist_dev if hist_dev is not None else x_dev
+        self._res = dict(x=(x_dev.rowptr, x_dev.col), gt=(gt_dev.rowptr, gt_dev.col) if gt_dev is not None else None,
+                         h1=(h1.rowptr, h1.col), h2=(hist2_dev.rowptr, hist2_dev.col) if hist2_dev is not None else None)
+
+    def load_users(self, users) -> None:
+        """Resident mode: global user ids int32 [B] (device or pinned host tensor) of the next step."""
+        assert self._res is not None and users.numel() == self.B
+        self.users.copy_(users, non_blocking=True)
+
     def load_host(self, users, tr, gt) -> None:
         """Pinned host tensors: users int32 [B]; tr / gt = (rowptr int32 [B+1] starting at 0, col int32 [nnz])."""
         self.users.copy_(users, non_blocking=True)
@@ -131,7 +148,29 @@ class StepEngine:
 
     # -- the step ----------------------------------------------------------------------------------
     def _batch(self) -> CsrBatch:
+        if self._res is not None:
+            return CsrBatch(self._res["x"][0], self._res["x"][1], self.users, self.n_item)
         return CsrBatch(self.tr_rowptr, self.tr_col, self.local_ids, self.n_item)
+
+    def _rank_and_metrics(self):
+        """p_sample -> history mask -> top-k -> metric sums (main.py:288-307) on the loaded batch."""
+        model, diff = self.model, self.diffusion
+        model.eval()
+        if not self.train and hasattr(model, "invalidate_time_tables"):
+            # an inference-only program may run after optimizer steps of another program (main.py: evaluation after an
+            # epoch): the bias tables are rebuilt inside the step; the bf16 operands are kept current by the optimizer pass
+            model.invalidate_time_tables()
+        batch = self._batch()
+        if self._res is not None:
+            idx = diff.rank(model, batch, self.k, hist=self._res["h1"], hist2=self._res["h2"], steps=self.sampling_steps,
+                            index=self.users)
+            gt = self._res["gt"]
+        else:
+            idx = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), steps=self.sampling_steps, index=self.users)
+            gt = (self.gt_rowptr, self.gt_col)
+        if gt is None:
+            return idx, None
+        return idx, evaluate_utils.metrics_from_device(idx, batch.users, gt[0], gt[1], self.topN)
 
     def _program(self):
         """The step as a generator. Between two yields everything is device work on the current stream (one CUDA graph
@@ -140,10 +179,7 @@ class StepEngine:
         yields and the whole step is a single graph."""
         model, diff, opt, G = self.model, self.diffusion, self.opt, self.dist.world_size
         if not self.train:
-            model.eval()
-            batch = self._batch()
-            idx = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
-            sums = evaluate_utils.metrics_from_device(idx, batch.users, self.gt_rowptr, self.gt_col, self.topN)
+            idx, sums = self._rank_and_metrics()
             self._result = (torch.zeros((), dtype=torch.float64, device=self.dev), idx, sums)
             return
         model.train()
@@ -192,10 +228,7 @@ class StepEngine:
                     K.gemm_set_sm_limit(max(2, _lib.load().gdmcf_num_sms() - self.nccl_sms))
 
         def rank_and_metrics():
-            model.eval()
-            batch = self._batch()
-            idx_ = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), index=self.users)
-            return idx_, evaluate_utils.metrics_from_device(idx_, batch.users, self.gt_rowptr, self.gt_col, self.topN)
+            return self._rank_and_metrics() if self.do_rank else (None, None)
 
         order = sorted(range(len(groups)), key=lambda gi: (0 if gi in self._small_keys else 1, gi))
         by_param = {id(sh["p"]): (n, sh) for n, sh in self._shards.items()}
@@ -369,11 +402,68 @@ class StepEngine:
             torch.cuda.set_stream(self._main_stream)
         return self._result
 
-    def capture(self, warmup: int = 3) -> None:
+    # -- state snapshot around the warm-up steps -------------------------------------------------------
+    def _snapshot(self):
+        opt, diff = self.opt, self.diffusion
+        snap = dict(params=[p.detach().clone() for p in self.model.parameters()],
+                    lt=(diff.Lt_history.clone(), diff.Lt_count.clone()),
+                    epoch=None if diff._epoch is None else diff._epoch.clone(),
+                    rng_calls=getattr(self.model, "_rng_calls", 0))
+        if opt is not None:
+            snap["step_dev"] = None if opt._step_dev is None else opt._step_dev.clone()
+            snap["state"] = {id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt.state[p].items()}
+                             for g in opt.param_groups for p in g["params"] if opt.state.get(p)}
+        return snap
+
+    def _restore(self, snap) -> None:
+        opt, diff = self.opt, self.diffusion
+        with torch.no_grad():
+            for p, v in zip(self.model.parameters(), snap["params"]):
+                p.copy_(v)
+            diff.Lt_history.copy_(snap["lt"][0]); diff.Lt_count.copy_(snap["lt"][1])
+            if diff._epoch is not None:
+                diff._epoch.zero_() if snap["epoch"] is None else diff._epoch.copy_(snap["epoch"])
+            if hasattr(self.model, "_rng_calls"):
+                self.model._rng_calls = snap["rng_calls"]
+            if opt is not None:
+                if opt._step_dev is not None:
+                    opt._step_dev.zero_() if snap["step_dev"] is None else opt._step_dev.copy_(snap["step_dev"])
+                for g in opt.param_groups:
+                    for p in g["params"]:
+                        st, old = opt.state.get(p), snap["state"].get(id(p))
+                        if not st:
+                            continue
+                        for k, v in st.items():  # tensors keep their storage (the captured graph holds their addresses)
+                            if torch.is_tensor(v):
+                                v.zero_() if old is None else v.copy_(old[k])
+                            else:
+                                st[k] = 0 if old is None else old[k]
+        # the captured step reads the bf16 operands / tables derived from the weights at fixed addresses and only rewrites
+        # them in its own optimizer pass: re-derive them in place from the restored weights
+        self.model.weights_updated()
+        by_id = {id(p): p for p in self.model.parameters()}
+        for pid, (kw, names) in self.model.refresh_specs().items():
+            K.refresh_derived(by_id[pid].data, **kw)
+            self.model.adopt_refreshed(by_id[pid], names)
+
+    def capture(self, warmup: int = 3, preserve_state: bool = False) -> None:
         """Eager warm-up on whatever the static inputs hold (call load_* first), then capture. The warm-up allocates the
         persistent operand buffers and optimizer state outside the graph pool and fills Lt_history; the first capture
-        needs at least one warm-up step (a re-capture of a warmed engine may pass 0)."""
+        needs at least one warm-up step (a re-capture of a warmed engine may pass 0). preserve_state: weights, optimizer
+        state, Lt_history and RNG counters are put back (in place) after the warm-up, so that the warm-up steps are not
+        part of the training run (main.py); the benchmark lets them count as training steps."""
+        snap = self._snapshot() if preserve_state and warmup > 0 else None
+        try:
+            self._capture(warmup)
+        finally:
+            if snap is not None:
+                self._restore(snap)
+
+    def _capture(self, warmup: int) -> None:
         lib = _lib.load()
+        if hasattr(self.model, "build_derived"):
+            with torch.no_grad():
+                self.model.build_derived()  # the captured optimizer pass refreshes what exists now (see build_derived)
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):

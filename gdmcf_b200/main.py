@@ -6,7 +6,10 @@ model-selection rule), rebuilt CSR-native on the B200 engine:
   * evaluate() (main.py:267-310) is fused: p_sample -> history mask -> top-K -> metric sums, all on the device;
   * `--n_user` replaces the hard-coded `n_user = 3000` (D3); 0 means all users;
   * data-parallel over logical user batches when launched under torchrun (gradient all-reduce + metric all-reduce
-    over NCCL; everything else is rank-local), see gdmcf_b200/dist_utils.py.
+    over NCCL; everything else is rank-local), see gdmcf_b200/dist_utils.py;
+  * by default the loop body and evaluate() are engine.StepEngine programs (the training step / the denoise + rank step
+    captured once as CUDA graphs and replayed per batch, overlapped collectives under torchrun); `--eager` issues the
+    same kernels call by call through the reference-shaped API (training_losses -> backward -> optimizer.step).
 """
 from __future__ import annotations
 
@@ -20,6 +23,7 @@ import torch
 
 from . import data_utils, dist_utils, evaluate_utils
 from .models import gaussian_diffusion as gd
+from .engine import StepEngine
 from .models.DNN import DNN, DNNOneHotEmbeddingGCN
 from .optim import FusedAdamW
 from .parse_args_util import parse_args
@@ -75,43 +79,80 @@ def build(args, n_user_rows, n_item, device):
     return diffusion, model
 
 
-def evaluate(diffusion, model, train_dev, gt_dev, hist_devs, n_user, batch_size, topN, sampling_steps, dist):
-    """main.py:267-310: rank the first floor(n_user / batch_size) * batch_size users (drop_last=True, :156)."""
+def evaluate(diffusion, model, train_dev, gt_dev, hist_devs, n_user, batch_size, topN, sampling_steps, dist, drop_last=True):
+    """main.py:267-310: rank the first floor(n_user / batch_size) * batch_size users (drop_last=True, :156); every user
+    with drop_last=False (the --tst_w_val loader, main.py:174)."""
     model.eval()
     k = topN[-1]
-    n_batches = n_user // batch_size
+    n_batches = n_user // batch_size if drop_last else -(-n_user // batch_size)
     sums = torch.zeros(len(topN), 4, dtype=torch.float64, device=train_dev.device)
     for b in range(dist.rank, n_batches, dist.world_size):
-        users = torch.arange(b * batch_size, (b + 1) * batch_size, dtype=torch.int32, device=train_dev.device)
+        users = torch.arange(b * batch_size, min((b + 1) * batch_size, n_user), dtype=torch.int32, device=train_dev.device)
         batch = train_dev.batch(users)
         idx = diffusion.rank(model, batch, k, hist=hist_devs[0].csr, hist2=hist_devs[1].csr if len(hist_devs) > 1 else None,
                              steps=sampling_steps)
         sums += evaluate_utils.metrics_from_device(idx, users, gt_dev.rowptr, gt_dev.col, topN)
     dist.all_reduce(sums)
-    return evaluate_utils.finalize_metrics(sums, n_batches * batch_size)
+    return evaluate_utils.finalize_metrics(sums, n_batches * batch_size if drop_last else n_user)
 
 
-def save_checkpoint(path, epoch, model, optimizer, diffusion, rng, best):
+def evaluate_engine(eng, n_user, batch_size, topN, dist, tail=None):
+    """evaluate() through a captured denoise + rank step (StepEngine, train=False, resident mode). tail: callable that
+    ranks the users the fixed-size batches leave over (--tst_w_val iterates without drop_last, main.py:174)."""
+    n_batches = n_user // batch_size
+    dev = eng.dev
+    sums = torch.zeros(len(topN), 4, dtype=torch.float64, device=dev)
+    for b in range(dist.rank, n_batches, dist.world_size):
+        eng.load_users(torch.arange(b * batch_size, (b + 1) * batch_size, dtype=torch.int32, device=dev))
+        _, _, s = eng.step()
+        sums += s
+    n_ranked = n_batches * batch_size
+    if tail is not None and n_ranked < n_user:
+        if dist.rank == 0:
+            sums += tail(n_ranked, n_user)
+        n_ranked = n_user
+    dist.all_reduce(sums)
+    return evaluate_utils.finalize_metrics(sums, n_ranked)
+
+
+def _gather_ranks(t, dist):
+    """[world_size, ...] copy of a per-rank tensor on every rank (checkpoints keep every rank's diffusion state)."""
+    if dist.world_size == 1:
+        return t.unsqueeze(0).cpu()
+    out = [torch.empty_like(t) for _ in range(dist.world_size)]
+    torch.distributed.all_gather(out, t.contiguous())
+    return torch.stack(out).cpu()
+
+
+def save_checkpoint(path, epoch, model, optimizer, diffusion, rng, best, dist):
     """Everything a bit-exact continuation needs: weights, AdamW moments and step counters, the
-    importance-sampling history, the device-resident RNG epoch, the shuffle generator and the model-selection state."""
+    importance-sampling history and the device-resident RNG epoch OF EVERY RANK (they are rank-local: each rank sees its
+    own batches and draws from its own Philox stream), the shuffle generator and the model-selection state.
+    Collective: every rank calls it, rank 0 writes."""
+    optimizer.flush_lazy()  # row-sparse user-table updates: replay the pending zero-gradient steps before saving
+    dev = diffusion.Lt_history.device
+    epoch_t = diffusion._epoch if diffusion._epoch is not None else torch.full((1,), -1, dtype=torch.int64, device=dev)
+    lt_h, lt_c, ep = (_gather_ranks(t, dist) for t in (diffusion.Lt_history, diffusion.Lt_count, epoch_t))
+    if dist.rank != 0:
+        return
     torch.save({"epoch": epoch, "model": model.state_dict(), "optimizer": optimizer.state_dict(),
                 "optimizer_step_dev": None if optimizer._step_dev is None else int(optimizer._step_dev.item()),
-                "Lt_history": diffusion.Lt_history.cpu(), "Lt_count": diffusion.Lt_count.cpu(),
-                "rng_epoch": None if diffusion._epoch is None else int(diffusion._epoch.item()),
+                "world_size": dist.world_size, "Lt_history": lt_h, "Lt_count": lt_c, "rng_epoch": ep,
                 "shuffle_rng": rng.bit_generator.state, "best": best}, path)
 
 
-def load_checkpoint(path, model, optimizer, diffusion, rng, device):
+def load_checkpoint(path, model, optimizer, diffusion, rng, device, dist):
     ck = torch.load(path, map_location="cpu", weights_only=False)
     model.load_state_dict(ck["model"])
     model.weights_updated()
     optimizer.load_state_dict(ck["optimizer"])
     if ck["optimizer_step_dev"] is not None:
         optimizer._step_dev = torch.tensor([ck["optimizer_step_dev"]], dtype=torch.int64, device=device)
-    diffusion.Lt_history = ck["Lt_history"].to(device)
-    diffusion.Lt_count = ck["Lt_count"].to(device)
-    if ck["rng_epoch"] is not None:
-        diffusion._epoch = torch.tensor([ck["rng_epoch"]], dtype=torch.int64, device=device)
+    r = dist.rank if ck.get("world_size", 1) == dist.world_size else 0  # another world size: every rank starts from rank 0's
+    diffusion.Lt_history = ck["Lt_history"][r].to(device)
+    diffusion.Lt_count = ck["Lt_count"][r].to(device)
+    if int(ck["rng_epoch"][r]) >= 0:
+        diffusion._epoch = ck["rng_epoch"][r].reshape(1).to(device)
     rng.bit_generator.state = ck["shuffle_rng"]
     return ck["epoch"], ck["best"]
 
@@ -148,7 +189,9 @@ def main(args):
     diffusion, model = build(args, n_rows, n_item, device)
     diffusion.seed = model.seed = args.random_seed + 1000 * dist.rank
     dist.broadcast_parameters(model)
-    optimizer = FusedAdamW(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, modules=[model])
+    use_engine = not args.eager
+    optimizer = FusedAdamW(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, modules=[model],
+                           capturable=use_engine)
     print("models ready.")
     param_num = sum(p.nelement() for p in model.parameters()) + sum(p.nelement() for p in diffusion.parameters())
     print("Number of all parameters:", param_num)
@@ -162,11 +205,71 @@ def main(args):
     rng = np.random.default_rng(args.random_seed)
     start_epoch = 1
     if args.resume:
-        last, best = load_checkpoint(args.resume, model, optimizer, diffusion, rng, device)
+        last, best = load_checkpoint(args.resume, model, optimizer, diffusion, rng, device, dist)
         best_recall, best_epoch, best_test_results = best
         start_epoch = last + 1
         print('resumed from', args.resume, 'after epoch', last)
+    # test-time input rows: the training rows, or training + validation rows with --tst_w_val (main.py:172-175,354-358)
+    tv_dev = None
+    if args.tst_w_val:
+        tv_dev = data_utils.DeviceInteractions((train_data[:n_rows] + valid_y_data[:n_rows]).astype(bool).astype('float64'), device)
+    train_eng = valid_eng = test_eng = None
+    if use_engine:
+        # the loop body (main.py:331-351) and evaluate() (main.py:267-310) as captured steps; the warm-up steps the capture
+        # needs are rolled back (preserve_state), so the run starts from the same state as the eager loop
+        if n_batches > 0:
+            train_eng = StepEngine(model, diffusion, optimizer, dist, batch_size=B, n_item=n_item, topk=topN[-1], topN=topN,
+                                   cap_train_nnz=1, cap_gt_nnz=1, reweight=args.reweight, rank=False, nccl_sms=args.nccl_sms)
+            train_eng.bind_resident(train_dev)
+            train_eng.load_users(torch.arange(B, dtype=torch.int32, device=device))
+            train_eng.capture(warmup=2, preserve_state=True)
+        if n_rows // eval_B > 0:
+            def mk():
+                return StepEngine(model, diffusion, None, dist_utils.Dist(), batch_size=eval_B, n_item=n_item, topk=topN[-1],
+                                  topN=topN, cap_train_nnz=1, cap_gt_nnz=1, train=False, sampling_steps=args.sampling_steps)
+            valid_eng, test_eng = mk(), mk()
+            valid_eng.bind_resident(train_dev, gt_dev=valid_dev, hist_dev=train_dev)
+            if args.tst_w_val:
+                test_eng.bind_resident(tv_dev, gt_dev=test_dev, hist_dev=tv_dev)
+            else:
+                test_eng.bind_resident(train_dev, gt_dev=test_dev, hist_dev=train_dev, hist2_dev=valid_dev)
+            for e in (valid_eng, test_eng):
+                e.load_users(torch.arange(eval_B, dtype=torch.int32, device=device))
+                e.capture(warmup=1, preserve_state=True)
+
+    def tail_rows(x_dev, gt_dev, hists):
+        def run(lo, hi):  # users the fixed-size batches leave over: ranked call by call
+            users = torch.arange(lo, hi, dtype=torch.int32, device=device)
+            idx = diffusion.rank(model, x_dev.batch(users), topN[-1], hist=hists[0].csr,
+                                 hist2=hists[1].csr if len(hists) > 1 else None, steps=args.sampling_steps)
+            return evaluate_utils.metrics_from_device(idx, users, gt_dev.rowptr, gt_dev.col, topN)
+        return run
+
+    def run_evaluation():
+        model.eval()
+        if train_eng is not None:
+            train_eng.flush()  # row-sparse user-table updates: every user's row must be current before all users are ranked
+        if valid_eng is not None:
+            valid = evaluate_engine(valid_eng, n_rows, eval_B, topN, dist)
+        else:
+            valid = evaluate(diffusion, model, train_dev, valid_dev, [train_dev], n_rows, eval_B, topN, args.sampling_steps, dist)
+        if args.tst_w_val:
+            if test_eng is not None:
+                test = evaluate_engine(test_eng, n_rows, eval_B, topN, dist, tail=tail_rows(tv_dev, test_dev, [tv_dev]))
+            else:
+                test = evaluate(diffusion, model, tv_dev, test_dev, [tv_dev], n_rows, eval_B, topN, args.sampling_steps, dist,
+                                drop_last=False)
+        elif test_eng is not None:
+            test = evaluate_engine(test_eng, n_rows, eval_B, topN, dist)
+        else:
+            test = evaluate(diffusion, model, train_dev, test_dev, [train_dev, valid_dev], n_rows, eval_B, topN,
+                            args.sampling_steps, dist)
+        return valid, test
+
     print("Start training...")
+    stats = {"train_s": [], "eval_s": [], "users_per_epoch": (n_batches - n_batches % dist.world_size) * B,
+             "users_per_eval": 2 * (n_rows // eval_B) * eval_B, "engine": use_engine}
+    main.last_stats = stats  # wall-clock seconds per epoch of training / per evaluation (valid + test), for callers and tests
     for epoch in range(start_epoch, args.epochs + 1):
         if epoch - best_epoch >= 200:
             print('-' * 18)
@@ -179,6 +282,11 @@ def main(args):
         # data parallel: G consecutive logical batches form one optimizer step
         for b0 in range(0, n_batches - n_batches % dist.world_size, dist.world_size):
             b = b0 + dist.rank
+            if train_eng is not None:
+                train_eng.load_users(perm[b * B:(b + 1) * B])
+                loss, _, _ = train_eng.step()
+                total_loss += loss
+                continue
             batch = train_dev.batch(perm[b * B:(b + 1) * B])
             optimizer.zero_grad()
             losses = diffusion.training_losses(model, batch, args.reweight, index=batch.users)
@@ -188,11 +296,13 @@ def main(args):
             dist.all_reduce_gradients(model)
             optimizer.step(grad_scale=1.0 / dist.world_size)
 
+        torch.cuda.synchronize(device)
+        train_s = time.time() - start_time  # the epoch's training steps alone (evaluation below is timed separately)
         if epoch % args.eval_every == 0:
-            valid_results = evaluate(diffusion, model, train_dev, valid_dev, [train_dev], n_rows, eval_B, topN,
-                                     args.sampling_steps, dist)
-            test_results = evaluate(diffusion, model, train_dev, test_dev, [train_dev, valid_dev], n_rows, eval_B, topN,
-                                    args.sampling_steps, dist)
+            t_eval = time.time()
+            valid_results, test_results = run_evaluation()
+            torch.cuda.synchronize(device)
+            stats["eval_s"].append(time.time() - t_eval)
             evaluate_utils.print_results(None, valid_results, test_results)
             sys.stdout.flush()
             if valid_results[2][1] > best_recall:  # NDCG@topN[1] despite the name (main.py:362-363)
@@ -202,9 +312,10 @@ def main(args):
                     model_path = os.path.join(out_path, 'model.pth')
                     print('model_path:', model_path)
                     torch.save(model, model_path)
-        if args.checkpoint_every and epoch % args.checkpoint_every == 0 and dist.rank == 0:
+        if args.checkpoint_every and epoch % args.checkpoint_every == 0:
             save_checkpoint(os.path.join(out_path, 'checkpoint.pt'), epoch, model, optimizer, diffusion, rng,
-                            (best_recall, best_epoch, best_test_results))
+                            (best_recall, best_epoch, best_test_results), dist)
+        stats["train_s"].append(train_s)
         print("Runing Epoch {:03d} ".format(epoch) + 'train loss {:.4f}'.format(float(total_loss)) + " costs " +
               time.strftime("%H: %M: %S", time.gmtime(time.time() - start_time)))
         print('---' * 18)
@@ -212,6 +323,8 @@ def main(args):
     print('===' * 18)
     print("End. Best Epoch {:03d} ".format(best_epoch))
     evaluate_utils.print_results(None, None, best_test_results)
+    if train_eng is not None:
+        train_eng.flush()
     main.last_model = model  # handle for callers / tests (the reference keeps everything local to main())
     print("End time: ", time.strftime('%Y-%m-%d %H:%M:%S', time.localtime(time.time())))
     dist.shutdown()

@@ -70,6 +70,12 @@ class _OperandCache:
         if hit is not None:
             self._items[name] = ((self.epoch,) + tuple((p._version, p.data_ptr()) for p in params), hit[1])
 
+    def invalidate(self, prefix: str) -> None:
+        """Mark the entries whose name starts with `prefix` stale; their storage is kept and refreshed in place."""
+        for name, (ver, val) in list(self._items.items()):
+            if name.startswith(prefix):
+                self._items[name] = (None, val)
+
     def clear(self):
         self._items.clear()
 
@@ -115,6 +121,16 @@ class _EngineModule(nn.Module):
     def refresh_specs(self) -> Dict[int, tuple]:
         """id(param) -> (kwargs for kernels.adamw_refresh, cache names it refreshes). Overridden per backbone."""
         return {}
+
+    def build_derived(self) -> None:
+        """Build every tensor the contractions derive from the weights (training- AND inference-side). A captured training
+        step refreshes, in its optimizer pass, exactly the derived tensors that exist when it is captured; an
+        inference-only program captured later relies on that refresh. Overridden per backbone."""
+
+    def invalidate_time_tables(self) -> None:
+        """The per-timestep bias tables are derived from emb_layer and the first layers' time columns and are not part of
+        the optimizer's fused refresh: rebuild them (in place) at the next use."""
+        self._ops.invalidate("tb")
 
     def adopt_refreshed(self, param, names) -> None:
         for n in names:
@@ -203,6 +219,10 @@ class DNN(_EngineModule):
         return self._ops.get(f"tb{T}", [self.emb_layer.weight, self.emb_layer.bias, l0.weight, l0.bias],
                              lambda prev: K.time_bias_table(self.emb_layer.weight.detach(), self.emb_layer.bias.detach(),
                                                             l0.weight.detach(), self.n_item, l0.bias.detach(), T, out=prev))[0]
+
+    def build_derived(self) -> None:
+        self._weight_operand("in0", self.in_layers[0].weight, cols=self.n_item)
+        self._weight_operand("out0", self.out_layers[0].weight)
 
     def refresh_specs(self):
         pr, out = self.precision, {}
@@ -391,6 +411,14 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
             return inv
         inv = self._ops.get("E.inv", [E], build_inv)
         return e_op, inv
+
+    def build_derived(self) -> None:
+        self._weight_operand("in0", self.in_layers[0].weight, cols=self.n_item)
+        self._weight_operand("in2", self.in_layers2[0].weight, cols=2 * self.n_item)
+        self._weight_operand("gcn1", self.gcn_model.conv1.lin.weight)
+        self._weight_operand("gcn2", self.gcn_model.conv2.lin.weight)
+        self._onehot_tables()   # inference-side: sparse one-hot encoder tables
+        self._item_operands()   # item table operand + inverse norms
 
     def refresh_specs(self):
         pr, out = self.precision, {}

@@ -118,6 +118,8 @@ class FusedAdamW(torch.optim.Optimizer):
             st["last_step"] = torch.full((p.shape[0],), int(st["step"]), dtype=torch.int32, device=p.device)
             if self._capturable and self._step_dev is not None:
                 st["last_step"] += (self._step_dev.to(torch.int32) - int(st["step"]))
+        elif st["last_step"].dtype != torch.int32:  # Optimizer.load_state_dict casts state tensors to the parameter's dtype
+            st["last_step"] = st["last_step"].to(torch.int32)
         self._lazy[id(p)] = p
         group = next(g for g in self.param_groups if any(q is p for q in g["params"]))
         b1, b2 = group["betas"]

@@ -2,7 +2,7 @@
 (configargparse is not a dependency). Differences, all fixes of defects listed in SURVEY.md §0:
 `-c/--config` is optional and merged as defaults (D10); `--dims` accepts `--dims 1000`, repeated flags, and the
 README's `--dims=[1000]` (D11); boolean flags parse real booleans (D13). Added flags: --n_user (D3: the
-reference hard-codes 3000; 0 = all users), --precision, --eval_batch_size, --synthetic,
+reference hard-codes 3000; 0 = all users), --precision, --eval_batch_size, --synthetic, --eager, --nccl_sms,
 --checkpoint_every / --resume (the reference only pickles the best model, main.py:375)."""
 from __future__ import annotations
 
@@ -74,6 +74,9 @@ def build_parser():
     parser.add_argument('--eval_every', type=int, default=5)
     parser.add_argument('--checkpoint_every', type=int, default=0, help='write <out_path>/checkpoint.pt every N epochs (0 = never)')
     parser.add_argument('--resume', type=str, default='', help='checkpoint.pt to continue from (weights, AdamW state, Lt_history, RNG)')
+    parser.add_argument('--eager', action='store_true',
+                        help='run the loop call by call through the reference-shaped API instead of the captured StepEngine programs')
+    parser.add_argument('--nccl_sms', type=int, default=32, help='torchrun: SMs the contractions leave to NCCL while collectives are in flight')
     parser.add_argument('--synthetic', type=str, default='', help="'yelp' | 'amazon' | 'U,I,pairs': generate data instead of loading")
     return parser
 

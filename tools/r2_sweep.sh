@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python bench.py --steps 30 --no_cpu_baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ms',d['ms_per_step'],'frac',d['roofline']['frac'],'launches',d['launches_per_step'])"
-python bench.py --steps 30 --no_cpu_baseline --mode rank 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('rank ms',d['ms_per_step'])"
+timeout 1200 python -m pytest tests/test_main_gpu.py tests/test_engine_gpu.py -x -q -s > gpurun_out/main_test.log 2>&1
+grep -n "main.py yelp shape" gpurun_out/main_test.log; tail -25 gpurun_out/main_test.log
