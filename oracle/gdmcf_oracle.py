@@ -213,30 +213,60 @@ class _GCNConvParams(nn.Module):
 
 
 class _LayerGCNParams(nn.Module):
-    def __init__(self, i, h, o):
+    """LayerGCN.__init__ (models/DNN.py:1078-1086): gcnLayerNum == 1 builds a single in -> out convolution, every other
+    value builds conv1 (in -> hidden) and conv2 (hidden -> out) (gcnLayerNum == 0 builds them too but never calls them)."""
+
+    def __init__(self, i, h, o, n_layers: int = 2):
         super().__init__()
-        self.conv1 = _GCNConvParams(i, h)
-        self.conv2 = _GCNConvParams(h, o)
+        self.n_layers = n_layers
+        if n_layers == 1:
+            self.conv1 = _GCNConvParams(i, o)
+        else:
+            self.conv1 = _GCNConvParams(i, h)
+            self.conv2 = _GCNConvParams(h, o)
 
 
 def gcn_user_rows(gcn: _LayerGCNParams, hc: torch.Tensor) -> torch.Tensor:
-    """LayerGCN.forward (models/DNN.py:1093-1103, gcnLayerNum == 2) restricted to the user rows.
+    """LayerGCN.forward (models/DNN.py:1093-1103) restricted to the user rows.
     Edges are user -> item only (DNN.py:1217-1219) and GCNConv aggregates at the target, so a user node receives
     only its own self loop with normalisation deg^-1/2 * 1 * deg^-1/2 = 1: conv(x)[user] = x W^T + b.
     relu then LeakyReLU(0.1) (:1097-1098) is relu. PARITY UNPINNED against real torch_geometric (absent)."""
     h = F.linear(hc, gcn.conv1.lin.weight) + gcn.conv1.bias
+    if getattr(gcn, "n_layers", 2) == 1:
+        return h  # gcnLayerNum == 1: conv1 only, no activation (:1095-1096)
     h = F.leaky_relu(torch.relu(h), 0.1)
     return F.linear(h, gcn.conv2.lin.weight) + gcn.conv2.bias
+
+
+def gcn_all_rows(gcn: _LayerGCNParams, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """LayerGCN.forward on ALL B + I nodes with the edge set (models/DNN.py:1093-1103, 1277-1280): restated GCNConv
+    (torch_geometric 2.5.3 defaults: self loops added, symmetric in-degree normalisation, aggregation at the target).
+    out[i] = sum_{j -> i} deg_j^-1/2 deg_i^-1/2 (x_j W^T) + b, deg = in-degree including the self loop."""
+    def conv(c, x):
+        n = x.shape[0]
+        row, col = edge_index[0], edge_index[1]
+        ar = torch.arange(n)
+        row, col = torch.cat([row, ar]), torch.cat([col, ar])
+        deg = torch.zeros(n, dtype=x.dtype).scatter_add_(0, col, torch.ones(col.numel(), dtype=x.dtype))
+        dis = deg.pow(-0.5)
+        w = dis[row] * dis[col]
+        h = F.linear(x, c.lin.weight)
+        return torch.zeros_like(h).index_add_(0, col, h[row] * w[:, None]) + c.bias
+    h = conv(gcn.conv1, x)
+    if getattr(gcn, "n_layers", 2) == 1:
+        return h
+    return conv(gcn.conv2, F.leaky_relu(torch.relu(h), 0.1))
 
 
 class OracleGDMCF(nn.Module):
     """DNNOneHotEmbeddingGCN (models/DNN.py:1105-1327), noise_type=0, gcnLayerNum=2, graph-free closed form."""
 
-    def __init__(self, in_dims, out_dims, emb_size, item_num, user_num, norm=False, dropout=0.5):
+    def __init__(self, in_dims, out_dims, emb_size, item_num, user_num, norm=False, dropout=0.5, noise_type=0, gcnLayerNum=2):
         super().__init__()
         in_dims, out_dims = list(in_dims), list(out_dims)
         assert out_dims[0] == in_dims[-1]
         self.time_emb_dim, self.norm, self.p = emb_size, norm, dropout
+        self.noise_type, self.gcnLayerNum = noise_type, gcnLayerNum  # ablation switches (DNN.py:1236-1259, :1278)
         in_dims2 = list(in_dims)
         in_dims2[0] *= 2
         self.emb_layer = nn.Linear(emb_size, emb_size)
@@ -251,7 +281,7 @@ class OracleGDMCF(nn.Module):
         e_item = in_t[-1] + e_user + in_t2[-1]
         self.embedding_item = nn.Embedding(item_num, e_item)
         self.embedding_user = nn.Embedding(user_num, e_user)
-        self.gcn_model = _LayerGCNParams(e_item, 512, e_item)
+        self.gcn_model = _LayerGCNParams(e_item, 512, e_item, gcnLayerNum)
         for l in list(self.in_layers) + list(self.in_layers2) + list(self.out_layers) + [self.emb_layer]:
             _init_linear(l)
         nn.init.xavier_uniform_(self.embedding_item.weight)
@@ -265,17 +295,21 @@ class OracleGDMCF(nn.Module):
             x, x_U = F.normalize(x), F.normalize(x_U)
         x = _dropout(x, keep_x, self.p)
         x_U = _dropout(x_U, keep_xU, self.p)
-        h = torch.cat([x, emb], dim=-1)
+        # noise_type 1: the continuous branch is fed the first n_item columns of the INTERLEAVED one-hot matrix (:1236-1237);
+        # noise_type 2: the one-hot branch is fed [x, x] (:1246-1247); both zero the contrastive loss (:1258-1259)
+        h = torch.cat([x_U[:, :x.shape[1]] if self.noise_type == 1 else x, emb], dim=-1)
         for layer in self.in_layers:
             h = torch.tanh(layer(h))
-        h_U = torch.cat([x_U, emb], dim=-1)
+        h_U = torch.cat([x, x, emb] if self.noise_type == 2 else [x_U, emb], dim=-1)
         for layer in self.in_layers2:
             h_U = torch.tanh(layer(h_U))
         closs = nt_xent_loss(h, h_U) if RCloss else None
+        if closs is not None and self.noise_type != 0:
+            closs = closs * 0
         e_item = self.embedding_item.weight
         e_user = self.embedding_user(index)
         hc = torch.cat([h, h_U, e_user], dim=1)
-        g = gcn_user_rows(self.gcn_model, hc)
+        g = gcn_user_rows(self.gcn_model, hc) if self.gcnLayerNum > 0 else hc  # :1278: no GCN at all with 0 layers
         hc = hc * self.sumW + g * (1 - self.sumW)  # DNN.py:1288
         user_norms = torch.norm(hc, dim=1, keepdim=True)  # DNN.py:1320-1325
         item_norms = torch.norm(e_item, dim=1)
@@ -288,7 +322,8 @@ class OracleGDMCF(nn.Module):
 # --------------------------------------------------------------------------------------------------------
 class OracleDiffusion:
     def __init__(self, noise_schedule="linear-var", noise_scale=0.01, noise_min=0.001, noise_max=0.01, steps=5,
-                 history_num_per_term=10, discrete=0.9995, CatOneHot=True, indexIn=True):
+                 history_num_per_term=10, discrete=0.9995, CatOneHot=True, indexIn=True, mean_type="x0"):
+        self.mean_type = mean_type  # "x0" (ModelMeanType.START_X) or "eps" (EPSILON), gaussian_diffusion.py:10-12
         self.sch = Schedule(noise_schedule, noise_scale, noise_min, noise_max, steps)
         self.steps, self.noise_scale, self.discrete = steps, noise_scale, discrete
         self.CatOneHot, self.indexIn = CatOneHot, indexIn
@@ -343,9 +378,20 @@ class OracleDiffusion:
             x_tU = None
             out = model(x_t, ts, keep_x=keep_x)
         assert out.shape == x_start.shape
-        mse = ((x_start - out) ** 2).mean(dim=1)
-        weight = self.sch.reweight(ts) if reweight else torch.ones(len(ts))
-        loss = weight * mse
+        target = x_start if self.mean_type == "x0" else noise           # :895-898
+        mse = ((target - out) ** 2).mean(dim=1)
+        lossv = mse
+        if not reweight:
+            weight = torch.ones(len(ts))
+        elif self.mean_type == "x0":
+            weight = self.sch.reweight(ts)
+        else:  # :924-928
+            sch = self.sch
+            weight = (1 - sch.alphas_cumprod[ts]) / ((1 - sch.alphas_cumprod_prev[ts]) ** 2 * (1 - sch.betas[ts]))
+            weight = torch.where(ts == 0, 1.0, weight)
+            likelihood = ((x_start - self.predict_xstart_from_eps(x_t, ts, out)) ** 2 / 2.0).mean(dim=1)
+            lossv = torch.where(ts == 0, likelihood, mse)
+        loss = weight * lossv
         self.update_history(ts, loss)
         loss = loss / pt
         if closs is not None:
@@ -353,7 +399,14 @@ class OracleDiffusion:
         return {"loss": loss, "model_output": out, "mse": mse, "closs": closs, "x_t": x_t, "x_tU": x_tU}
 
     # -- gaussian_diffusion.py:668-768, :1041-1103 (graph bookkeeping :710-729 cannot affect user rows: omitted)
-    def p_sample(self, model, x_start, sampling_steps, index=None, noise=None, ts_u_keep=None):
+    def predict_xstart_from_eps(self, x_t, t, eps):
+        """gaussian_diffusion.py:1106-1111."""
+        return (extract(self.sch.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t
+                - extract(self.sch.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * eps)
+
+    def p_sample(self, model, x_start, sampling_steps, index=None, noise=None, ts_u_keep=None, sampling_noise=None):
+        """sampling_noise: None (= sampling_noise False) or the list of N(0,1) draws of the reverse steps, one [B, I]
+        tensor per step in the order t = T-1 .. 0 (:745-750; the t = 0 draw is made but masked out)."""
         assert sampling_steps <= self.steps, "Too much steps in inference."
         B = x_start.shape[0]
         if self.CatOneHot:
@@ -376,9 +429,17 @@ class OracleDiffusion:
             if self.noise_scale == 0.0:
                 x_t = out
                 continue
-            # p_mean_variance (START_X) + q_posterior_mean_variance; sampling_noise=False -> x_t = mean
-            x_t = (extract(self.sch.posterior_mean_coef1, t, x_t.shape) * out
-                   + extract(self.sch.posterior_mean_coef2, t, x_t.shape) * x_t)
+            # p_mean_variance + q_posterior_mean_variance (:1041-1103); sampling_noise=False -> x_t = mean
+            pred = out if self.mean_type == "x0" else self.predict_xstart_from_eps(x_t, t, out)
+            mean = (extract(self.sch.posterior_mean_coef1, t, x_t.shape) * pred
+                    + extract(self.sch.posterior_mean_coef2, t, x_t.shape) * x_t)
+            if sampling_noise is not None:
+                z = sampling_noise[self.steps - 1 - i]
+                nonzero = (t != 0).float().view(-1, 1)
+                logvar = extract(self.sch.posterior_log_variance_clipped, t, x_t.shape)
+                x_t = mean + nonzero * torch.exp(0.5 * logvar) * z
+            else:
+                x_t = mean
         return x_t
 
 
