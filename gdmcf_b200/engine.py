@@ -35,13 +35,14 @@ class StepEngine:
                  cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
                  rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
                  shard_min_bytes: int = 64 << 20, train: bool = True, overlap_sms: int = 0,
-                 lazy_user_rows: bool = True, rank: bool = True, sampling_steps: int = 0):
+                 lazy_user_rows: bool = True, rank: bool = True, sampling_steps: int = 0, sampling_noise: bool = False):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
         self.train = train  # False: denoise + rank only (BASELINE.json configs[2]); no gradients, no collectives
         self.do_rank = rank or not train  # False: training step only (main.py's epoch loop, main.py:331-351)
         self.sampling_steps = sampling_steps  # forward-process steps before the reverse loop (--sampling_steps, main.py:288)
+        self.sampling_noise = sampling_noise  # --sampling_noise: stochastic reverse steps (gaussian_diffusion.py:745-750)
         self._res = None  # device-resident interaction matrices bound with bind_resident()
         # the item table's norm-term gradient (-E_i * ri^2 * c_i) is applied inside the AdamW pass instead of the wgrad
         # contraction's epilogue (saves a 412 MB read of E per step at the Yelp shape)
@@ -163,10 +164,11 @@ class StepEngine:
         batch = self._batch()
         if self._res is not None:
             idx = diff.rank(model, batch, self.k, hist=self._res["h1"], hist2=self._res["h2"], steps=self.sampling_steps,
-                            index=self.users)
+                            index=self.users, sampling_noise=self.sampling_noise)
             gt = self._res["gt"]
         else:
-            idx = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), steps=self.sampling_steps, index=self.users)
+            idx = diff.rank(model, batch, self.k, hist=(self.tr_rowptr, self.tr_col), steps=self.sampling_steps, index=self.users,
+                            sampling_noise=self.sampling_noise)
             gt = (self.gt_rowptr, self.gt_col)
         if gt is None:
             return idx, None

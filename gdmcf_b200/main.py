@@ -79,7 +79,8 @@ def build(args, n_user_rows, n_item, device):
     return diffusion, model
 
 
-def evaluate(diffusion, model, train_dev, gt_dev, hist_devs, n_user, batch_size, topN, sampling_steps, dist, drop_last=True):
+def evaluate(diffusion, model, train_dev, gt_dev, hist_devs, n_user, batch_size, topN, sampling_steps, dist, drop_last=True,
+             sampling_noise=False):
     """main.py:267-310: rank the first floor(n_user / batch_size) * batch_size users (drop_last=True, :156); every user
     with drop_last=False (the --tst_w_val loader, main.py:174)."""
     model.eval()
@@ -90,7 +91,7 @@ def evaluate(diffusion, model, train_dev, gt_dev, hist_devs, n_user, batch_size,
         users = torch.arange(b * batch_size, min((b + 1) * batch_size, n_user), dtype=torch.int32, device=train_dev.device)
         batch = train_dev.batch(users)
         idx = diffusion.rank(model, batch, k, hist=hist_devs[0].csr, hist2=hist_devs[1].csr if len(hist_devs) > 1 else None,
-                             steps=sampling_steps)
+                             steps=sampling_steps, sampling_noise=sampling_noise)
         sums += evaluate_utils.metrics_from_device(idx, users, gt_dev.rowptr, gt_dev.col, topN)
     dist.all_reduce(sums)
     return evaluate_utils.finalize_metrics(sums, n_batches * batch_size if drop_last else n_user)
@@ -226,7 +227,8 @@ def main(args):
         if n_rows // eval_B > 0:
             def mk():
                 return StepEngine(model, diffusion, None, dist_utils.Dist(), batch_size=eval_B, n_item=n_item, topk=topN[-1],
-                                  topN=topN, cap_train_nnz=1, cap_gt_nnz=1, train=False, sampling_steps=args.sampling_steps)
+                                  topN=topN, cap_train_nnz=1, cap_gt_nnz=1, train=False, sampling_steps=args.sampling_steps,
+                                  sampling_noise=args.sampling_noise)
             valid_eng, test_eng = mk(), mk()
             valid_eng.bind_resident(train_dev, gt_dev=valid_dev, hist_dev=train_dev)
             if args.tst_w_val:
@@ -241,7 +243,8 @@ def main(args):
         def run(lo, hi):  # users the fixed-size batches leave over: ranked call by call
             users = torch.arange(lo, hi, dtype=torch.int32, device=device)
             idx = diffusion.rank(model, x_dev.batch(users), topN[-1], hist=hists[0].csr,
-                                 hist2=hists[1].csr if len(hists) > 1 else None, steps=args.sampling_steps)
+                                 hist2=hists[1].csr if len(hists) > 1 else None, steps=args.sampling_steps,
+                                 sampling_noise=args.sampling_noise)
             return evaluate_utils.metrics_from_device(idx, users, gt_dev.rowptr, gt_dev.col, topN)
         return run
 
@@ -252,18 +255,19 @@ def main(args):
         if valid_eng is not None:
             valid = evaluate_engine(valid_eng, n_rows, eval_B, topN, dist)
         else:
-            valid = evaluate(diffusion, model, train_dev, valid_dev, [train_dev], n_rows, eval_B, topN, args.sampling_steps, dist)
+            valid = evaluate(diffusion, model, train_dev, valid_dev, [train_dev], n_rows, eval_B, topN, args.sampling_steps, dist,
+                             sampling_noise=args.sampling_noise)
         if args.tst_w_val:
             if test_eng is not None:
                 test = evaluate_engine(test_eng, n_rows, eval_B, topN, dist, tail=tail_rows(tv_dev, test_dev, [tv_dev]))
             else:
                 test = evaluate(diffusion, model, tv_dev, test_dev, [tv_dev], n_rows, eval_B, topN, args.sampling_steps, dist,
-                                drop_last=False)
+                                drop_last=False, sampling_noise=args.sampling_noise)
         elif test_eng is not None:
             test = evaluate_engine(test_eng, n_rows, eval_B, topN, dist)
         else:
             test = evaluate(diffusion, model, train_dev, test_dev, [train_dev, valid_dev], n_rows, eval_B, topN,
-                            args.sampling_steps, dist)
+                            args.sampling_steps, dist, sampling_noise=args.sampling_noise)
         return valid, test
 
     print("Start training...")

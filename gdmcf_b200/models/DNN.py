@@ -148,9 +148,14 @@ class _EngineModule(nn.Module):
         return b
 
     def _mm(self, a: Bf16Mat, b: Bf16Mat, m: int, n: int, k: int, **epi):
-        """C[m,n] = a[m,k] @ b[n,k]^T (+ fused epilogue) in the module's precision mode."""
-        if self._lo:
+        """C[m,n] = a[m,k] @ b[n,k]^T (+ fused epilogue) in the module's precision mode (fp32 mode: hi/lo split segments;
+        an operand without a lo part is exact in bf16, e.g. one-hot rows)."""
+        if self._lo and a.lo is not None and b.lo is not None:
             K.gemm([a.hi, a.hi, a.lo], [b.hi, b.lo, b.hi], m, n, [k, k, k], **epi)
+        elif self._lo and b.lo is not None:
+            K.gemm([a.hi, a.hi], [b.hi, b.lo], m, n, [k, k], **epi)
+        elif self._lo and a.lo is not None:
+            K.gemm([a.hi, a.lo], [b.hi, b.hi], m, n, [k, k], **epi)
         else:
             K.gemm([a.hi], [b.hi], m, n, [k], **epi)
 
@@ -263,7 +268,7 @@ class DNN(_EngineModule):
 
     @torch.no_grad()
     def reverse_loop(self, x0_f32, B: int, index, steps_total: int, c1, c2, x0_op: Optional[Bf16Mat] = None,
-                     csr=None, users=None):
+                     csr=None, users=None, noise_hook=None):
         """The p_sample loop (models/gaussian_diffusion.py:695-752) for this backbone: x_t <- c1[t]*f(x_t,t) + c2[t]*x_t,
         t = T-1..0, with the posterior mean fused into the output GEMM's epilogue. x0_f32: [B, ld4] fp32 start
         (x_t = x_start, or its q_sample); returns the fp32 buffer [B, ld4] holding the final x_t."""
@@ -281,6 +286,8 @@ class DNN(_EngineModule):
             self._encode(x_op, B, None, t, steps_total, bufs["h"])
             last = t == 0
             self._decode(bufs["h"], B, nxt, None if last else bufs["xop"], c1=c1, c2=c2, xt=cur, t_const=t)
+            if noise_hook is not None and not last:
+                noise_hook(nxt, bufs["xop"], t)  # sampling_noise: x_{t-1} = mean + sigma[t] * z (gaussian_diffusion.py:745-750)
             x_op = bufs["xop"]
             cur, nxt = nxt, (bufs["xb"] if nxt is bufs["xa"] else bufs["xa"])
         return cur
@@ -304,17 +311,21 @@ class GCNConvParams(nn.Module):
 
 
 class LayerGCN(nn.Module):
-    """models/DNN.py:1077-1103 (gcnLayerNum == 2). Holds the parameters; DNNOneHotEmbeddingGCN evaluates it on the
-    user rows (self loop only): conv2(relu(conv1(x))) = W2 relu(W1 x + b1) + b2."""
+    """models/DNN.py:1077-1103. Holds the parameters; DNNOneHotEmbeddingGCN evaluates it on the user rows (self loop
+    only): gcnLayerNum == 2: W2 relu(W1 x + b1) + b2; == 1: W1 x + b1; == 0: not applied."""
 
     def __init__(self, in_channels, hidden_channels, out_channels, residual=False, args=None):
         super().__init__()
-        if args is not None and getattr(args, "gcnLayerNum", 2) != 2:
-            raise NotImplementedError("gcnLayerNum in {0,1} are ablations outside the hot path")
         if residual:
             raise NotImplementedError("residual=True is never used by the reference model")
-        self.conv1 = GCNConvParams(in_channels, hidden_channels)
-        self.conv2 = GCNConvParams(hidden_channels, out_channels)
+        # models/DNN.py:1081-1085: gcnLayerNum == 1 -> one in -> out convolution; any other value builds conv1 / conv2
+        # (gcnLayerNum == 0 builds them as well but the model never calls the GCN, :1278)
+        self.n_layers = getattr(args, "gcnLayerNum", 2) if args is not None else 2
+        if self.n_layers == 1:
+            self.conv1 = GCNConvParams(in_channels, out_channels)
+        else:
+            self.conv1 = GCNConvParams(in_channels, hidden_channels)
+            self.conv2 = GCNConvParams(hidden_channels, out_channels)
 
 
 class DNNOneHotEmbeddingGCN(_EngineModule):
@@ -324,8 +335,11 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
                  user_num=5949, args=None, precision="bf16"):
         super().__init__()
         self.args = args
-        if args is not None and getattr(args, "noise_type", 0) != 0:
-            raise NotImplementedError("noise_type in {1,2} are ablations outside the hot path")
+        # ablation switches of the reference CLI (models/DNN.py:1236-1259, :1278)
+        self.noise_type = getattr(args, "noise_type", 0) if args is not None else 0
+        self.gcn_layers = getattr(args, "gcnLayerNum", 2) if args is not None else 2
+        if self.noise_type not in (0, 1, 2):
+            raise ValueError("noise_type must be 0, 1 or 2")
         in_dims, out_dims = list(in_dims), list(out_dims)
         self.in_dims = in_dims
         self.in_dims2 = copy.deepcopy(in_dims)
@@ -415,21 +429,26 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
     def build_derived(self) -> None:
         self._weight_operand("in0", self.in_layers[0].weight, cols=self.n_item)
         self._weight_operand("in2", self.in_layers2[0].weight, cols=2 * self.n_item)
-        self._weight_operand("gcn1", self.gcn_model.conv1.lin.weight)
-        self._weight_operand("gcn2", self.gcn_model.conv2.lin.weight)
+        if self.gcn_layers > 0:
+            self._weight_operand("gcn1", self.gcn_model.conv1.lin.weight)
+        if self.gcn_layers == 2:
+            self._weight_operand("gcn2", self.gcn_model.conv2.lin.weight)
         self._onehot_tables()   # inference-side: sparse one-hot encoder tables
         self._item_operands()   # item table operand + inverse norms
 
     def refresh_specs(self):
         pr, out = self.precision, {}
         w1, w2, E = self.in_layers[0].weight, self.in_layers2[0].weight, self.embedding_item.weight
-        g1, g2 = self.gcn_model.conv1.lin.weight, self.gcn_model.conv2.lin.weight
-        for prm, ent in (
-                (w1, self._refresh_entry(w1, op="in0" + pr, tcols="in_layers.0.tcols", cols_used=self.n_item)),
+        ents = [(w1, self._refresh_entry(w1, op="in0" + pr, tcols="in_layers.0.tcols", cols_used=self.n_item)),
                 (w2, self._refresh_entry(w2, op="in2" + pr, onehot="onehot", tcols="in_layers2.0.tcols", cols_used=2 * self.n_item)),
-                (E, self._refresh_entry(E, op="E" + pr, op_t="E.T" + pr, inv="E.inv")),
-                (g1, self._refresh_entry(g1, op="gcn1" + pr, op_t="gcn1.T" + pr)),
-                (g2, self._refresh_entry(g2, op="gcn2" + pr, op_t="gcn2.T" + pr))):
+                (E, self._refresh_entry(E, op="E" + pr, op_t="E.T" + pr, inv="E.inv"))]
+        if self.gcn_layers > 0:
+            g1 = self.gcn_model.conv1.lin.weight
+            ents.append((g1, self._refresh_entry(g1, op="gcn1" + pr, op_t="gcn1.T" + pr)))
+        if self.gcn_layers == 2:
+            g2 = self.gcn_model.conv2.lin.weight
+            ents.append((g2, self._refresh_entry(g2, op="gcn2" + pr, op_t="gcn2.T" + pr)))
+        for prm, ent in ents:
             if ent is not None:
                 out[id(prm)] = ent
         return out
@@ -462,10 +481,35 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         K.bias_act_rows(bufs["S"], B, self.hidden, bias=tb2, ld_bias=self.hidden, row_t=ts, t_const=t_const,
                         act=K.ACT_TANH, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
 
-    def _encode_onehot_dense(self, bufs, xu_op_hi: torch.Tensor, B: int, ts, t_const: int, T: int, to_S: bool):
-        """h_U from a dense one-hot-branch operand [B, 2I] (training / noised inference): tensor-core GEMM."""
+    def _x_branch_operand(self, x_op: Bf16Mat, xu_op_hi: Optional[torch.Tensor], B: int) -> Bf16Mat:
+        """Input of the continuous encoder: x (models/DNN.py:1238), or with noise_type 1 the first n_item columns of the
+        INTERLEAVED one-hot matrix [i0c0, i0c1, i1c0, ...] (:1236-1237) — a column slice of the one-hot operand."""
+        if self.noise_type != 1:
+            return x_op
+        return Bf16Mat(xu_op_hi[:, : self.n_item], None, B, self.n_item)
+
+    def _xx_operand(self, x_op: Bf16Mat, B: int) -> Bf16Mat:
+        """noise_type 2: the one-hot encoder is fed cat([x, x]) (models/DNN.py:1246-1247)."""
+        I = self.n_item
+        xx = self._buf(("xx", B), lambda: Bf16Mat.empty(B, 2 * I, x_op.hi.device, self._lo))
+        for src, dst in ((x_op.hi, xx.hi), (x_op.lo, xx.lo)):
+            if src is not None:
+                dst[:, :I].copy_(src[:, :I])
+                dst[:, I:2 * I].copy_(src[:, :I])
+        return xx
+
+    def _encode_onehot_dense(self, bufs, xu_op_hi: torch.Tensor, B: int, ts, t_const: int, T: int, to_S: bool, lo=None):
+        """h_U from a dense one-hot-branch operand [B, 2I] (training / noised inference): tensor-core GEMM. lo: residual of
+        the operand in fp32 mode when it is not exact in bf16 (noise_type 2 feeds continuous values)."""
         w2 = self._weight_operand("in2", self.in_layers2[0].weight, cols=2 * self.n_item)
         k = 2 * self.n_item
+        if lo is not None and self._lo:
+            assert not to_S
+            _, tb2 = self._tables(T)
+            f32, hi, lo_out = self._seg(bufs, 1)
+            K.gemm([xu_op_hi, xu_op_hi, lo], [w2.hi, w2.lo, w2.hi], B, self.hidden, [k, k, k], act=K.ACT_TANH, bias=tb2,
+                   ld_bias=self.hidden, row_t=ts, t_const=t_const, out_f32=f32, out_bf16=hi, out_bf16_lo=lo_out)
+            return
         if to_S:  # pre-activation only (step-invariant part, hoisted out of the reverse loop)
             K.gemm([xu_op_hi], [w2.hi], B, self.hidden, [k], out_f32=bufs["S"]) if not self._lo else \
                 K.gemm([xu_op_hi, xu_op_hi], [w2.hi, w2.lo], B, self.hidden, [k, k], out_f32=bufs["S"])
@@ -482,8 +526,16 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
     def _user_tower(self, bufs, B: int):
         """GCN on the user rows + sumW mix + row norms (models/DNN.py:1274-1288, :1320)."""
         d3 = 3 * self.hidden
-        c1, c2 = self.gcn_model.conv1, self.gcn_model.conv2
+        if self.gcn_layers == 0:  # no GCN (:1278): hc * sumW + hc * (1 - sumW)
+            K.mix_rownorm(bufs["hc_f32"], B, d3, g=bufs["hc_f32"], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
+            return
+        c1 = self.gcn_model.conv1
         wc1 = self._weight_operand("gcn1", c1.lin.weight)
+        if self.gcn_layers == 1:  # one convolution 3d -> 3d, no activation (:1095-1096)
+            self._mm(bufs["hc"], wc1, B, d3, d3, bias=c1.bias.detach(), out_f32=bufs["g2"])
+            K.mix_rownorm(bufs["hc_f32"], B, d3, g=bufs["g2"], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
+            return
+        c2 = self.gcn_model.conv2
         wc2 = self._weight_operand("gcn2", c2.lin.weight)
         if self._fused_tower():
             # both linears, the mix and the norms in one launch (csrc/tower.cu)
@@ -497,7 +549,14 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
 
     def _fused_tower(self) -> bool:
         """bf16 mode uses the one-launch tower kernel (GDMCF_FUSED_TOWER=0: the two contractions + mix kernels)."""
-        return not self._lo and os.environ.get("GDMCF_FUSED_TOWER", "1") != "0" and c_ok(self.gcn_model.conv1.lin.weight.shape[0])
+        return (not self._lo and self.gcn_layers == 2 and os.environ.get("GDMCF_FUSED_TOWER", "1") != "0"
+                and c_ok(self.gcn_model.conv1.lin.weight.shape[0]))
+
+    @property
+    def needs_dense_onehot(self) -> bool:
+        """noise_type 1 feeds columns of the interleaved one-hot matrix to the continuous encoder: the dense operand must
+        exist even when x_tU = one_hot(x0) (no sparse shortcut)."""
+        return self.noise_type == 1
 
     def _score(self, bufs, B: int, out_f32, out_op: Optional[Bf16Mat] = None, **post):
         """cosine_similarity_cuda (models/DNN.py:1304-1327) with the norms applied in the GEMM epilogue."""
@@ -531,12 +590,16 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         bufs = self._hc_buffers(B, dev)
         p = self.drop.p if self.training else 0.0
         K.qsample_dropout(x, B, I, bufs["xop"], dropout_p=p, seed=self.seed, offset=self._next_offset())
-        self._encode_x(bufs, bufs["xop"], B, ts, 0, _MAX_T_TABLE)
         xu = self._buf(("xu", B), lambda: torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev))
         xu_f = x_U.reshape(B, 2 * I).float()
         tmp = Bf16Mat(xu, None, B, 2 * I)
         K.qsample_dropout(xu_f, B, 2 * I, tmp, dropout_p=p, seed=self.seed + 1, offset=self._next_offset())
-        self._encode_onehot_dense(bufs, xu, B, ts, 0, _MAX_T_TABLE, to_S=False)
+        self._encode_x(bufs, self._x_branch_operand(bufs["xop"], xu, B), B, ts, 0, _MAX_T_TABLE)
+        if self.noise_type == 2:
+            xx = self._xx_operand(bufs["xop"], B)
+            self._encode_onehot_dense(bufs, xx.hi, B, ts, 0, _MAX_T_TABLE, to_S=False, lo=xx.lo)
+        else:
+            self._encode_onehot_dense(bufs, xu, B, ts, 0, _MAX_T_TABLE, to_S=False)
         f32, hi, lo = self._seg(bufs, 2)
         K.gather_rows(self.embedding_user.weight.detach(), _as_i32(index.to(dev)), B, self.hidden, out_f32=f32, out_bf16=hi,
                       out_bf16_lo=lo)
@@ -547,7 +610,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
 
     @torch.no_grad()
     def reverse_loop(self, x0_f32, B: int, index, steps_total: int, c1, c2, x0_op: Optional[Bf16Mat] = None,
-                     csr=None, users=None, xu_op: Optional[torch.Tensor] = None):
+                     csr=None, users=None, xu_op: Optional[torch.Tensor] = None, noise_hook=None):
         """The p_sample loop (models/gaussian_diffusion.py:695-752) for GDMCF. The one-hot encoder's pre-activation
         S(x_tU) does not depend on t and is computed once: sparse gather from the CSR rows when x_tU = one_hot(x0)
         (csr=(rowptr, col), users), else one dense GEMM on `xu_op` [B, 2I]. Per step: encoder GEMM (split-K) ->
@@ -557,7 +620,10 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         bufs = self._hc_buffers(B, dev)
         rb = self._buf(("rev", B, ld4), lambda: dict(xa=torch.empty(B, ld4, dtype=torch.float32, device=dev),
                                                      xb=torch.empty(B, ld4, dtype=torch.float32, device=dev)))
-        if xu_op is not None:
+        nt = self.noise_type
+        if nt == 2:
+            pass  # the one-hot encoder is fed [x_t, x_t]: nothing step-invariant to hoist
+        elif xu_op is not None:
             self._encode_onehot_dense(bufs, xu_op, B, None, 0, steps_total, to_S=True)
         else:
             base, delta = self._onehot_tables()
@@ -573,11 +639,17 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
             K.qsample_dropout(x0_f32, B, I, x_op)
         cur, nxt = x0_f32, rb["xa"]
         for t in reversed(range(steps_total)):
-            self._encode_x(bufs, x_op, B, None, t, steps_total)
-            self._encode_onehot_from_S(bufs, B, None, t, steps_total)
+            self._encode_x(bufs, self._x_branch_operand(x_op, xu_op, B), B, None, t, steps_total)
+            if nt == 2:
+                xx = self._xx_operand(x_op, B)
+                self._encode_onehot_dense(bufs, xx.hi, B, None, t, steps_total, to_S=False, lo=xx.lo)
+            else:
+                self._encode_onehot_from_S(bufs, B, None, t, steps_total)
             self._user_tower(bufs, B)
             last = t == 0
             self._score(bufs, B, nxt, None if last else bufs["xop"], c1=c1, c2=c2, xt=cur, t_const=t)
+            if noise_hook is not None and not last:
+                noise_hook(nxt, bufs["xop"], t)  # sampling_noise (gaussian_diffusion.py:745-750)
             x_op = bufs["xop"]
             cur, nxt = nxt, (rb["xb"] if nxt is rb["xa"] else rb["xa"])
         return cur

@@ -7,8 +7,9 @@ tensors runs in libgdmcf_sm100.so. Extensions that the reference lacks (all opti
 reference behaviour): CSR batches instead of dense rows (`CsrBatch`), fused mask+top-K ranking (`rank`),
 `precision`, injected random draws (`inject=`) for parity tests.
 
-What is NOT reproduced (cannot change any result): the per-step random graph bookkeeping of
-p_sample (gaussian_diffusion.py:710-729) — it only feeds GCN item rows the model discards.
+Both mean types (START_X / EPSILON) and sampling_noise are covered. The per-step random graph bookkeeping of p_sample
+(gaussian_diffusion.py:710-729) cannot change any result (it only feeds GCN item rows the model discards)
+and is only executed in the faithful-graph mode (`faithful_graph`, see sample_graph_step).
 """
 from __future__ import annotations
 
@@ -87,8 +88,8 @@ class GaussianDiffusionDiscrete(nn.Module):
         self._calls = 0
         self._epoch = None
         self._importance_ready = False
-        if mean_type != ModelMeanType.START_X:
-            raise NotImplementedError("mean_type=eps is an ablation outside the hot path (SURVEY.md §8f)")
+        if mean_type not in (ModelMeanType.START_X, ModelMeanType.EPSILON):
+            raise NotImplementedError(mean_type)
         if noise_scale != 0.0:
             self.betas = torch.tensor(self.get_betas(), dtype=torch.float64).to(self.device)
             if beta_fixed:
@@ -137,6 +138,21 @@ class GaussianDiffusionDiscrete(nn.Module):
         # fp32 device tables consumed by the kernels (the reference gathers the f64 value and casts, :1131)
         self._f32 = {k: getattr(self, k).float().contiguous() for k in (
             "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2")}
+        # reverse-step coefficients x_{t-1} = ra[t] * model_output + rb[t] * x_t:
+        #   START_X: pred_xstart = output                               -> ra = coef1, rb = coef2          (:1085-1086)
+        #   EPSILON: pred_xstart = sr[t] * x_t - srm1[t] * output       -> ra = -coef1 * srm1, rb = coef1 * sr + coef2
+        #            (_predict_xstart_from_eps :1106-1111 folded into q_posterior_mean_variance :1041-1050, in float64)
+        if self.mean_type == ModelMeanType.EPSILON:
+            ra = -self.posterior_mean_coef1 * self.sqrt_recipm1_alphas_cumprod
+            rb = self.posterior_mean_coef1 * self.sqrt_recip_alphas_cumprod + self.posterior_mean_coef2
+        else:
+            ra, rb = self.posterior_mean_coef1, self.posterior_mean_coef2
+        self._f32["reverse_a"], self._f32["reverse_b"] = ra.float().contiguous(), rb.float().contiguous()
+        # sampling_noise (:745-750): x_{t-1} = mean + [t != 0] * exp(0.5 * log_variance[t]) * N(0, 1)
+        sigma = torch.exp(0.5 * self.posterior_log_variance_clipped)
+        sigma[0] = 0.0
+        self._f32["noise_sigma"] = sigma.float().contiguous()
+        self._f32["ones"] = torch.ones_like(self._f32["noise_sigma"])
 
     def get_Qt_bar(self, alpha_bar_t):
         alpha_bar_t = alpha_bar_t.unsqueeze(1).unsqueeze(1)
@@ -295,14 +311,12 @@ class GaussianDiffusionDiscrete(nn.Module):
         """Reverse process over all `self.steps` timesteps starting from x_start (steps == 0) or its
         q_sample at t = steps-1. Returns fp32 [B, n_item]. x_start: dense fp32 CUDA tensor or CsrBatch."""
         assert steps <= self.steps, "Too much steps in inference."
-        if sampling_noise:
-            raise NotImplementedError("sampling_noise=True is an ablation outside the hot path (default False)")
         if not hasattr(model, "reverse_loop"):
             raise TypeError("p_sample needs a gdmcf_b200 denoiser (DNN / DNNOneHotEmbeddingGCN); there is no generic torch path")
         lo = getattr(model, "_lo", False)
         x0, x0_op, csr, users, B, I = self._dense_start(x_start, want_op=(steps == 0), lo=lo)
         dev = x0.device
-        if steps != 0:
+        if steps != 0 or sampling_noise:
             self._begin_step(dev)
         gdmcf = self.CatOneHot and self.indexIn
         if self.CatOneHot and not self.indexIn:
@@ -339,20 +353,34 @@ class GaussianDiffusionDiscrete(nn.Module):
             x_t = xp
         if self.noise_scale == 0.0:
             raise NotImplementedError("noise_scale == 0 (no diffusion) is outside the hot path")
-        c1, c2 = self._f32["posterior_mean_coef1"], self._f32["posterior_mean_coef2"]
+        c1, c2 = self._f32["reverse_a"], self._f32["reverse_b"]
+        noise_hook = None
+        if sampling_noise:
+            draws = inject.get("sampling_noise") if inject else None  # optional: one [B, I] tensor per step, t = T-1 .. 0
+
+            def noise_hook(x_f32, x_op_, t):  # x_{t-1} = mean + sigma[t] * z, t != 0; refreshes the bf16 operand too
+                if t == 0:
+                    return
+                z = draws[self.steps - 1 - t].float().contiguous() if draws is not None else None
+                K.qsample_dropout(x_f32, B, I, x_op_, t_const=t, sqrt_ab=self._f32["ones"], sqrt_1mab=self._f32["noise_sigma"],
+                                  noise=z, seed=self.seed, offset=self._offset(), epoch=self._epoch, xt_out=x_f32)
         if gdmcf:
-            out = model.reverse_loop(x_t, B, idx32, self.steps, c1, c2, x0_op=x_op, csr=csr, users=users, xu_op=xu_op)
+            if getattr(model, "needs_dense_onehot", False) and xu_op is None:
+                xu_op = torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)
+                K.onehot_noise(x0, B, I, xu_op)
+            out = model.reverse_loop(x_t, B, idx32, self.steps, c1, c2, x0_op=x_op, csr=csr, users=users, xu_op=xu_op,
+                                     noise_hook=noise_hook)
         else:
-            out = model.reverse_loop(x_t, B, None, self.steps, c1, c2, x0_op=x_op)
+            out = model.reverse_loop(x_t, B, None, self.steps, c1, c2, x0_op=x_op, noise_hook=noise_hook)
         # the loop's result lives in a cached ping-pong buffer that the next call overwrites: the public API hands back a
         # fresh tensor like the reference; rank() consumes the buffer in place (_raw)
         return out if _raw else out[:, :I].clone()
 
     @torch.no_grad()
-    def rank(self, model, x_start, k, hist=None, hist2=None, steps=0, index=None, with_values=False):
+    def rank(self, model, x_start, k, hist=None, hist2=None, steps=0, index=None, with_values=False, sampling_noise=False):
         """Fused evaluate step (main.py:288-304): p_sample -> history mask -> top-k, all on the device.
         hist / hist2: (rowptr, col) device CSR of the items to mask, indexed by the batch's user ids."""
-        out = self.p_sample(model, x_start, steps, index=index, _raw=True)
+        out = self.p_sample(model, x_start, steps, sampling_noise, index=index, _raw=True)
         B, I = x_start.shape
         users = x_start.users if isinstance(x_start, CsrBatch) else (index.to(out.device).to(torch.int32) if index is not None else None)
         return K.mask_topk(out, B, I, k, users=users, hist=hist, hist2=hist2, with_values=with_values)
@@ -366,6 +394,12 @@ class GaussianDiffusionDiscrete(nn.Module):
         posterior_log_variance_clipped = self._extract_into_tensor(self.posterior_log_variance_clipped, t, x_t.shape)
         return posterior_mean, posterior_variance, posterior_log_variance_clipped
 
+    def _predict_xstart_from_eps(self, x_t, t, eps):
+        """gaussian_diffusion.py:1106-1111."""
+        assert x_t.shape == eps.shape
+        return (self._extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t
+                - self._extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * eps)
+
     def p_mean_variance(self, model, x, t, x_tU=None, index=None, graph=None):
         """gaussian_diffusion.py:1063-1103 (START_X): one denoiser call + posterior mean (API parity; p_sample
         uses the fused loop instead)."""
@@ -377,7 +411,10 @@ class GaussianDiffusionDiscrete(nn.Module):
             model_output = model(x, t)
         model_variance = self._extract_into_tensor(self.posterior_variance, t, x.shape)
         model_log_variance = self._extract_into_tensor(self.posterior_log_variance_clipped, t, x.shape)
-        pred_xstart = model_output
+        if self.mean_type == ModelMeanType.START_X:
+            pred_xstart = model_output
+        else:
+            pred_xstart = self._predict_xstart_from_eps(x, t, eps=model_output)
         model_mean, _, _ = self.q_posterior_mean_variance(x_start=pred_xstart, x_t=x, t=t)
         return {"mean": model_mean, "variance": model_variance, "log_variance": model_log_variance,
                 "pred_xstart": pred_xstart}

@@ -106,7 +106,10 @@ def _hand_over(model, grads: Dict[str, torch.Tensor], names):
     params = dict(model.named_parameters())
     out = []
     for n in names:
-        g = grads[n]
+        g = grads.get(n)  # None: the parameter takes no part in this configuration (gcnLayerNum 0: the GCN is never called)
+        if g is None:
+            out.append(None)
+            continue
         if g.dim() == 2 and not g.is_contiguous():
             prm = params[n]
             if prm.grad is None:
@@ -120,6 +123,51 @@ def _hand_over(model, grads: Dict[str, torch.Tensor], names):
 
 class _Ctx:
     """Tensors the backward needs (kept alive between forward and backward of one step)."""
+
+
+def _is_eps(diff) -> bool:
+    return getattr(diff.mean_type, "name", "") == "EPSILON"
+
+
+def _noised_input(diff, model, c, x0, B, I, ts, inject, p):
+    """q_sample + dropout + operand cast (gaussian_diffusion.py:868-870, DNN.py:78/1232) -> c.A1, and the regression target
+    of the loss: x_start (START_X) or the noise (EPSILON, :895-898). With EPSILON the rows drawn at t == 0 use the
+    likelihood term mean((x0 - pred_xstart)^2 / 2) (:924-928), which is the same squared distance to the model output
+    after a change of variables: (srm1^2 / 2) * mean((out - (sr * x_t - x0) / srm1)^2). c.loss_scale carries the factor."""
+    dev = x0.device
+    c.A1 = Bf16Mat.empty(B, I, dev, model._lo, zero=False)
+    keep = inject.get("keep_x")
+    noise = inject.get("noise")
+    eps_mode = _is_eps(diff)
+    xt = None
+    if eps_mode:
+        if noise is None:
+            noise = torch.randn(B, I, device=dev)
+        xt = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
+    K.qsample_dropout(x0, B, I, c.A1, row_t=ts, sqrt_ab=diff._f32["sqrt_alphas_cumprod"],
+                      sqrt_1mab=diff._f32["sqrt_one_minus_alphas_cumprod"],
+                      noise=noise.float().contiguous() if noise is not None else None,
+                      keep=keep.to(torch.uint8).contiguous() if keep is not None else None, dropout_p=p, seed=diff.seed,
+                      offset=diff._offset(), epoch=diff._epoch, xt_out=xt)
+    c.target, c.loss_scale = x0, None
+    if eps_mode:
+        sr0 = float(diff.sqrt_recip_alphas_cumprod[0])
+        srm0 = float(diff.sqrt_recipm1_alphas_cumprod[0])
+        t0 = (ts == 0)
+        tgt = torch.zeros(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
+        tgt[:, :I] = torch.where(t0[:, None], (sr0 * xt[:, :I] - x0[:, :I]) / srm0, noise.float())
+        c.target = tgt
+        c.loss_scale = torch.where(t0, torch.full((), srm0 * srm0 / 2.0, device=dev), torch.ones((), device=dev)).float()
+
+
+def _row_mse(c, B, I):
+    mse = K.mse_rows(c.out, c.target, B, I)
+    return mse * c.loss_scale if c.loss_scale is not None else mse
+
+
+def _loss_seed(c, g_mse):
+    g = g_mse.float()
+    return (g * c.loss_scale).contiguous() if c.loss_scale is not None else g.contiguous()
 
 
 # ======================================================================================================
@@ -136,13 +184,9 @@ def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc,
     p = model.drop.p if model.training else 0.0
     c = _Ctx()
     c.B, c.I, c.x0, c.ts, c.idx32 = B, I, x0, ts, idx32
+    nt, gl = model.noise_type, model.gcn_layers
     # noising + dropout + operand cast, one pass each (gaussian_diffusion.py:849-870, DNN.py:1232-1233)
-    c.A1 = Bf16Mat.empty(B, I, dev, model._lo, zero=False)
-    keep = inject.get("keep_x")
-    K.qsample_dropout(x0, B, I, c.A1, row_t=ts, sqrt_ab=diff._f32["sqrt_alphas_cumprod"],
-                      sqrt_1mab=diff._f32["sqrt_one_minus_alphas_cumprod"], noise=inject.get("noise"),
-                      keep=keep.to(torch.uint8).contiguous() if keep is not None else None, dropout_p=p, seed=diff.seed,
-                      offset=diff._offset(), epoch=diff._epoch)
+    _noised_input(diff, model, c, x0, B, I, ts, inject, p)
     c.A2 = torch.empty(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)
     kxu = inject.get("keep_xU")
     K.onehot_noise(x0, B, I, c.A2, ts=ts_disc, discrete=float(diff.discrete), dropout_p=p, u_keep=inject.get("u_keep"),
@@ -151,28 +195,56 @@ def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc,
     c.hc_f32 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
     c.hc = Bf16Mat.empty(B, 3 * d, dev, True)
     bufs = dict(hc_f32=c.hc_f32, hc=c.hc, S=None)
-    model._encode_x(bufs, c.A1, B, ts, 0, T)
-    model._encode_onehot_dense(bufs, c.A2, B, ts, 0, T, to_S=False)
+    # encoder inputs: noise_type 1 feeds columns of the interleaved one-hot matrix to the continuous encoder (DNN.py:1236),
+    # noise_type 2 feeds [x, x] to the one-hot encoder (:1246); they are also the wgrad operands of the backward pass
+    c.enc1_in = model._x_branch_operand(c.A1, c.A2, B)
+    model._encode_x(bufs, c.enc1_in, B, ts, 0, T)
+    if nt == 2:
+        xx = Bf16Mat.empty(B, 2 * I, dev, model._lo)
+        for src, dst in ((c.A1.hi, xx.hi), (c.A1.lo, xx.lo)):
+            if src is not None:
+                dst[:, :I].copy_(src[:, :I])
+                dst[:, I:2 * I].copy_(src[:, :I])
+        c.enc2_in = xx
+        model._encode_onehot_dense(bufs, xx.hi, B, ts, 0, T, to_S=False, lo=xx.lo)
+    else:
+        c.enc2_in = Bf16Mat(c.A2, None, B, 2 * I)
+        model._encode_onehot_dense(bufs, c.A2, B, ts, 0, T, to_S=False)
     f32, hi, lo = model._seg(bufs, 2)
     K.gather_rows(model.embedding_user.weight.detach(), idx32, B, d, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
-    # nt_xent logits (DNN.py:488): S_raw = h h_U^T, split precision
-    h_op = Bf16Mat(c.hc.hi[:, :d], c.hc.lo[:, :d], B, d)
-    hu_op = Bf16Mat(c.hc.hi[:, d:2 * d], c.hc.lo[:, d:2 * d], B, d)
-    c.S = torch.empty(B, K.round_up(B, 4), dtype=torch.float32, device=dev)
-    _mm3(h_op, hu_op, B, B, d, out_f32=c.S)
-    c.closs_rows = torch.empty(B, dtype=torch.float32, device=dev)
-    K.ntxent_rows(c.S, B, loss_rows=c.closs_rows)
+    c.closs_rows = torch.zeros(B, dtype=torch.float32, device=dev)
+    c.S = None
+    if nt == 0:  # noise_type != 0 multiplies the contrastive loss by zero (DNN.py:1258-1259)
+        # nt_xent logits (DNN.py:488): S_raw = h h_U^T, split precision
+        h_op = Bf16Mat(c.hc.hi[:, :d], c.hc.lo[:, :d], B, d)
+        hu_op = Bf16Mat(c.hc.hi[:, d:2 * d], c.hc.lo[:, d:2 * d], B, d)
+        c.S = torch.empty(B, K.round_up(B, 4), dtype=torch.float32, device=dev)
+        _mm3(h_op, hu_op, B, B, d, out_f32=c.S)
+        K.ntxent_rows(c.S, B, loss_rows=c.closs_rows)
     # GCN on user rows, mix, norms (DNN.py:1274-1288)
     g = model.gcn_model
-    wc1 = model._weight_operand("gcn1", g.conv1.lin.weight)
-    wc2 = model._weight_operand("gcn2", g.conv2.lin.weight)
-    H = g.conv1.lin.weight.shape[0]
-    c.g1_f32 = torch.empty(B, H, dtype=torch.float32, device=dev)
     c.g2 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
     c.hcp_f32 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
     c.hcp = Bf16Mat.empty(B, 3 * d, dev, model._lo)
     c.inv_u = torch.empty(B, dtype=torch.float32, device=dev)
     hc_in = c.hc if model._lo else Bf16Mat(c.hc.hi, None, B, 3 * d)
+    if gl == 0:    # no GCN (:1278): hc * sumW + hc * (1 - sumW)
+        c.g2 = c.hc_f32
+        K.mix_rownorm(c.hc_f32, B, 3 * d, g=c.hc_f32, sumw=model.sumW.detach(), out_f32=c.hcp_f32, out=c.hcp, inv_norm=c.inv_u)
+    elif gl == 1:  # a single 3d -> 3d convolution, no activation (:1095-1096)
+        wc1 = model._weight_operand("gcn1", g.conv1.lin.weight)
+        _mm_auto(model, hc_in, wc1, B, 3 * d, 3 * d, bias=g.conv1.bias.detach(), out_f32=c.g2)
+        K.mix_rownorm(c.hc_f32, B, 3 * d, g=c.g2, sumw=model.sumW.detach(), out_f32=c.hcp_f32, out=c.hcp, inv_norm=c.inv_u)
+    if gl != 2:
+        e_op, c.inv_i = model._item_operands()
+        c.out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
+        _mm_auto(model, c.hcp, e_op, B, I, 3 * d, row_scale=c.inv_u, col_scale=c.inv_i, out_f32=c.out)
+        c.mse = _row_mse(c, B, I)
+        return c
+    wc1 = model._weight_operand("gcn1", g.conv1.lin.weight)
+    wc2 = model._weight_operand("gcn2", g.conv2.lin.weight)
+    H = g.conv1.lin.weight.shape[0]
+    c.g1_f32 = torch.empty(B, H, dtype=torch.float32, device=dev)
     if model._fused_tower():
         # one launch for both linears, the mix and the norms; the fp32 copies feed the backward pass
         K.user_tower(hc_in, c.hc_f32, wc1, g.conv1.bias.detach(), wc2, g.conv2.bias.detach(), model.sumW.detach(), B,
@@ -187,7 +259,7 @@ def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc,
     e_op, c.inv_i = model._item_operands()
     c.out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
     _mm_auto(model, c.hcp, e_op, B, I, 3 * d, row_scale=c.inv_u, col_scale=c.inv_i, out_f32=c.out)
-    c.mse = K.mse_rows(c.out, x0, B, I)
+    c.mse = _row_mse(c, B, I)
     return c
 
 
@@ -217,7 +289,7 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     n_cb = (I + 31) // 32
     colsum = torch.empty(I, dtype=torch.float32, device=dev)
     rowpart = torch.empty(n_cb, B, dtype=torch.float32, device=dev)
-    K.loss_grad(c.out, c.x0, g_mse.float().contiguous(), B, I, Gs, GT=GsT, row_scale=c.inv_u, col_scale=c.inv_i,
+    K.loss_grad(c.out, c.target, _loss_seed(c, g_mse), B, I, Gs, GT=GsT, row_scale=c.inv_u, col_scale=c.inv_i,
                 with_out=True, colsum=colsum, rowpart=rowpart)
     # ---- d E = Gs^T hc' - E * ri^2 * c_i   (written straight into the parameter's gradient)
     hcpT = K.cast_bf16_transpose(c.hcp_f32, with_lo=lo)  # [3d, B]
@@ -248,6 +320,30 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     grads["sumW"] = dw_rows.sum()
     # ---- GCN (user rows) backward
     g = model.gcn_model
+    gl = model.gcn_layers
+    d_hc_tot = torch.empty(B, d3, dtype=torch.float32, device=dev)
+    if gl == 0:    # hc' = hc * sumW + hc * (1 - sumW): both mix branches lead straight back to hc
+        K.ew_binary(K.EW_AXPBY, d_hc, d_g2, B, d3, alpha=1.0, beta=1.0, out_f32=d_hc_tot)
+    elif gl == 1:  # g2 = hc W1^T + b1
+        d_g2_op = K.cast_bf16(d_g2, with_lo=lo)
+        d_g2T = K.cast_bf16_transpose(d_g2, with_lo=lo)      # [3d, B]
+        hcT = K.cast_bf16_transpose(c.hc_f32, with_lo=lo)    # [3d, B]
+        gW1 = torch.empty_like(P["gcn_model.conv1.lin.weight"])
+        _mm_auto(model, d_g2T, hcT, d3, d3, B, out_f32=gW1)
+        grads["gcn_model.conv1.lin.weight"] = gW1
+        grads["gcn_model.conv1.bias"] = K.colsum_f32(d_g2, B, d3)
+        wc1T = model._weight_operand("gcn1", g.conv1.lin.weight, transpose=True)  # [3d_in, 3d_out]
+        _mm_auto(model, d_g2_op, wc1T, B, d3, d3, out_f32=d_hc_tot, c1=ones1, c2=ones1, xt=d_hc, t_const=0)
+    if gl != 2:
+        gU_rows = d_hc_tot[:, 2 * d:]
+        model._user_grad_rows = (c.idx32, gU_rows)
+        if not sparse_user_grad:
+            gU = torch.zeros_like(P["embedding_user.weight"])
+            K.scatter_rows_add(gU_rows, c.idx32, gU, B, d)
+            grads["embedding_user.weight"] = gU
+        yield grads
+        yield _first_layer_grads(model, diff, c, d_hc_tot, g_closs, P)
+        return
     d_g2_op = K.cast_bf16(d_g2, with_lo=lo)
     d_g2T = K.cast_bf16_transpose(d_g2, with_lo=lo)      # [3d, B]
     g1T = K.cast_bf16_transpose(c.g1_f32, with_lo=lo)    # [512, B]
@@ -268,7 +364,6 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     grads["gcn_model.conv1.lin.weight"] = gW1
     grads["gcn_model.conv1.bias"] = K.colsum_f32(d_pre1, B, 512)
     wc1T = model._weight_operand("gcn1", g.conv1.lin.weight, transpose=True)  # [3d, 512]
-    d_hc_tot = torch.empty(B, d3, dtype=torch.float32, device=dev)
     _mm_auto(model, d_pre1_op, wc1T, B, d3, 512, out_f32=d_hc_tot, c1=ones1, c2=ones1, xt=d_hc, t_const=0)
     # ---- user embedding rows
     # the rows of the user table that received a gradient (sparse exchange / row-sparse optimizer instead of a dense table)
@@ -278,18 +373,31 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
         K.scatter_rows_add(d_hc_tot[:, 2 * d:], c.idx32, gU, B, d)
         grads["embedding_user.weight"] = gU
     yield grads  # stage 2: sumW, the GCN linears, the user table — small messages, final before the two big wgrads
-    grads = {}
-    # ---- nt_xent backward (DNN.py:479-508) into h and h_U
-    dS = torch.empty(B, K.round_up(B, 4), dtype=torch.float32, device=dev)
-    K.ntxent_rows(c.S, B, dscale=g_closs.float().reshape(1), dS=dS)
-    dS_op = K.cast_bf16(dS[:, :B], with_lo=True)
-    dST_op = K.cast_bf16_transpose(dS[:, :B], with_lo=True)
-    hT = K.cast_bf16_transpose(c.hc_f32[:, :d], with_lo=True)          # [d, B]
-    hUT = K.cast_bf16_transpose(c.hc_f32[:, d:2 * d], with_lo=True)    # [d, B]
-    dh_tot = torch.empty(B, d, dtype=torch.float32, device=dev)
-    dhU_tot = torch.empty(B, d, dtype=torch.float32, device=dev)
-    _mm3(dS_op, hUT, B, d, B, out_f32=dh_tot, c1=ones1, c2=ones1, xt=d_hc_tot[:, :d], t_const=0)
-    _mm3(dST_op, hT, B, d, B, out_f32=dhU_tot, c1=ones1, c2=ones1, xt=d_hc_tot[:, d:2 * d], t_const=0)
+    yield _first_layer_grads(model, diff, c, d_hc_tot, g_closs, P)  # stage 3: the two first-layer weights (+ biases, emb_layer)
+
+
+def _first_layer_grads(model, diff, c: _Ctx, d_hc_tot, g_closs, P):
+    """Stage 3 of the GDMCF backward: contrastive-loss gradient into h / h_U, tanh backward, the two first-layer weight
+    gradients and the time-embedding layer."""
+    B, I, d, dev, T = c.B, c.I, model.hidden, c.x0.device, diff.steps
+    e = model.time_emb_dim
+    lo = model._lo
+    ones1 = _ones(model, 1, dev)
+    grads: Dict[str, torch.Tensor] = {}
+    if c.S is not None:
+        # ---- nt_xent backward (DNN.py:479-508) into h and h_U
+        dS = torch.empty(B, K.round_up(B, 4), dtype=torch.float32, device=dev)
+        K.ntxent_rows(c.S, B, dscale=g_closs.float().reshape(1), dS=dS)
+        dS_op = K.cast_bf16(dS[:, :B], with_lo=True)
+        dST_op = K.cast_bf16_transpose(dS[:, :B], with_lo=True)
+        hT = K.cast_bf16_transpose(c.hc_f32[:, :d], with_lo=True)          # [d, B]
+        hUT = K.cast_bf16_transpose(c.hc_f32[:, d:2 * d], with_lo=True)    # [d, B]
+        dh_tot = torch.empty(B, d, dtype=torch.float32, device=dev)
+        dhU_tot = torch.empty(B, d, dtype=torch.float32, device=dev)
+        _mm3(dS_op, hUT, B, d, B, out_f32=dh_tot, c1=ones1, c2=ones1, xt=d_hc_tot[:, :d], t_const=0)
+        _mm3(dST_op, hT, B, d, B, out_f32=dhU_tot, c1=ones1, c2=ones1, xt=d_hc_tot[:, d:2 * d], t_const=0)
+    else:  # noise_type != 0: the contrastive loss is multiplied by zero (DNN.py:1258-1259)
+        dh_tot, dhU_tot = d_hc_tot[:, :d], d_hc_tot[:, d:2 * d]
     # ---- tanh backward, first-layer weight gradients
     dh_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
     dhU_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
@@ -303,8 +411,8 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     temb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
     K.gather_rows(emb_table, c.ts, B, e, out_f32=emb_rows)
     K.gather_rows(_temb_table(model, T, dev), c.ts, B, e, out_f32=temb_rows)
-    A1T = _input_T_with_time_rows(model, c.A1, emb_rows, B, I, e, dev)                                    # [I + e, B]
-    A2T = _input_T_with_time_rows(model, Bf16Mat(c.A2, None, B, 2 * I), emb_rows, B, 2 * I, e, dev)       # [2I + e, B]
+    A1T = _input_T_with_time_rows(model, c.enc1_in, emb_rows, B, I, e, dev)        # [I + e, B]
+    A2T = _input_T_with_time_rows(model, c.enc2_in, emb_rows, B, 2 * I, e, dev)    # [2I + e, B]
     d_emb = torch.empty(B, e, dtype=torch.float32, device=dev)
     for name, dpre, dpreT, AT, n_in, first in (("in_layers.0", dh_pre, dh_preT, A1T, I, True),
                                               ("in_layers2.0", dhU_pre, dhU_preT, A2T, 2 * I, False)):
@@ -324,7 +432,7 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     K.sgemm_small(d_emb, temb_rows, gWe, e, e, B, trans_a=True)
     grads["emb_layer.weight"] = gWe
     grads["emb_layer.bias"] = K.colsum_f32(d_emb, B, e)
-    yield grads  # stage 3: the two first-layer weights (+ their biases and the time-embedding layer)
+    return grads
 
 
 class _GdmcfTrainFn(torch.autograd.Function):
@@ -332,6 +440,7 @@ class _GdmcfTrainFn(torch.autograd.Function):
     def forward(ctx, model, diff, x0, B, I, idx32, ts_disc, ts, inject, *params):
         c = _gdmcf_forward(model, diff, x0, B, I, idx32, ts_disc, ts, inject)
         ctx.c, ctx.model, ctx.diff = c, model, diff
+        ctx.names = [n for n in _GDMCF_PARAMS if n in dict(model.named_parameters())]
         closs = c.closs_rows.mean()
         ctx.mark_non_differentiable(c.out)
         return c.mse, closs, c.out
@@ -340,7 +449,7 @@ class _GdmcfTrainFn(torch.autograd.Function):
     def backward(ctx, g_mse, g_closs, g_out):
         grads = _gdmcf_backward(ctx.model, ctx.diff, ctx.c, g_mse, g_closs)
         ctx.c = None
-        return (None,) * 9 + _hand_over(ctx.model, grads, _GDMCF_PARAMS)
+        return (None,) * 9 + _hand_over(ctx.model, grads, ctx.names)
 
 
 # ======================================================================================================
@@ -356,18 +465,13 @@ def _dnn_forward(model: DNN, diff, x0, B, I, ts, inject) -> _Ctx:
     p = model.drop.p if model.training else 0.0
     c = _Ctx()
     c.B, c.I, c.x0, c.ts = B, I, x0, ts
-    c.A1 = Bf16Mat.empty(B, I, dev, model._lo, zero=False)
-    keep = inject.get("keep_x")
-    K.qsample_dropout(x0, B, I, c.A1, row_t=ts, sqrt_ab=diff._f32["sqrt_alphas_cumprod"],
-                      sqrt_1mab=diff._f32["sqrt_one_minus_alphas_cumprod"], noise=inject.get("noise"),
-                      keep=keep.to(torch.uint8).contiguous() if keep is not None else None, dropout_p=p, seed=diff.seed,
-                      offset=diff._offset(), epoch=diff._epoch)
+    _noised_input(diff, model, c, x0, B, I, ts, inject, p)
     c.h_f32 = torch.empty(B, d, dtype=torch.float32, device=dev)
     c.h = Bf16Mat.empty(B, d, dev, model._lo)
     model._encode(c.A1, B, ts, 0, T, c.h, h_f32=c.h_f32)
     c.out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
     model._decode(c.h, B, c.out)
-    c.mse = K.mse_rows(c.out, x0, B, I)
+    c.mse = _row_mse(c, B, I)
     return c
 
 
@@ -380,7 +484,7 @@ def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
     G = Bf16Mat.empty(B, I, dev, lo, zero=True)
     GT = Bf16Mat.empty(I, B, dev, lo, zero=False)
     colsum = torch.empty(I, dtype=torch.float32, device=dev)
-    K.loss_grad(c.out, c.x0, g_mse.float().contiguous(), B, I, G, GT=GT, with_out=False, colsum=colsum)
+    K.loss_grad(c.out, c.target, _loss_seed(c, g_mse), B, I, G, GT=GT, with_out=False, colsum=colsum)
     grads["out_layers.0.bias"] = colsum
     # d W_out [I, d] = G^T h
     hT = K.cast_bf16_transpose(c.h_f32, with_lo=lo)  # [d, B]
@@ -464,10 +568,14 @@ def _prepare(diff, model, x_start, index, inject):
 
 
 def _loss_weight(diff, ts, B, dev, reweight):
-    if reweight:
-        weight = diff.SNR(ts - 1) - diff.SNR(ts)
+    if not reweight:
+        return torch.ones(B, device=dev)
+    if _is_eps(diff):  # gaussian_diffusion.py:924-926 (float64 schedule tensors; t == 0 divides by zero, then overwritten)
+        ac, acp, betas = (getattr(diff, n).to(dev) for n in ("alphas_cumprod", "alphas_cumprod_prev", "betas"))
+        weight = (1 - ac[ts]) / ((1 - acp[ts]) ** 2 * (1 - betas[ts]))
         return torch.where((ts == 0), 1.0, weight)
-    return torch.ones(B, device=dev)
+    weight = diff.SNR(ts - 1) - diff.SNR(ts)
+    return torch.where((ts == 0), 1.0, weight)
 
 
 def training_losses(diff, model, x_start, reweight=False, index=None, inject: Optional[dict] = None):
@@ -479,7 +587,7 @@ def training_losses(diff, model, x_start, reweight=False, index=None, inject: Op
     params = dict(model.named_parameters())
     if gdmcf:
         mse, closs, out = _GdmcfTrainFn.apply(model, diff, x0, B, I, idx32, ts_disc, ts32, inject,
-                                              *[params[n] for n in _GDMCF_PARAMS])
+                                              *[params[n] for n in _GDMCF_PARAMS if n in params])
     else:
         mse, out = _DnnTrainFn.apply(model, diff, x0, B, I, ts32, inject, *[params[n] for n in _DNN_PARAMS])
         closs = None
