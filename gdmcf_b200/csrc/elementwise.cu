@@ -240,6 +240,45 @@ __global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x
 }
 
 // ---------------------------------------------------------------------------------------------
+// Faithful graph bookkeeping of p_sample (models/gaussian_diffusion.py:710-729), one reverse step:
+//   x_i      = apply_noise(t, one_hot(state))           per entry: class 0 -> 1 w.p. (1 - a)(1 - p), a = t / batch
+//   s_b      ~ Bernoulli(deg_b / max_b deg)             "degree-guided" draw per user (:711-716)
+//   state   |= user_guided ? (x_i == 1 && s_b == 1) : (x_i == 1)      (:721-726, OR-accumulated over the steps)
+// state: uint8 [rows, ld] (1 = edge user -> item). Entries already 1 stay 1 whatever is drawn. One thread per 4 entries.
+// u_entry / u_user: optional injected uniforms in [0,1) (entry flips iff u >= P(0 -> 0); s_b = 1 iff u < deg fraction).
+// ---------------------------------------------------------------------------------------------
+__global__ void graph_noise_step_kernel(uint8_t* __restrict__ state, long long ld, const float* __restrict__ deg_frac, int t,
+                                        int batch, float discrete, int user_guided, uint64_t seed, uint64_t offset0,
+                                        const uint64_t* __restrict__ epoch, const float* __restrict__ u_entry,
+                                        const float* __restrict__ u_user, int rows, int cols) {
+  pdl_entry();
+  const uint64_t ep = epoch ? (epoch[0] << 8) : 0ull;
+  const Philox rng(seed);
+  const float a = (float)t / (float)batch;                 // gaussian_diffusion.py:775
+  const float q_zero = a * 1.0f + (1.0f - a) * discrete;   // P(class 0 stays 0), Q_bar = a*I + (1-a)*u_x (:601)
+  const int groups = (cols + 3) / 4;
+  const long long total = (long long)rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / groups), c0 = (int)(i % groups) * 4;
+    bool guide = true;
+    if (user_guided) {
+      const float uu = u_user ? u_user[r] : (1.0f - u32_to_unit_open(rng(offset0 + (uint64_t)r, ep | 5ull).x));
+      guide = uu < deg_frac[r];
+    }
+    const uint4 g = u_entry ? make_uint4(0, 0, 0, 0) : rng(offset0 + (uint64_t)i, ep | 6ull);
+    const uint32_t gk[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      if (c < cols) {
+        const float u = u_entry ? u_entry[(long long)r * cols + c] : (1.0f - u32_to_unit_open(gk[j]));
+        if (guide && u >= q_zero) state[(long long)r * ld + c] = 1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Sparse one-hot encoder (inference): S[r,:] = base + sum_{i in row} delta[i,:]
 // ---------------------------------------------------------------------------------------------
 // delta[i,k] = W2[k,2i+1] - W2[k,2i] via 32x32 transposing tiles; base accumulated separately.
@@ -684,4 +723,17 @@ extern "C" int gdmcf_counter_add(uint64_t* counter_dev, uint64_t inc, gdmcf_stre
   GD_PRE();
   launch_kernel(counter_add_kernel, 1, 32, 0, st, reinterpret_cast<unsigned long long*>(counter_dev), inc);
   return cuda_check_launch("counter_add_kernel");
+}
+
+extern "C" int gdmcf_graph_noise_step(uint8_t* state, int64_t ld, const float* deg_frac, int t, int batch, float discrete,
+                                      int user_guided, uint64_t seed, uint64_t offset, const uint64_t* epoch_dev,
+                                      const float* u_entry, const float* u_user, int rows, int cols, gdmcf_stream_t stream) {
+  if (!state || rows <= 0 || cols <= 0 || ld < cols || batch <= 0 || (user_guided && !deg_frac)) {
+    set_error("graph_noise_step: bad arguments");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  launch_kernel(graph_noise_step_kernel, grid_1d((long long)rows * ((cols + 3) / 4)), TPB, 0, st, state, (long long)ld, deg_frac, t,
+                batch, discrete, user_guided, seed, offset, epoch_dev, u_entry, u_user, rows, cols);
+  return cuda_check_launch("graph_noise_step_kernel");
 }

@@ -300,6 +300,16 @@ def onehot_noise(x0, rows: int, cols: int, out: torch.Tensor, *, ts=None, discre
                                     offset, ptr(epoch), ptr(out), out.stride(0), rows, cols, stream()), "onehot_noise")
 
 
+def graph_noise_step(state: torch.Tensor, t: int, batch: int, *, deg_frac=None, discrete: float = 0.9995, user_guided: bool = True,
+                     seed: int = 0, offset: int = 0, epoch=None, u_entry=None, u_user=None) -> None:
+    """One reverse step of p_sample's random graph bookkeeping on a uint8 edge matrix [rows, cols] (gdmcf_graph_noise_step)."""
+    require_cuda(state, deg_frac, epoch, u_entry, u_user)
+    assert state.dtype == torch.uint8 and state.dim() == 2 and state.stride(1) == 1
+    rows, cols = state.shape
+    check(load().gdmcf_graph_noise_step(ptr(state), state.stride(0), ptr(deg_frac), int(t), int(batch), discrete, int(user_guided),
+                                        seed, offset, ptr(epoch), ptr(u_entry), ptr(u_user), rows, cols, stream()), "graph_noise_step")
+
+
 def onehot_tables(w2: torch.Tensor, d: int, n_items: int, out=None):
     """out: optional (base, delta) pair from an earlier call, refreshed in place (stable addresses for CUDA graphs)."""
     require_cuda(w2)

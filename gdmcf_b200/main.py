@@ -190,7 +190,7 @@ def main(args):
     diffusion, model = build(args, n_rows, n_item, device)
     diffusion.seed = model.seed = args.random_seed + 1000 * dist.rank
     dist.broadcast_parameters(model)
-    use_engine = not args.eager
+    use_engine = not (args.eager or args.faithful_graph)  # the faithful graph mode builds its edge CSR with host-visible sizes
     optimizer = FusedAdamW(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, modules=[model],
                            capturable=use_engine)
     print("models ready.")

@@ -374,6 +374,10 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         self.init_weights()
         self.sumW = nn.Parameter(torch.tensor(1.0))
         self.item_num, self.user_num = item_num, user_num
+        # faithful graph mode: run LayerGCN over all B + I nodes with the edge set like the reference (item rows included)
+        # instead of the user-row closed form; the results the model returns are the same
+        self.faithful_graph = bool(getattr(args, "faithful_graph", False)) if args is not None else False
+        self._edges = None
         self._engine_init(precision)
 
     def init_weights(self):
@@ -526,6 +530,11 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
     def _user_tower(self, bufs, B: int):
         """GCN on the user rows + sumW mix + row norms (models/DNN.py:1274-1288, :1320)."""
         d3 = 3 * self.hidden
+        edges = getattr(self, "_edges", None)
+        if self.faithful_graph and edges is not None and self.gcn_layers > 0:
+            g_all = self.gcn_all_nodes(bufs["hc"], B, edges)
+            K.mix_rownorm(bufs["hc_f32"], B, d3, g=g_all[:B], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
+            return
         if self.gcn_layers == 0:  # no GCN (:1278): hc * sumW + hc * (1 - sumW)
             K.mix_rownorm(bufs["hc_f32"], B, d3, g=bufs["hc_f32"], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
             return
@@ -546,6 +555,64 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         self._mm(bufs["hc"], wc1, B, 512, d3, act=K.ACT_RELU, bias=c1.bias.detach(), out_bf16=g1.hi, out_bf16_lo=g1.lo)
         self._mm(g1, wc2, B, d3, 512, bias=c2.bias.detach(), out_f32=bufs["g2"])
         K.mix_rownorm(bufs["hc_f32"], B, d3, g=bufs["g2"], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
+
+    # -- faithful graph mode --------------------------------------------------
+    @torch.no_grad()
+    def gcn_all_nodes(self, hc: Bf16Mat, B: int, edges: torch.Tensor) -> torch.Tensor:
+        """LayerGCN over ALL B + I nodes with the user -> item edge set, as the reference runs it (models/DNN.py:1217-1219,
+        1277-1280, 1093-1103): GCNConv = self loops + symmetric in-degree normalisation + aggregation at the target node,
+        here as tcgen05 contractions over all rows + the CSR SpMM kernel (gdmcf_spmm_csr_f32) for the aggregation.
+        edges: [B, I] (non-zero = edge user b -> item i). Returns fp32 [B + I, 3d]; rows [:B] are the user rows the model
+        consumes (identical to the self-loop-only closed form of the default path), rows [B:] the item rows it discards."""
+        I, d3, dev = self.n_item, 3 * self.hidden, hc.hi.device
+        N = B + I
+        G = edges.bool()
+        cnt = G.sum(0)                                             # in-degree of every item node (without the self loop)
+        deg_item = (cnt + 1).float()
+        pairs = G.t().nonzero()                                    # [E, 2] = (item, user), sorted by item then user
+        E_n = pairs.shape[0]
+        rowptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        rowptr[1:B + 1] = torch.arange(1, B + 1, device=dev)       # user rows: the self loop only
+        rowptr[B + 1:] = B + torch.cumsum(cnt + 1, 0)
+        col = torch.empty(N + E_n, dtype=torch.int32, device=dev)
+        val = torch.empty(N + E_n, dtype=torch.float32, device=dev)
+        col[:B] = torch.arange(B, dtype=torch.int32, device=dev)
+        val[:B] = 1.0                                              # deg = 1: weight 1
+        starts = rowptr[B:B + I]
+        col[starts] = (B + torch.arange(I, device=dev)).int()
+        val[starts] = 1.0 / deg_item                               # self loop of an item: deg^-1/2 * deg^-1/2
+        if E_n:
+            item_of = pairs[:, 0]
+            first = torch.cumsum(cnt, 0) - cnt
+            pos = starts[item_of] + 1 + (torch.arange(E_n, device=dev) - first[item_of])
+            col[pos] = pairs[:, 1].int()
+            val[pos] = deg_item[item_of].rsqrt()                   # user (deg 1) -> item: 1 * deg_item^-1/2
+        plan = K.spmm_plan(rowptr.to(torch.int32).cpu(), chunk=128, device=dev)
+        e_op, _ = self._item_operands()
+        c1 = self.gcn_model.conv1
+        wc1 = self._weight_operand("gcn1", c1.lin.weight)
+        w_out = c1.lin.weight.shape[0]                             # hidden (2 layers) or 3d (1 layer)
+        wp = K.round_up(w_out, 64)                                 # the SpMM kernel walks 64-column slabs
+        X1 = torch.zeros(N, wp, dtype=torch.float32, device=dev)
+        self._mm(hc, wc1, B, w_out, d3, out_f32=X1[:B])            # x W^T on the user rows ...
+        self._mm(e_op, wc1, I, w_out, d3, out_f32=X1[B:])          # ... and on the item rows (the reference's dead 211 GF)
+        Y1 = K.spmm_csr(plan, col, val, X1)                        # aggregation at the target nodes
+        bias1 = torch.zeros(wp, dtype=torch.float32, device=dev)
+        bias1[:w_out] = c1.bias.detach()
+        if self.gcn_layers == 1:
+            out = Y1 + bias1
+            self.last_gcn_all = out[:, :w_out]
+            return self.last_gcn_all
+        R = torch.empty_like(Y1)
+        K.bias_act_rows(Y1, N, wp, bias=bias1, act=K.ACT_RELU, out_f32=R)   # relu, then LeakyReLU(0.1) = identity (:1097-1098)
+        Z = K.spmm_csr(plan, col, val, R)                          # A'(R W2^T) = (A' R) W2^T: aggregate in the narrow space
+        c2 = self.gcn_model.conv2
+        wc2 = self._weight_operand("gcn2", c2.lin.weight)
+        Zop = K.cast_bf16(Z[:, :w_out], with_lo=self._lo)
+        out = torch.empty(N, K.round_up(d3, 4), dtype=torch.float32, device=dev)
+        self._mm(Zop, wc2, N, d3, w_out, bias=c2.bias.detach(), out_f32=out)
+        self.last_gcn_all = out[:, :d3]
+        return self.last_gcn_all
 
     def _fused_tower(self) -> bool:
         """bf16 mode uses the one-launch tower kernel (GDMCF_FUSED_TOWER=0: the two contractions + mix kernels)."""
@@ -577,8 +644,8 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
     # -- reference call surface ----------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, timesteps, x_U, index=None, graph=None, RCloss=False):
-        """models/DNN.py:1207-1302. x: fp32 [B, I]; x_U: [B, I, 2]; index: user ids [B]. `graph` is accepted and
-        ignored: it only feeds item rows of the GCN, which the model never reads (see module docstring).
+        """models/DNN.py:1207-1302. x: fp32 [B, I]; x_U: [B, I, 2]; index: user ids [B]. `graph` only feeds item rows of
+        the GCN, which the model never reads (see module docstring): it is ignored unless `faithful_graph` is set.
         Inference/eval forward (no autograd); training goes through GaussianDiffusionDiscrete.training_losses."""
         if RCloss:
             raise NotImplementedError("RCloss is produced by the fused training step (training_losses), not by forward()")
@@ -586,6 +653,8 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         B, I = x.shape
         assert I == self.n_item and timesteps.shape == (B,) and index is not None
         dev = x.device
+        # ct = graph.argmax(2); edges = nonzero(ct) (models/DNN.py:1217-1219) — only consumed in faithful graph mode
+        self._edges = graph.argmax(dim=2).to(torch.uint8) if (self.faithful_graph and graph is not None) else None
         ts = _as_i32(timesteps)
         bufs = self._hc_buffers(B, dev)
         p = self.drop.p if self.training else 0.0
@@ -610,7 +679,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
 
     @torch.no_grad()
     def reverse_loop(self, x0_f32, B: int, index, steps_total: int, c1, c2, x0_op: Optional[Bf16Mat] = None,
-                     csr=None, users=None, xu_op: Optional[torch.Tensor] = None, noise_hook=None):
+                     csr=None, users=None, xu_op: Optional[torch.Tensor] = None, noise_hook=None, graph_hook=None):
         """The p_sample loop (models/gaussian_diffusion.py:695-752) for GDMCF. The one-hot encoder's pre-activation
         S(x_tU) does not depend on t and is computed once: sparse gather from the CSR rows when x_tU = one_hot(x0)
         (csr=(rowptr, col), users), else one dense GEMM on `xu_op` [B, 2I]. Per step: encoder GEMM (split-K) ->
@@ -645,6 +714,8 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
                 self._encode_onehot_dense(bufs, xx.hi, B, None, t, steps_total, to_S=False, lo=xx.lo)
             else:
                 self._encode_onehot_from_S(bufs, B, None, t, steps_total)
+            # faithful graph mode: the diffusion's random edge bookkeeping of this step (gaussian_diffusion.py:710-729)
+            self._edges = graph_hook(t) if (graph_hook is not None and self.faithful_graph) else None
             self._user_tower(bufs, B)
             last = t == 0
             self._score(bufs, B, nxt, None if last else bufs["xop"], c1=c1, c2=c2, xt=cur, t_const=t)

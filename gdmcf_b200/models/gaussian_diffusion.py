@@ -364,12 +364,29 @@ class GaussianDiffusionDiscrete(nn.Module):
                 z = draws[self.steps - 1 - t].float().contiguous() if draws is not None else None
                 K.qsample_dropout(x_f32, B, I, x_op_, t_const=t, sqrt_ab=self._f32["ones"], sqrt_1mab=self._f32["noise_sigma"],
                                   noise=z, seed=self.seed, offset=self._offset(), epoch=self._epoch, xt_out=x_f32)
+        graph_hook = None
+        if gdmcf and getattr(model, "faithful_graph", False):
+            # faithful graph mode: the per-step random edge set of the reference (:710-729) — apply_noise on the accumulated
+            # graph, degree-guided user draw (x_degree / x_degree.max() is a batch-global reduction, :711-712), OR-accumulate
+            self._graph_state = torch.zeros(B, I, dtype=torch.uint8, device=dev)
+            deg = x0[:, :I].sum(dim=1)
+            deg_frac = (deg / deg.max()).float().contiguous()
+            guided = bool(getattr(self.args, "user_guided", 1)) if self.args is not None else True
+            g_inj = inject.get("graph_draws") if inject else None  # optional [(u_entry [B, I], u_user [B])] per step
+            if self._epoch is None:
+                self._begin_step(dev)
+
+            def graph_hook(t):
+                u_e, u_u = g_inj[self.steps - 1 - t] if g_inj is not None else (None, None)
+                K.graph_noise_step(self._graph_state, t, B, deg_frac=deg_frac, discrete=float(self.discrete), user_guided=guided,
+                                   seed=self.seed, offset=self._offset(), epoch=self._epoch, u_entry=u_e, u_user=u_u)
+                return self._graph_state
         if gdmcf:
             if getattr(model, "needs_dense_onehot", False) and xu_op is None:
                 xu_op = torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)
                 K.onehot_noise(x0, B, I, xu_op)
             out = model.reverse_loop(x_t, B, idx32, self.steps, c1, c2, x0_op=x_op, csr=csr, users=users, xu_op=xu_op,
-                                     noise_hook=noise_hook)
+                                     noise_hook=noise_hook, graph_hook=graph_hook)
         else:
             out = model.reverse_loop(x_t, B, None, self.steps, c1, c2, x0_op=x_op, noise_hook=noise_hook)
         # the loop's result lives in a cached ping-pong buffer that the next call overwrites: the public API hands back a

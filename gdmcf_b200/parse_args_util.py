@@ -74,6 +74,9 @@ def build_parser():
     parser.add_argument('--eval_every', type=int, default=5)
     parser.add_argument('--checkpoint_every', type=int, default=0, help='write <out_path>/checkpoint.pt every N epochs (0 = never)')
     parser.add_argument('--resume', type=str, default='', help='checkpoint.pt to continue from (weights, AdamW state, Lt_history, RNG)')
+    parser.add_argument('--faithful_graph', action='store_true',
+                        help="run the reference's per-step random edge bookkeeping and LayerGCN over all B + I nodes (item rows "
+                             "included) instead of the user-row closed form; same results, for parity work (implies --eager)")
     parser.add_argument('--eager', action='store_true',
                         help='run the loop call by call through the reference-shaped API instead of the captured StepEngine programs')
     parser.add_argument('--nccl_sms', type=int, default=32, help='torchrun: SMs the contractions leave to NCCL while collectives are in flight')

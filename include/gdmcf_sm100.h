@@ -192,6 +192,15 @@ int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t* ts, float 
                        const float* u_keep, const float* u_drop, uint64_t seed, uint64_t offset,
                        const uint64_t* epoch_dev, void* out_bf16, int64_t ld_out, int rows, int cols, gdmcf_stream_t stream);
 
+/* One reverse step of p_sample's random graph bookkeeping (models/gaussian_diffusion.py:710-729; "faithful graph" mode —
+ * the edges only feed GCN item rows that the model never reads, so the default path skips it): state uint8 [rows, ld],
+ * state |= guide_b & (class-0 entry flips to 1 w.p. (1 - t/batch)(1 - discrete)), guide_b ~ Bernoulli(deg_frac[b]) when
+ * user_guided (deg_frac = row degree / max row degree of the batch), else 1. u_entry [rows, cols] / u_user [rows]: optional
+ * injected uniforms replacing the Philox draws. */
+int gdmcf_graph_noise_step(uint8_t* state, int64_t ld, const float* deg_frac, int t, int batch, float discrete,
+                           int user_guided, uint64_t seed, uint64_t offset, const uint64_t* epoch_dev, const float* u_entry,
+                           const float* u_user, int rows, int cols, gdmcf_stream_t stream);
+
 /* Inference form of the one-hot encoder (models/DNN.py:1249-1251 with x_tU = one_hot(x0)):
  * S[r,:] = base[:] + sum_{i in row users[r]} delta[i,:], where base = sum_i W2[:,2i] and
  * delta[i,:] = W2[:,2i+1] - W2[:,2i] are fp32 tables prepared from in_layers2.0.weight. */

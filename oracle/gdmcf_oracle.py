@@ -443,6 +443,16 @@ class OracleDiffusion:
         return x_t
 
 
+def graph_bookkeeping_step(state: torch.Tensor, entry_sample: torch.Tensor, user_sample: torch.Tensor, user_guided: bool = True):
+    """One reverse step of p_sample's random graph bookkeeping (gaussian_diffusion.py:710-729) given the outcomes of its
+    two multinomial draws: entry_sample [B, I] = class sampled by apply_noise(t, one_hot(state)) for every entry,
+    user_sample [B] = the degree-guided draw (class 1 w.p. deg_b / max deg). x_start_io = x_start_i & one_hot(user draw)
+    keeps class 1 only where both are 1 (:721-722); the result is OR-ed into the accumulated state (:726).
+    The probabilities: an entry of class 0 is sampled as 1 w.p. (1 - a)(1 - p), a = t / B (get_Qt_bar :597-614, :775)."""
+    x_io = (entry_sample.bool() & user_sample.bool()[:, None]) if user_guided else entry_sample.bool()
+    return (state.bool() | x_io).long()
+
+
 # --------------------------------------------------------------------------------------------------------
 # Ranking — main.py:267-310, evaluate_utils.py:6-52
 # --------------------------------------------------------------------------------------------------------

@@ -128,3 +128,62 @@ def test_gcn_layers_and_noise_types(g, tag, kw, precision):
     batch = data_utils.DeviceInteractions(sp.csr_matrix(full), "cuda").batch(g["index"].astype(np.int32))
     assert rel(d.p_sample(m, batch, 0), g[tag + "p_sample_s0"]) < tol
     replay(g, tag, m, diffusion(), True, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_faithful_graph_gcn_all_nodes(g, precision):
+    """faithful_graph: LayerGCN over all B + I nodes with the user -> item edges (models/DNN.py:1217-1219,1277-1280) through the
+    tcgen05 contractions + the CSR SpMM kernel. Item rows against the reference's own GCN output (golden, PyG GCNConv
+    restated in oracle/ref_harness.py); user rows and the model output identical to the default closed-form path."""
+    x0, index = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["index"]).cuda()
+    x_U = torch.nn.functional.one_hot(x0.long(), 2).float()
+    xt, ts = torch.from_numpy(g["fwd_x"]).cuda(), torch.from_numpy(g["fwd_ts"]).cuda()
+    m = gdmcf(g, "graph.", precision).eval()
+    base = m(xt, ts, x_U, index=index, graph=x_U.long()).clone()
+    m.faithful_graph = True
+    out = m(xt, ts, x_U, index=index, graph=x_U.long())
+    tol = TOL[precision]["score"]
+    assert rel(out, g["graph.fwd_eval"]) < tol and rel(out, base) < (1e-6 if precision == "fp32" else 2e-3)
+    all_rows = m.last_gcn_all
+    assert all_rows.shape == (B + I, 3 * D)
+    assert rel(all_rows[B:], g["graph.gcn_out"][B:]) < tol * 2      # item rows: neighbour sums of the user rows
+    assert rel(all_rows[:B], g["graph.gcn_out"][:B]) < tol * 2      # user rows: self loop only
+    # an empty edge set leaves the user rows unchanged and reduces item rows to their self loop
+    out0 = m(xt, ts, x_U, index=index, graph=torch.zeros_like(x_U).long())
+    assert rel(out0, base) < (1e-6 if precision == "fp32" else 2e-3)
+
+
+def test_faithful_graph_bookkeeping(g):
+    """gdmcf_graph_noise_step against the reference's recorded draws (exact), its flip probability (statistical), and
+    p_sample in faithful mode: same scores as the default path whatever edges are drawn."""
+    from gdmcf_b200 import kernels as K
+    state = torch.zeros(B, I, dtype=torch.uint8, device="cuda")
+    deg = torch.from_numpy(g["x0"]).sum(1)
+    deg_frac = (deg / deg.max()).float().cuda()
+    for step in range(T):
+        t = T - 1 - step
+        # recorded multinomial outcomes -> uniforms that reproduce them: entry flips iff u >= P(0 -> 0); guide iff u < deg_frac
+        u_e = torch.from_numpy(g["graph.entry_draws"][step]).float().cuda().contiguous()
+        u_u = (1.0 - torch.from_numpy(g["graph.user_draws"][step]).float()).cuda().contiguous()
+        K.graph_noise_step(state, t, B, deg_frac=deg_frac, discrete=0.9995, user_guided=True, u_entry=u_e, u_user=u_u)
+        assert torch.equal(state.cpu().long(), torch.from_numpy(g["graph.states"][step]).long()), step
+    # Philox draws: flip rate of a class-0 entry = (1 - t/batch)(1 - p) for guided users (all users with deg_frac = 1)
+    rows, cols, t, batch, p = 512, 4096, 3, 512, 0.99
+    st = torch.zeros(rows, cols, dtype=torch.uint8, device="cuda")
+    K.graph_noise_step(st, t, batch, deg_frac=torch.ones(rows, device="cuda"), discrete=p, user_guided=True, seed=3, offset=1 << 40)
+    rate, want = st.float().mean().item(), (1 - t / batch) * (1 - p)
+    assert abs(rate - want) < 5 * (want / (rows * cols)) ** 0.5
+    st.zero_()
+    half = torch.full((rows,), 0.5, device="cuda")
+    K.graph_noise_step(st, t, batch, deg_frac=half, discrete=p, user_guided=True, seed=4, offset=2 << 40)
+    guided = (st.sum(1) > 0).float().mean().item()
+    assert abs(guided - 0.5) < 0.12 and abs(st.float().mean().item() - 0.5 * want) < 0.25 * want
+    # p_sample: the random edges cannot change the scores (they only reach item rows)
+    x0, index = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["index"]).cuda()
+    m = gdmcf(g, "graph.", "fp32").eval()
+    d = diffusion()
+    d.args = types.SimpleNamespace(user_guided=1)
+    base = d.p_sample(m, x0, 0, index=index)
+    m.faithful_graph = True
+    faithful = d.p_sample(m, x0, 0, index=index)
+    assert rel(faithful, base) < 1e-6 and m.last_gcn_all.shape == (B + I, 3 * D)
