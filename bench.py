@@ -61,6 +61,9 @@ def parse():
                     help="N > 1: all-reduce + full AdamW on every rank instead of reduce-scatter + sharded AdamW + all-gather")
     ap.add_argument("--kernel_times", action="store_true", help="print a per-kernel device-time table (torch.profiler) to stderr")
     ap.add_argument("--cpu_sample_users", type=int, default=3200)
+    ap.add_argument("--configs", default="all", choices=["all", "fast", "none"],
+                    help="side measurements of the other BASELINE.json configurations appended to the line: all = rank-only, "
+                         "Amazon-Book shape, reverse-steps sweep, scaled 1M x 200k shape; fast = without the scaled shape")
     ap.add_argument("--exact_steps", action="store_true", help="time exactly --steps steps even when that is less than 1 s of work")
     return ap.parse_args()
 
@@ -248,6 +251,83 @@ def run_reference(args):
 # ======================================================================================================
 # engine arm
 # ======================================================================================================
+def measure_case(dist, dev, workload, mode, diff_steps, batch, dims, topk, precision, min_seconds=0.4, nccl_sms=32, cache=None):
+    """One short measurement of another BASELINE.json configuration (driver-visible through the `configs` key of the
+    line): synthetic data of `workload`, GDMCF backbone initialised on the device, StepEngine in resident mode (the step
+    reads the batch's rows from the device-resident CSR through the user ids), captured, timed with CUDA events over
+    >= min_seconds of steps after 3 warm-up replays; max over ranks. mode: "train+rank" | "train" | "rank"."""
+    import numpy as np
+    import scipy.sparse as sp
+    import torch
+    from gdmcf_b200 import data_utils
+    from gdmcf_b200.engine import StepEngine
+    from gdmcf_b200.models import gaussian_diffusion as gd
+    from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    from gdmcf_b200.optim import FusedAdamW
+    G, rank = dist.world_size, dist.rank
+    U, I, P, seed = WORKLOADS[workload]
+    t_setup = time.time()
+    key = (workload, dims, precision)
+    if cache is not None and key in cache:
+        n_user, n_item, train_dev, test_dev, model = cache[key]
+    else:
+        tr, va, te = data_utils.synthetic_interactions(U, I, P, seed)
+        n_user, n_item = int(tr[:, 0].max()) + 1, int(tr[:, 1].max()) + 1
+        mk = lambda p: sp.csr_matrix((np.ones(len(p), dtype=np.float32), (p[:, 0], p[:, 1])), shape=(n_user, n_item))  # noqa: E731
+        train_dev, test_dev = data_utils.DeviceInteractions(mk(tr), dev), data_utils.DeviceInteractions(mk(te), dev)
+        del tr, va, te
+        torch.manual_seed(0)
+        with torch.device(dev):  # parameters are created and initialised on the device (2.6 G parameters at the scaled shape)
+            model = DNNOneHotEmbeddingGCN([n_item, dims], [dims, n_item], 10, item_num=n_item, user_num=n_user, precision=precision)
+        dist.broadcast_parameters(model)
+        if cache is not None:
+            cache[key] = (n_user, n_item, train_dev, test_dev, model)
+    diffusion = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, diff_steps, dev,
+                                             discrete=0.9995, CatOneHot=True)
+    diffusion.indexIn = True
+    diffusion.seed = model.seed = 4321 + rank
+    train = mode != "rank"
+    opt = FusedAdamW(model.parameters(), lr=1e-5, weight_decay=0.0, modules=[model], capturable=True) if train else None
+    topN = [10, topk] if topk > 10 else [topk]
+    eng = StepEngine(model, diffusion, opt, dist, batch_size=batch, n_item=n_item, topk=topk, topN=topN, cap_train_nnz=1,
+                     cap_gt_nnz=1, train=train, rank=mode != "train", nccl_sms=nccl_sms)
+    eng.bind_resident(train_dev, gt_dev=test_dev)
+    n_batches = n_user // batch
+
+    def users_of(step):
+        b = (step * G + rank) % n_batches
+        return torch.arange(b * batch, (b + 1) * batch, dtype=torch.int32, device=dev)
+
+    eng.load_users(users_of(0))
+    eng.capture(warmup=2)
+    setup_s = time.time() - t_setup
+
+    def run(n, off):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s_ in range(n):
+            eng.load_users(users_of(off + s_))
+            eng.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if G > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    ms3 = run(3, 1)  # warm-up replays, also sizes the timed region
+    n = int(max(5, min(400, -(-min_seconds * 1e3 // max(ms3 / 3, 1e-3)))))
+    ms = run(n, 4)
+    out = {"workload": f"{workload}-shape synthetic", "mode": mode, "n_user": n_user, "n_item": n_item, "interactions": P,
+           "steps": diff_steps, "batch_size": batch, "dims": [dims], "top_k": topk, "n_gpus": G, "timed_steps": n,
+           "ms_per_step": ms / n, "users_per_s": G * batch * n / (ms * 1e-3), "setup_s": round(setup_s, 1),
+           "hbm_gb_allocated": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)}
+    del eng, opt
+    return out
+
+
 def run_engine(args):
     import numpy as np
     import scipy.sparse as sp
@@ -489,6 +569,26 @@ def run_engine(args):
 
     clocks = sampler.stop() if sampler is not None else None
 
+    # ---- the other BASELINE.json configurations, short runs (configs[1]..[4]); the headline above is configs[0]/[1]'s shape
+    extra = []
+    if args.configs != "none" and args.mode == "train+rank" and args.workload == "yelp":
+        cases = [("yelp", "rank", 5)]                                        # configs[2]: inference only, top-20, at N GPUs
+        if G == 1:
+            cases += [("amazon", "train+rank", 5)]                           # configs[1]: Amazon-Book shape on 1 B200
+            cases += [("amazon", "rank", T_) for T_ in (5, 10, 50, 100)]     # configs[3]: reverse-steps sweep
+        if args.configs == "all":
+            cases += [("scaled", "train", 5)]                                # configs[4]: 1M x 200k, 50M pairs, DP training
+        cache = {("yelp", args.dims, args.precision): (n_user, n_item, train_dev, test_dev, model)}
+        for ci, (wl, mode_, T_) in enumerate(cases):
+            try:
+                extra.append(measure_case(dist, dev, wl, mode_, T_, B, args.dims, k, args.precision, nccl_sms=args.nccl_sms,
+                                          cache=cache))
+            except Exception as ex:  # noqa: BLE001  (a side measurement must never take the headline line down)
+                extra.append({"workload": wl, "mode": mode_, "steps": T_, "error": repr(ex)[:300]})
+            if wl != "yelp" and all(c[0] != wl for c in cases[ci + 1:]):
+                cache.pop((wl, args.dims, args.precision), None)  # last use of this shape: release its weights
+                torch.cuda.empty_cache()
+
     if args.kernel_times:  # every rank runs the steps (they contain collectives); rank 0 prints
         # per-kernel device times of 3 steps (CUPTI through torch.profiler) -> stderr table; not part of the JSON line
         from torch.profiler import ProfilerActivity, profile
@@ -526,7 +626,7 @@ def run_engine(args):
                 "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": ms_e2e / Kst},
                 "gpu_launches": int(launches), "launches_per_step": int(launches) // Kst, "cuda_graphs": bool(eng.launches_per_step),
-                "host_enqueue_ms_per_step": host_ms[0], "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu, "parity": parity}
+                "host_enqueue_ms_per_step": host_ms[0], "roofline": roofline, "spmm": spmm, "cpu_baseline": cpu, "parity": parity, "configs": extra}
         print(json.dumps(line), file=OUT, flush=True)
     dist.shutdown()
 
