@@ -565,7 +565,26 @@ def run_engine(args):
                               "note": "the binding resource: nnz x 256 B row gathers over the L2 -> SM fabric (measured "
                                       "ceiling ~9 TB/s, profiles/r1_ncu_summary.json); 70 % of HBM peak on the algorithmic "
                                       "bytes would need 33 TB/s of gathers"}}
-        del lg, flush
+        # bf16 mode: one persistent launch, bf16 iterated tables, hot rows staged in shared memory (spmm_bf16.cu)
+        plan16 = K.lightgcn_plan_bf16(lg.norm_adj_csr[0], col, device=dev)
+        ts16 = []
+        for it in range(13):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            K.lightgcn_propagate_bf16(plan16, lg.dinv, E0, 3, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ts16.append(e0.elapsed_time(e1))
+        t16 = sorted(ts16)[len(ts16) // 2]
+        ref32 = K.lightgcn_propagate(lg.plan, col, val, E0, 3, work=work, dinv=lg.dinv)
+        err16 = float((out - ref32).norm() / ref32.norm())
+        spmm["bf16_mode"] = {"kernel": "lightgcn_bf16_kernel (1 persistent launch, K=3, d=64; fp32 in / out, bf16 iterated tables)",
+                             "ms": t16, "achieved": bytes_alg / (t16 * 1e-3) / 1e9, "frac": bytes_alg / (t16 * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             "unit": "GB/s on the same algorithmic (fp32 interface) bytes", "rel_err_vs_fp32": err16,
+                             "hot_rows_in_smem": plan16.n_hot, "gather_bytes": 3 * nnz * 64 * 2}
+        del lg, flush, plan16
 
     clocks = sampler.stop() if sampler is not None else None
 

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(HERE, "libgdmcf_sm100.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "spmm.cu", "elementwise.cu", "topk.cu", "small.cu", "train.cu", "adamw_refresh.cu", "tower.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "spmm.cu", "elementwise.cu", "topk.cu", "small.cu", "train.cu", "adamw_refresh.cu", "tower.cu", "spmm_bf16.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

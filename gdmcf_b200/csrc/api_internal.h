@@ -40,4 +40,22 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in cuda_check_launch()
 }
 
+// Kernels whose CTAs wait for one another inside ONE launch (grid barriers of a single resident wave: user_tower_kernel,
+// lightgcn_bf16_kernel) are launched cooperatively: the driver either makes every CTA resident at once or fails the launch
+// (rc -3) — a partially resident grid can never spin on CTAs that were not scheduled.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace gd

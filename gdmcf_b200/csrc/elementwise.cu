@@ -240,6 +240,42 @@ __global__ void onehot_noise_kernel(const float* __restrict__ x0, long long ld_x
 }
 
 // ---------------------------------------------------------------------------------------------
+// out[r, c] = bf16(in[r, c] * col_scale[c]) (hi[, lo]); padding columns [cols, ld_out) are zeroed. Operand of the
+// projected reverse loop: the first-layer weight with the items' inverse norms folded into its K dimension.
+// One thread per 8 consecutive columns.
+// ---------------------------------------------------------------------------------------------
+__global__ void scale_cols_cast_kernel(const float* __restrict__ in, long long ld_in, const float* __restrict__ col_scale,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ld_out, int rows,
+                                       int cols) {
+  pdl_entry();
+  const int groups = (int)(ld_out / 8);
+  const long long total = (long long)rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / groups), c0 = (int)(i % groups) * 8;
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float v = c < cols ? in[(long long)r * ld_in + c] * col_scale[c] : 0.f;
+      split_bf16(v, h[j], l[j]);
+    }
+    uint4 ph, pl;
+    ph.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    ph.z = (uint32_t)__bfloat16_as_ushort(h[4]) | ((uint32_t)__bfloat16_as_ushort(h[5]) << 16);
+    ph.w = (uint32_t)__bfloat16_as_ushort(h[6]) | ((uint32_t)__bfloat16_as_ushort(h[7]) << 16);
+    *reinterpret_cast<uint4*>(hi + (long long)r * ld_out + c0) = ph;
+    if (lo) {
+      pl.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+      pl.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+      pl.z = (uint32_t)__bfloat16_as_ushort(l[4]) | ((uint32_t)__bfloat16_as_ushort(l[5]) << 16);
+      pl.w = (uint32_t)__bfloat16_as_ushort(l[6]) | ((uint32_t)__bfloat16_as_ushort(l[7]) << 16);
+      *reinterpret_cast<uint4*>(lo + (long long)r * ld_out + c0) = pl;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Faithful graph bookkeeping of p_sample (models/gaussian_diffusion.py:710-729), one reverse step:
 //   x_i      = apply_noise(t, one_hot(state))           per entry: class 0 -> 1 w.p. (1 - a)(1 - p), a = t / batch
 //   s_b      ~ Bernoulli(deg_b / max_b deg)             "degree-guided" draw per user (:711-716)
@@ -736,4 +772,17 @@ extern "C" int gdmcf_graph_noise_step(uint8_t* state, int64_t ld, const float* d
   launch_kernel(graph_noise_step_kernel, grid_1d((long long)rows * ((cols + 3) / 4)), TPB, 0, st, state, (long long)ld, deg_frac, t,
                 batch, discrete, user_guided, seed, offset, epoch_dev, u_entry, u_user, rows, cols);
   return cuda_check_launch("graph_noise_step_kernel");
+}
+
+extern "C" int gdmcf_scale_cols_cast(const float* in, int64_t ld_in, const float* col_scale, void* out_hi, void* out_lo,
+                                     int64_t ld_out, int rows, int cols, gdmcf_stream_t stream) {
+  if (!in || !col_scale || !out_hi || rows <= 0 || cols <= 0 || ld_in < cols || ld_out < cols || (ld_out & 7) ||
+      ((uintptr_t)out_hi & 15) || ((uintptr_t)out_lo & 15)) {
+    set_error("scale_cols_cast: bad arguments (ld_out %% 8 == 0, 16 B aligned outputs)");
+    return GDMCF_EBADARG;
+  }
+  GD_PRE();
+  launch_kernel(scale_cols_cast_kernel, grid_1d((long long)rows * (ld_out / 8)), TPB, 0, st, in, (long long)ld_in, col_scale,
+                (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, (long long)ld_out, rows, cols);
+  return cuda_check_launch("scale_cols_cast_kernel");
 }

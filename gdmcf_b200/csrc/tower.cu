@@ -424,6 +424,6 @@ extern "C" int gdmcf_user_tower(const void* hc_bf16, int64_t ld_hcb, const float
   const int budget = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
   const int units = std::max(p.mblocks * p.nslices1 * p.ksplit, p.mblocks * p.ntiles2);
   const int grid = std::max(1, std::min(units, budget));
-  launch_kernel(user_tower_kernel, grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), maps, p);
+  launch_kernel_cooperative(user_tower_kernel, grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), maps, p);
   return cuda_check_launch("user_tower_kernel");
 }

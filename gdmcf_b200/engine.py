@@ -394,6 +394,8 @@ class StepEngine:
         if self.train:
             self.opt.flush_lazy()
             self.model.weights_updated()
+            if hasattr(self.model, "refresh_inference_operands"):
+                self.model.refresh_inference_operands()
 
     def _eager_step(self):
         self._main_stream = torch.cuda.current_stream(self.dev)

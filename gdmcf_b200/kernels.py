@@ -85,7 +85,7 @@ def spmm_plan(rowptr, chunk: int = 256, device="cuda") -> SpmmPlan:
     check(lib.gdmcf_spmm_plan(rpp, n_rows, chunk, items.ctypes.data_as(C.c_void_p), ni.value,
                               longs.ctypes.data_as(C.c_void_p), nl.value, C.byref(ni), C.byref(nl), C.byref(ns)), "spmm_plan")
     return SpmmPlan(torch.from_numpy(items).to(device), torch.from_numpy(longs).to(device), ni.value, nl.value,
-                    ns.value, n_rows, chunk)
+                    ns.value, n_rows, chunk)  # device="cpu" keeps the plan on the host (lightgcn_plan_bf16 post-processes it)
 
 
 def spmm_csr(plan: SpmmPlan, col, val, X, Z=None, alpha: float = 1.0, beta: float = 0.0, out=None, scratch=None):
@@ -133,6 +133,74 @@ def lightgcn_sym_work(plan: SpmmPlan, E0):
     n, d = E0.shape
     mk = lambda: torch.zeros(n + 1, d, dtype=torch.float32, device=E0.device)  # noqa: E731
     return (mk(), mk(), torch.empty(max(plan.n_slots, 1), d, dtype=torch.float32, device=E0.device), mk())
+
+
+@dataclass
+class LightgcnBf16Plan:
+    """Device-side work description of gdmcf_lightgcn_propagate_bf16 (see lightgcn_plan_bf16)."""
+    col: torch.Tensor         # int32 [nnz] neighbour lists, hot-first, hot neighbours = 0x80000000 | slot
+    items: torch.Tensor       # int32 [n_items, 4]
+    mids: torch.Tensor        # int32 [n_items] end of each item's hot prefix
+    long_rows: torch.Tensor   # int32 [n_long, 3]
+    hot_rows: torch.Tensor    # int32 [n_hot]
+    n_items: int
+    n_long: int
+    n_hot: int
+    n_rows: int
+    u0: torch.Tensor
+    u1: torch.Tensor
+    scratch: torch.Tensor
+    sync: torch.Tensor
+
+
+def lightgcn_plan_bf16(rowptr, col, chunk: int = 128, device="cuda") -> LightgcnBf16Plan:
+    """Host-side plan: work items (rows / hub-row pieces), the hot set (most frequently gathered rows, staged in shared
+    memory by the kernel) and the hot-first reordering of every row's neighbour list."""
+    lib = load()
+    rp = np.ascontiguousarray(rowptr.cpu().numpy() if isinstance(rowptr, torch.Tensor) else rowptr, dtype=np.int64)
+    cl = np.ascontiguousarray(col.cpu().numpy() if isinstance(col, torch.Tensor) else col, dtype=np.int64)
+    n = rp.shape[0] - 1
+    base = spmm_plan(rp.astype(np.int32), chunk=chunk, device="cpu")
+    items = base.items.numpy().copy()[: base.n_items]
+    longs = base.long_rows.numpy().copy()[: max(base.n_long, 0)]
+    if base.n_long:
+        li_of_row = np.full(n, -1, dtype=np.int64)
+        li_of_row[longs[:, 0]] = np.arange(base.n_long)
+        piece = items[:, 3] >= 0
+        items[piece, 0] = -(li_of_row[items[piece, 0]] + 1)
+    cnt = np.bincount(cl, minlength=n)
+    n_hot = int(min(lib.gdmcf_lightgcn_hot_rows(), np.count_nonzero(cnt)))
+    hot = np.argsort(-cnt, kind="stable")[:n_hot]
+    slot_of = np.full(n, -1, dtype=np.int64)
+    slot_of[hot] = np.arange(n_hot)
+    s = slot_of[cl]
+    is_hot = s >= 0
+    row_of = np.repeat(np.arange(n), np.diff(rp))
+    order = np.lexsort((cl, ~is_hot, row_of))           # by row, hot neighbours first, then ascending id
+    enc = np.where(is_hot, s | 0x80000000, cl).astype(np.uint32)[order].view(np.int32)
+    hot_prefix = np.concatenate([[0], np.cumsum(is_hot[order])])
+    mids = items[:, 1] + (hot_prefix[items[:, 2]] - hot_prefix[items[:, 1]]) if len(items) else np.zeros(1)
+    i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)  # noqa: E731
+    mk = lambda: torch.zeros(n + 1, 64, dtype=torch.bfloat16, device=device)  # noqa: E731
+    return LightgcnBf16Plan(torch.from_numpy(enc.copy()).to(device), i32(items if len(items) else np.zeros((1, 4))), i32(mids),
+                            i32(longs if len(longs) else np.zeros((1, 3))), i32(hot if n_hot else np.zeros(1)),
+                            base.n_items, base.n_long, n_hot, n, mk(), mk(),
+                            torch.empty(max(base.n_slots, 1), 64, dtype=torch.float32, device=device),
+                            torch.zeros(33 + max(base.n_long, 1) + 32, dtype=torch.int32, device=device))
+
+
+def lightgcn_propagate_bf16(plan: LightgcnBf16Plan, dinv, E0, n_layers: int, out=None):
+    """mean_{k<=K} A~^k E0 with bf16 iterated tables, one persistent launch (gdmcf_lightgcn_propagate_bf16)."""
+    require_cuda(dinv, E0, plan.col)
+    n, d = E0.shape
+    assert n == plan.n_rows and d == 64 and E0.dtype == torch.float32 and E0.is_contiguous()
+    if out is None:
+        out = torch.empty_like(E0)
+    check(load().gdmcf_lightgcn_propagate_bf16(ptr(plan.col), ptr(plan.items), ptr(plan.mids), plan.n_items, ptr(plan.long_rows), plan.n_long,
+                                               ptr(plan.hot_rows), plan.n_hot, ptr(dinv), ptr(E0), ptr(plan.u0), ptr(plan.u1),
+                                               ptr(out), ptr(plan.scratch), ptr(plan.sync), n, d, n_layers, stream()),
+          "lightgcn_propagate_bf16")
+    return out
 
 
 def norm_adj_dinv(r_rowptr, rt_rowptr, n_users: int, n_items: int) -> torch.Tensor:
@@ -268,6 +336,18 @@ def cast_bf16_transpose(x: torch.Tensor, with_lo: bool = False, out: Optional[Bf
         out = Bf16Mat.empty(cols, rows, x.device, with_lo, zero=False)
     check(load().gdmcf_cast_bf16_transpose(ptr(x), x.stride(0), ptr(out.hi), ptr(out.lo), out.ld, rows, cols, stream()),
           "cast_bf16_transpose")
+    return out
+
+
+def scale_cols_cast(x: torch.Tensor, cols: int, col_scale: torch.Tensor, with_lo: bool = False, out: Optional[Bf16Mat] = None) -> Bf16Mat:
+    """bf16 operand of x[:, :cols] * col_scale[None, :] (gdmcf_scale_cols_cast)."""
+    require_cuda(x, col_scale)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1 and col_scale.numel() >= cols
+    rows = x.shape[0]
+    if out is None:
+        out = Bf16Mat.empty(rows, cols, x.device, with_lo, zero=False)
+    check(load().gdmcf_scale_cols_cast(ptr(x), x.stride(0), ptr(col_scale), ptr(out.hi), ptr(out.lo), out.ld, rows, cols, stream()),
+          "scale_cols_cast")
     return out
 
 

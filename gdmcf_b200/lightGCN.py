@@ -14,9 +14,13 @@ from . import kernels as K
 
 
 class LightGCN(nn.Module):
-    def __init__(self, data, n_users, n_items, n_layers, latent_dim, device="cuda", chunk=128):
-        """data: mapping with 'user_id_idx' / 'item_id_idx' columns (DataFrame or dict of arrays), as the reference."""
+    def __init__(self, data, n_users, n_items, n_layers, latent_dim, device="cuda", chunk=128, precision="fp32"):
+        """data: mapping with 'user_id_idx' / 'item_id_idx' columns (DataFrame or dict of arrays), as the reference.
+        precision: "fp32" (1e-5 mode, the spmm.cu kernels) or "bf16" (bf16 iterated tables + shared-memory staged hot rows
+        in one persistent launch, spmm_bf16.cu; ~1e-3 normwise on the layer mean; latent_dim must be 64)."""
         super().__init__()
+        assert precision in ("fp32", "bf16")
+        self.precision = precision
         if latent_dim % 64:
             raise NotImplementedError("latent_dim must be a multiple of 64 (the reference uses 64)")
         self.data, self.n_users, self.n_items = data, n_users, n_items
@@ -45,6 +49,7 @@ class LightGCN(nn.Module):
         # D^-1/2 of the interaction graph (pattern only, like build_norm_adj): the propagation uses the separable form
         self.dinv = K.norm_adj_dinv(r_rp, rt_rp, self.n_users, self.n_items)
         self.plan = K.spmm_plan(rowptr.cpu(), chunk=self.chunk, device=dev)
+        self.plan16 = K.lightgcn_plan_bf16(rowptr, col, chunk=self.chunk, device=dev) if self.precision == "bf16" else None
         self.norm_adj_mat_sparse_tensor = (rowptr, col, val)  # reference attribute name; CSR triple here
         return rowptr, col, val
 
@@ -63,6 +68,8 @@ class LightGCN(nn.Module):
 
     def _propagate(self, X: torch.Tensor) -> torch.Tensor:
         _, col, val = self.norm_adj_csr
+        if self.plan16 is not None:
+            return K.lightgcn_propagate_bf16(self.plan16, self.dinv, X.contiguous(), self.n_layers)
         return K.lightgcn_propagate(self.plan, col, val, X.contiguous(), self.n_layers, dinv=self.dinv)
 
     def forward(self, users, pos_items, neg_items):

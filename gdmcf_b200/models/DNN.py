@@ -439,6 +439,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
             self._weight_operand("gcn2", self.gcn_model.conv2.lin.weight)
         self._onehot_tables()   # inference-side: sparse one-hot encoder tables
         self._item_operands()   # item table operand + inverse norms
+        self._weight_operand("E", self.embedding_item.weight, transpose=True)
 
     def refresh_specs(self):
         pr, out = self.precision, {}
@@ -555,6 +556,87 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         self._mm(bufs["hc"], wc1, B, 512, d3, act=K.ACT_RELU, bias=c1.bias.detach(), out_bf16=g1.hi, out_bf16_lo=g1.lo)
         self._mm(g1, wc2, B, d3, 512, bias=c2.bias.detach(), out_f32=bufs["g2"])
         K.mix_rownorm(bufs["hc_f32"], B, d3, g=bufs["g2"], sumw=self.sumW.detach(), out=bufs["hcp"], inv_norm=bufs["inv_u"])
+
+    # -- projected reverse loop ------------------------------------------------------------------------
+    def _projection_operand(self) -> Bf16Mat:
+        """P = W1[:, :I] diag(1 / ||E_i||) E   [d, 3d], K-major bf16 operand (hi[, lo]).
+        The reverse step x_{t-1} = c1[t] * s_t + c2[t] * x_t (models/gaussian_diffusion.py:1047-1050) only ever re-enters
+        the model through the LINEAR first layer h = tanh(W1 [x, emb] + b) (models/DNN.py:1240-1242), and the scores are
+        s_t = ru * (hc' E^T) * ri (:1320-1325). Pushing the recurrence through W1:
+            W1 x_{t-1} = c1[t] * ru * (hc' P^T) + c2[t] * (W1 x_t)
+        so the intermediate steps need a [B, 3d] x [3d, d] product instead of the catalogue-wide scorer [B, 3d] x [3d, I]
+        AND encoder [B, I] x [I, d]; only the last step (c1[0] = 1, c2[0] = 0: its output IS x_0) runs the full scorer.
+        Same arithmetic as the reference up to rounding order; P is rebuilt whenever W1 or E change (one 2*d*3d*I
+        contraction per weight version)."""
+        W1, E = self.in_layers[0].weight, self.embedding_item.weight
+        d, d3, I = self.hidden, 3 * self.hidden, self.n_item
+
+        def build(prev):
+            _, inv_i = self._item_operands()
+            eT = self._weight_operand("E", E, transpose=True)                      # [3d, I]
+            w1r = self._buf(("w1r", self.precision), lambda: Bf16Mat.empty(d, I, W1.device, self._lo))
+            K.scale_cols_cast(W1.detach(), I, inv_i, with_lo=self._lo, out=w1r)      # W1 diag(ri)
+            ok = prev is not None and (prev.rows, prev.cols) == (d, d3) and prev.hi.device == W1.device and (prev.lo is None) != self._lo
+            P = prev if ok else Bf16Mat.empty(d, d3, W1.device, self._lo)
+            self._mm(w1r, eT, d, d3, I, out_bf16=P.hi, out_bf16_lo=P.lo)
+            return P
+        return self._ops.get("proj" + self.precision, [W1, E], build)
+
+    def refresh_inference_operands(self) -> None:
+        """Rebuild (in place) the inference-only operands that no optimizer pass refreshes: the projection P. Called by
+        engine.StepEngine.flush() before inference-only captured programs run on weights that training has changed."""
+        if self.can_project() and self._ops.peek("proj" + self.precision) is not None:
+            self._ops.invalidate("proj")
+            with torch.no_grad():
+                self._projection_operand()
+
+    def can_project(self) -> bool:
+        """The projected reverse loop covers the configured model (noise_type 0, closed-form user rows)."""
+        return self.noise_type == 0 and not self.faithful_graph and os.environ.get("GDMCF_PROJECTED_LOOP", "1") != "0"
+
+    @torch.no_grad()
+    def reverse_loop_projected(self, x0_f32, B: int, index, steps_total: int, c1, c2, x0_op: Optional[Bf16Mat] = None,
+                               csr=None, users=None, xu_op: Optional[torch.Tensor] = None):
+        """The p_sample loop (models/gaussian_diffusion.py:695-752) with the recurrence carried in the encoder's
+        pre-activation space (see _projection_operand). Requires c1[0] = 1, c2[0] = 0 (START_X, every schedule: the last
+        reverse step returns the model output) and no per-step noise. Returns the fp32 buffer [B, ld4] holding x_0."""
+        I, d, dev = self.n_item, self.hidden, x0_f32.device
+        ld4 = x0_f32.shape[1]
+        bufs = self._hc_buffers(B, dev)
+        rb = self._buf(("proj", B, ld4), lambda: dict(out=torch.empty(B, ld4, dtype=torch.float32, device=dev),
+                                                       pa=torch.empty(B, d, dtype=torch.float32, device=dev),
+                                                       pb=torch.empty(B, d, dtype=torch.float32, device=dev)))
+        if xu_op is not None:
+            self._encode_onehot_dense(bufs, xu_op, B, None, 0, steps_total, to_S=True)
+        else:
+            base, delta = self._onehot_tables()
+            K.encode_onehot_gather(csr[0], csr[1], users, B, base, delta, d, bufs["S"])
+        if getattr(self, "_user_rows_staged", False):
+            self._user_rows_staged = False
+        else:
+            f32, hi, lo = self._seg(bufs, 2)
+            K.gather_rows(self.embedding_user.weight.detach(), index, B, d, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+        x_op = x0_op
+        if x_op is None:
+            x_op = bufs["xop"]
+            K.qsample_dropout(x0_f32, B, I, x_op)
+        # W1 x_{T-1}: the only catalogue-wide encoder product of the loop
+        w1 = self._weight_operand("in0", self.in_layers[0].weight, cols=I)
+        cur, nxt = rb["pa"], rb["pb"]
+        self._mm(x_op, w1, B, d, I, out_f32=cur)
+        P = self._projection_operand()
+        tb1, _ = self._tables(steps_total)
+        for t in reversed(range(steps_total)):
+            f32, hi, lo = self._seg(bufs, 0)
+            K.bias_act_rows(cur, B, d, bias=tb1, ld_bias=d, t_const=t, act=K.ACT_TANH, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+            self._encode_onehot_from_S(bufs, B, None, t, steps_total)
+            self._user_tower(bufs, B)
+            if t == 0:
+                self._score(bufs, B, rb["out"])          # x_0 = the model output of the last step
+            else:
+                self._mm(bufs["hcp"], P, B, d, 3 * d, row_scale=bufs["inv_u"], c1=c1, c2=c2, xt=cur, t_const=t, out_f32=nxt)
+                cur, nxt = nxt, cur
+        return rb["out"]
 
     # -- faithful graph mode (SURVEY.md §8f item 3) --------------------------------------------------
     @torch.no_grad()

@@ -148,6 +148,8 @@ class GaussianDiffusionDiscrete(nn.Module):
         else:
             ra, rb = self.posterior_mean_coef1, self.posterior_mean_coef2
         self._f32["reverse_a"], self._f32["reverse_b"] = ra.float().contiguous(), rb.float().contiguous()
+        # the last reverse step returns the model output itself when ra[0] = 1, rb[0] = 0 (START_X: alphas_cumprod_prev[0] = 1)
+        self._last_step_is_output = bool(float(ra[0].float()) == 1.0 and float(rb[0].float()) == 0.0)
         # sampling_noise (:745-750): x_{t-1} = mean + [t != 0] * exp(0.5 * log_variance[t]) * N(0, 1)
         sigma = torch.exp(0.5 * self.posterior_log_variance_clipped)
         sigma[0] = 0.0
@@ -385,8 +387,13 @@ class GaussianDiffusionDiscrete(nn.Module):
             if getattr(model, "needs_dense_onehot", False) and xu_op is None:
                 xu_op = torch.zeros(B, K.round_up(2 * I, 64), dtype=torch.bfloat16, device=dev)
                 K.onehot_noise(x0, B, I, xu_op)
-            out = model.reverse_loop(x_t, B, idx32, self.steps, c1, c2, x0_op=x_op, csr=csr, users=users, xu_op=xu_op,
-                                     noise_hook=noise_hook, graph_hook=graph_hook)
+            if (noise_hook is None and graph_hook is None and self._last_step_is_output and hasattr(model, "can_project")
+                    and model.can_project()):
+                # the recurrence carried in the encoder's pre-activation space: one catalogue-wide scorer instead of T
+                out = model.reverse_loop_projected(x_t, B, idx32, self.steps, c1, c2, x0_op=x_op, csr=csr, users=users, xu_op=xu_op)
+            else:
+                out = model.reverse_loop(x_t, B, idx32, self.steps, c1, c2, x0_op=x_op, csr=csr, users=users, xu_op=xu_op,
+                                         noise_hook=noise_hook, graph_hook=graph_hook)
         else:
             out = model.reverse_loop(x_t, B, None, self.steps, c1, c2, x0_op=x_op, noise_hook=noise_hook)
         # the loop's result lives in a cached ping-pong buffer that the next call overwrites: the public API hands back a

@@ -192,6 +192,26 @@ int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t* ts, float 
                        const float* u_keep, const float* u_drop, uint64_t seed, uint64_t offset,
                        const uint64_t* epoch_dev, void* out_bf16, int64_t ld_out, int rows, int cols, gdmcf_stream_t stream);
 
+/* LightGCN propagation in bf16 mode (lightGCN.py:180-194): out = mean_{k<=K} (A~^k E0) for the binary pattern
+ * `col_hot_first` with D^-1/2 = dinv, all K layers in one persistent launch. The iterated tables are bf16 rows (fp32
+ * accumulation; E0 / out stay fp32), the gdmcf_lightgcn_hot_rows() most frequently gathered rows are staged in shared
+ * memory every layer. Plan (host): items / long_rows from gdmcf_spmm_plan with items[.].row replaced by -(long index + 1)
+ * for hub-row pieces; every row's neighbour list reordered hot-first with a hot neighbour encoded as 0x80000000 | slot;
+ * item_mids[i] = end of item i's hot prefix; hot_rows[slot] = row id. u0 / u1: bf16 [n + 1, 64] with row n zero; scratch: fp32 [n_slots, 64]; sync_block: 33 + n_long + 32
+ * zero-initialised uint32 (counters, left zeroed, + 32 words of phase timestamps). d must be 64. Deterministic. Normwise error vs fp32 ~1e-3. */
+int gdmcf_lightgcn_hot_rows(void);
+int gdmcf_lightgcn_propagate_bf16(const int32_t* col_hot_first, const int32_t* items, const int32_t* item_mids, int n_items, const int32_t* long_rows,
+                                  int n_long, const int32_t* hot_rows, int n_hot, const float* dinv, const float* E0,
+                                  void* u0_bf16, void* u1_bf16, float* out, float* scratch, uint32_t* sync_block, int n, int d,
+                                  int n_layers, gdmcf_stream_t stream);
+
+/* out[r, c] = bf16(in[r, c] * col_scale[c]) as a K-major operand (hi[, lo] residual; columns [cols, ld_out) zeroed).
+ * Builds W1 diag(1/||E_i||), the operand of the projected reverse loop: the next encoder pre-activation
+ * W1 x_{t-1} = c1[t] * ru * hc' (E^T diag(ri) W1^T) + c2[t] * W1 x_t never needs the [B, n_item] scores of the
+ * intermediate reverse steps (models/gaussian_diffusion.py:1047-1050 pushed through the linear first layer, DNN.py:1240). */
+int gdmcf_scale_cols_cast(const float* in, int64_t ld_in, const float* col_scale, void* out_hi, void* out_lo,
+                          int64_t ld_out, int rows, int cols, gdmcf_stream_t stream);
+
 /* One reverse step of p_sample's random graph bookkeeping (models/gaussian_diffusion.py:710-729; "faithful graph" mode —
  * the edges only feed GCN item rows that the model never reads, so the default path skips it): state uint8 [rows, ld],
  * state |= guide_b & (class-0 entry flips to 1 w.p. (1 - t/batch)(1 - discrete)), guide_b ~ Bernoulli(deg_frac[b]) when

@@ -151,6 +151,13 @@ def test_lightgcn_cuda_vs_reference_golden():
     from gdmcf_b200 import kernels as Kk
     out = Kk.lightgcn_propagate(lg.plan, col, val, lg.E0.weight.detach(), K)
     np.testing.assert_allclose(out.cpu().numpy(), np.concatenate([g["final_user"], g["final_item"]]), rtol=0, atol=2e-6)
+    # bf16 mode (spmm_bf16.cu) on the same graph: one persistent launch, ~1e-3 normwise
+    lg16 = LightGCN({"user_id_idx": pairs[:, 0], "item_id_idx": pairs[:, 1]}, nu, ni, K, 64, device="cuda", precision="bf16")
+    with torch.no_grad():
+        lg16.E0.weight.copy_(torch.from_numpy(g["E0"]).cuda())
+        fu16, fi16, _, _ = lg16.propagate_through_layers()
+    ref_all = torch.from_numpy(np.concatenate([g["final_user"], g["final_item"]])).cuda()
+    assert ((torch.cat([fu16, fi16]) - ref_all).norm() / ref_all.norm()).item() < 3e-3
     # differentiable like the reference's torch.sparse.mm chain (its BPR loop trains E0 through forward())
     lg.zero_grad()
     users, pos, neg = torch.tensor([0, 3, 7]).cuda(), torch.tensor([1, 2, 5]).cuda(), torch.tensor([4, 0, 9]).cuda()

@@ -1,9 +1,2 @@
-( time python bench.py > gpurun_out/r2_bench_b.json 2> gpurun_out/r2_bench_b.err ) 2> gpurun_out/r2_bench_b.time
-tail -3 gpurun_out/r2_bench_b.time; tail -3 gpurun_out/r2_bench_b.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_bench_b.json').read())
-print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'frac',d['roofline']['frac'],'spmm',d['spmm']['frac'])
-print('parity',{k:v for k,v in d['parity'].items() if k not in('shape','oracle')})
-for c in d['configs']: print(c)
-PY
+timeout 600 python -m pytest tests/test_headline_parity_gpu.py tests/test_fullsize_gpu.py -x -q -s -k lightgcn 2>&1 | tail -12
+python bench.py --steps 20 --no_cpu_baseline --configs none 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(json.dumps(d['spmm'], indent=1))"
