@@ -186,4 +186,5 @@ def test_faithful_graph_bookkeeping(g):
     base = d.p_sample(m, x0, 0, index=index)
     m.faithful_graph = True
     faithful = d.p_sample(m, x0, 0, index=index)
-    assert rel(faithful, base) < 1e-6 and m.last_gcn_all.shape == (B + I, 3 * D)
+    # (the default path carries the recurrence in the encoder's pre-activation space: same values up to fp32 rounding order)
+    assert rel(faithful, base) < 1e-5 and m.last_gcn_all.shape == (B + I, 3 * D)
