@@ -832,6 +832,31 @@ extern "C" int gdmcf_gemm_auto_splits(int m, int n, int k_total) {
   const int tiles = ((m + BM - 1) / BM) * ((n + bn - 1) / bn);
   const int total_kb = (k_total + BK - 1) / BK;
   const int sms = sm_budget();
+  if (bn == 256 && use_2cta()) {
+    // CTA-pair kernel: work units are (pair of m-blocks, n-block, split) walked by sms / 2 persistent clusters. Pick the
+    // split count that fills whole waves best (a 1000 x 3000 x 34395 product is 48 units: 3 splits = 144 units on 74
+    // clusters instead of 48), among those that keep >= min_kb k-blocks per split; ties go to fewer splits.
+    const int clusters = std::max(1, sms / 2);
+    const int units = (((m + BM - 1) / BM + 1) / 2) * ((n + bn - 1) / bn);
+    static int min_kb2 = 0;
+    if (min_kb2 == 0) {
+      const char* e = getenv("GDMCF_GEMM_MIN_KB");
+      min_kb2 = (e && atoi(e) > 0) ? atoi(e) : 8;
+    }
+    const int max_splits = std::max(1, std::min(16, total_kb / min_kb2));
+    int best = 1;
+    double best_eff = 0.0;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const long long u = (long long)units * sp;
+      const long long waves = (u + clusters - 1) / clusters;
+      // useful fraction of the cluster-waves, minus ~2 % per extra split for its slab epilogue + reduce pass
+      const double eff = (double)u / (double)(waves * clusters) - 0.02 * (sp - 1);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+    }
+    if (units >= clusters && best_eff < (double)units / (double)(((units + clusters - 1) / clusters) * clusters) + 0.05) best = 1;
+    const int per2 = (total_kb + best - 1) / best;
+    return (total_kb + per2 - 1) / per2;
+  }
   if (tiles >= sms) return 1;
   int splits = sms / tiles;
   // keep at least GDMCF_GEMM_MIN_KB (default 8) k-blocks per split: a split costs a partial-slab epilogue (the slow
