@@ -97,7 +97,7 @@ SIGNATURES = {
     "gdmcf_qsample_dropout": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _F, _U64, _U64, _P, _P, _L, _P, _P, _L, _I, _I, _P]),
     "gdmcf_onehot_noise": (_I, [_P, _L, _P, _F, _F, _P, _P, _U64, _U64, _P, _P, _L, _I, _I, _P]),
     "gdmcf_lightgcn_hot_rows": (_I, []),
-    "gdmcf_lightgcn_propagate_bf16": (_I, [_P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "gdmcf_lightgcn_propagate_bf16": (_I, [_P, _P, _P, _I, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "gdmcf_scale_cols_cast": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _P]),
     "gdmcf_graph_noise_step": (_I, [_P, _L, _P, _I, _I, _F, _I, _U64, _U64, _P, _P, _P, _I, _I, _P]),
     "gdmcf_encode_onehot_gather_workspace_bytes": (_SZ, [_I, _I]),

@@ -10,9 +10,9 @@
 //    the user-row half's non-zeros) are copied into a 128 KB shared-memory tile per CTA at the start of every layer; the
 //    plan reorders each row's neighbour list hot-first and encodes a hot neighbour as 0x80000000 | slot, so ~1/3 of all
 //    gathers never leave the SM;
-//  * warp-level segmented reduction: a warp owns a work item (a row, or a <= chunk piece of a hub row); its 4 lane groups
-//    of 8 gather 4 neighbour rows per load instruction (8 x 16 B = one 128 B row), 4 loads in flight per lane, and the
-//    groups' partial sums are folded with two shuffle steps; hub-row pieces go to a scratch slab and the LAST piece to
+//  * warp-level segmented reduction: lane groups of 8 gather one 128 B neighbour row per load instruction (8 x 16 B), 4
+//    loads in flight per lane; a piece of a hub row is walked by a whole warp (4 groups), ordinary rows by half-warps (2
+//    groups each, two rows per warp in flight), and the groups' partial sums are folded with shuffle steps; hub-row pieces go to a scratch slab and the LAST piece to
 //    finish adds them in slab order (deterministic; no floating-point atomics, no second kernel);
 //  * one resident wave of CTAs (one per SM, 32 warps) walks phase 0 (U_0 = bf16(dinv * E0)) and the K layers, separated by
 //    grid barriers: 1 launch instead of 7.
@@ -35,7 +35,8 @@ struct Params {
   const int* col;          // neighbour lists, hot-first; hot neighbours are 0x80000000 | slot
   const int4* items;       // {row or -(long_idx + 1), begin, end, slot or -1}
   const int* mids;         // [n_items] end of the item's hot prefix (begin <= mid <= end)
-  int n_items;
+  int n_items, n_pieces;   // the first n_pieces items are pieces of hub rows (slot >= 0), the others whole rows
+  const int* warp_ptr;     // [grid * WARPS + 1] whole-row items of warp slot w: items[n_pieces + warp_ptr[w] .. n_pieces + warp_ptr[w + 1])
   const int* long_rows;    // {row, first_slot, n_slots}
   int n_long;
   const int* hot_rows;     // [n_hot] row ids staged into shared memory
@@ -159,15 +160,16 @@ lightgcn_bf16_kernel(const Params p) {
     // ---- items: one warp each, dealt round-robin (heavy hub pieces come first in the plan). A neighbour list is hot-first:
     // [begin, mid) are shared-memory slots, [mid, end) global row ids, so each part runs its own loop with one kind of load.
     // The next item's descriptor and this row's own E0 / dinv (epilogue operands) are requested before the gathers.
+    // (a) pieces of hub rows — the first n_pieces items of the plan — one per warp
     const int stride = gridDim.x * WARPS;
     int item = blockIdx.x * WARPS + warp;
     int4 it = make_int4(0, 0, 0, -1);
     int mid = 0;
-    if (item < p.n_items) { it = __ldg(&p.items[item]); mid = __ldg(p.mids + item); }
-    for (; item < p.n_items; item += stride) {
+    if (item < p.n_pieces) { it = __ldg(&p.items[item]); mid = __ldg(p.mids + item); }
+    for (; item < p.n_pieces; item += stride) {
       int4 it_n = make_int4(0, 0, 0, -1);
       int mid_n = 0;
-      if (item + stride < p.n_items) { it_n = __ldg(&p.items[item + stride]); mid_n = __ldg(p.mids + item + stride); }
+      if (item + stride < p.n_pieces) { it_n = __ldg(&p.items[item + stride]); mid_n = __ldg(p.mids + item + stride); }
       const bool whole = it.w < 0;
       float dv = 0.f;
       float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
@@ -269,7 +271,81 @@ lightgcn_bf16_kernel(const Params p) {
       it = it_n;
       mid = mid_n;
     }
+    if (layer == 0 && threadIdx.x == 0) p.sync[HUB_CTR0 + p.n_long + 1 + 32 + 2 * blockIdx.x] = (unsigned int)(globaltimer_ns() - t_start);
+    // (b) whole rows — two per warp: each half-warp (16 lanes = 2 lane groups of 8) walks its own row, so a warp keeps two
+    // dependent chains (descriptor -> neighbour ids -> rows -> epilogue) in flight with the registers of one. Trip counts are
+    // made warp-uniform (max over the two halves); the shorter row's extra trips read the all-zero slot / row. Which rows a
+    // warp walks is fixed by the plan (warp_ptr): pairs of equal cost, dealt so that every warp of the grid carries the same
+    // estimated work including its hub pieces — the layer ends at the slowest warp.
+    {
+      const int l16 = lane & 15, g2 = l16 >> 3;
+      const int wslot = blockIdx.x * WARPS + warp;
+      const int rend = p.n_pieces + __ldg(p.warp_ptr + wslot + 1);
+      int ritem = p.n_pieces + __ldg(p.warp_ptr + wslot) + (lane >> 4);
+      bool have = ritem < rend;
+      int4 rit = make_int4(0, 0, 0, -1);
+      int rmid = 0;
+      if (have) { rit = __ldg(&p.items[ritem]); rmid = __ldg(p.mids + ritem); }
+      while (__any_sync(0xffffffffu, have)) {
+        const int ritem_n = ritem + 2;
+        const bool have_n = ritem_n < rend;
+        int4 rit_n = make_int4(0, 0, 0, -1);
+        int rmid_n = 0;
+        if (have_n) { rit_n = __ldg(&p.items[ritem_n]); rmid_n = __ldg(p.mids + ritem_n); }
+        float dv = 0.f;
+        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+        if (have && l16 < 8) {
+          dv = __ldg(p.dinv + rit.x);
+          e0 = __ldg(reinterpret_cast<const float4*>(p.E0 + (long long)rit.x * D + sub * 8));
+          e1 = __ldg(reinterpret_cast<const float4*>(p.E0 + (long long)rit.x * D + sub * 8 + 4));
+        }
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int nh = have ? rmid - rit.y : 0, nc = have ? rit.z - rmid : 0;
+        const int nh_max = max(nh, __shfl_xor_sync(0xffffffffu, nh, 16));
+        const int nc_max = max(nc, __shfl_xor_sync(0xffffffffu, nc, 16));
+        for (int b = 0; b < nh_max; b += 16) {              // hot neighbours: staged rows
+          const int n = max(0, min(16, nh - b));
+          const int n_u = min(16, nh_max - b);
+          const int cc = l16 < n ? (__ldg(p.col + rit.y + b + l16) & 0x7fffffff) : p.n_hot;
+#pragma unroll 1
+          for (int j0 = 0; j0 < n_u; j0 += 8) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = __shfl_sync(0xffffffffu, cc, j0 + 2 * u + g2, 16);
+              v[u] = lds128(hot_base + (uint32_t)c * 128u + (uint32_t)sub * 16u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) add_bf16x8(acc, v[u]);
+          }
+        }
+        for (int b = 0; b < nc_max; b += 16) {              // the others: 128 B rows from L2
+          const int n = max(0, min(16, nc - b));
+          const int n_u = min(16, nc_max - b);
+          const int cc = l16 < n ? __ldg(p.col + rmid + b + l16) : p.n;
+#pragma unroll 1
+          for (int j0 = 0; j0 < n_u; j0 += 8) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = __shfl_sync(0xffffffffu, cc, j0 + 2 * u + g2, 16);
+              v[u] = __ldg(reinterpret_cast<const uint4*>(src + (long long)c * D + sub * 8));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) add_bf16x8(acc, v[u]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);  // fold the half's two lane groups
+        if (have && l16 < 8) finish_row(p, rit.x, sub, acc, e0, e1, dv, last, dst, inv_layers);
+        ritem = ritem_n;
+        have = have_n;
+        rit = rit_n;
+        rmid = rmid_n;
+      }
+    }
     __syncthreads();
+    if (layer == 0 && threadIdx.x == 0) p.sync[HUB_CTR0 + p.n_long + 1 + 32 + 2 * blockIdx.x + 1] = (unsigned int)(globaltimer_ns() - t_start);
     GD_STAMP();
     if (!last) grid_barrier(&p.sync[bar++], gridDim.x);
     GD_STAMP();
@@ -296,11 +372,12 @@ using namespace gd::spmm16;
 extern "C" int gdmcf_lightgcn_hot_rows(void) { return HOT_ROWS; }
 
 extern "C" int gdmcf_lightgcn_propagate_bf16(const int32_t* col_hot_first, const int32_t* items, const int32_t* item_mids, int n_items,
+                                             int n_pieces, const int32_t* warp_ptr, int n_warp_slots,
                                              const int32_t* long_rows, int n_long, const int32_t* hot_rows, int n_hot,
                                              const float* dinv, const float* E0, void* u0_bf16, void* u1_bf16, float* out,
                                              float* scratch, uint32_t* sync_block, int n, int d, int n_layers,
                                              gdmcf_stream_t stream) {
-  if (!col_hot_first || !items || !item_mids || !dinv || !E0 || !u0_bf16 || !u1_bf16 || !out || !sync_block || n <= 0 || n_items < 0 ||
+  if (!col_hot_first || !items || !item_mids || !warp_ptr || n_warp_slots < WARPS || n_warp_slots % WARPS || !dinv || !E0 || !u0_bf16 || !u1_bf16 || !out || !sync_block || n <= 0 || n_items < 0 ||
       n_layers < 1 || n_layers + 1 > MAX_BARRIERS || n_hot < 0 || n_hot > HOT_ROWS || (n_hot > 0 && !hot_rows) ||
       (n_long > 0 && (!long_rows || !scratch))) {
     set_error("lightgcn_propagate_bf16: bad arguments");
@@ -321,12 +398,17 @@ extern "C" int gdmcf_lightgcn_propagate_bf16(const int32_t* col_hot_first, const
   }
   Params p{};
   p.col = col_hot_first; p.items = reinterpret_cast<const int4*>(items); p.mids = item_mids; p.n_items = n_items;
+  p.n_pieces = std::max(0, std::min(n_pieces, n_items));
+  p.warp_ptr = warp_ptr;
   p.long_rows = long_rows; p.n_long = n_long; p.hot_rows = hot_rows; p.n_hot = n_hot;
   p.dinv = dinv; p.E0 = E0;
   p.u[0] = reinterpret_cast<__nv_bfloat16*>(u0_bf16); p.u[1] = reinterpret_cast<__nv_bfloat16*>(u1_bf16);
   p.out = out; p.scratch = scratch; p.sync = sync_block; p.n = n; p.n_layers = n_layers;
-  const int sms = gdmcf_num_sms() > 0 ? gdmcf_num_sms() : 148;
-  const int grid = std::max(1, std::min(sms, (n_items + WARPS - 1) / WARPS));
+  const int grid = n_warp_slots / WARPS;  // the plan dealt the rows over exactly this many warps
+  if (grid > gdmcf_num_sms()) {
+    set_error("lightgcn_propagate_bf16: plan made for %d CTAs, device has %d SMs (cooperative launch)", grid, gdmcf_num_sms());
+    return GDMCF_EBADARG;
+  }
   launch_kernel_cooperative(lightgcn_bf16_kernel, grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), p);
   return cuda_check_launch("lightgcn_bf16_kernel");
 }

@@ -144,6 +144,9 @@ class LightgcnBf16Plan:
     long_rows: torch.Tensor   # int32 [n_long, 3]
     hot_rows: torch.Tensor    # int32 [n_hot]
     n_items: int
+    n_pieces: int             # the first n_pieces items are pieces of hub rows
+    warp_ptr: torch.Tensor    # int32 [n_slots + 1] whole-row items of warp slot w: items[n_pieces + warp_ptr[w] : n_pieces + warp_ptr[w + 1]]
+    n_slots: int
     n_long: int
     n_hot: int
     n_rows: int
@@ -180,13 +183,43 @@ def lightgcn_plan_bf16(rowptr, col, chunk: int = 128, device="cuda") -> Lightgcn
     enc = np.where(is_hot, s | 0x80000000, cl).astype(np.uint32)[order].view(np.int32)
     hot_prefix = np.concatenate([[0], np.cumsum(is_hot[order])])
     mids = items[:, 1] + (hot_prefix[items[:, 2]] - hot_prefix[items[:, 1]]) if len(items) else np.zeros(1)
+    n_pieces = int((items[:, 3] >= 0).sum()) if len(items) else 0
+    # Static, cost-balanced dealing. Hub pieces go round-robin over the warp slots (one per warp at a time, kernel part
+    # (a)); whole rows are walked two per warp (part (b)), so they are paired by estimated cost, heaviest first, and every
+    # pair goes to the warp slot with the least work so far (longest-processing-time greedy, seeded with the slot's pieces).
+    # Cost unit = one gather trip of a warp (16 neighbour rows from L2; staged rows ~3x cheaper; +1 per item for the
+    # descriptor / epilogue). The grid barrier at the end of a layer waits for the slowest warp, so this is the layer time.
+    n_slots = 32 * max(int(lib.gdmcf_num_sms()), 1)
+    load_of = np.zeros(n_slots)
+    if n_pieces:
+        pc = np.ceil((items[:n_pieces, 2] - mids[:n_pieces]) / 16) + 0.35 * np.ceil((mids[:n_pieces] - items[:n_pieces, 1]) / 16) + 1.5
+        np.add.at(load_of, np.arange(n_pieces) % n_slots, pc)
+    rows = np.arange(n_pieces, len(items))
+    warp_ptr = np.zeros(n_slots + 1, dtype=np.int64)
+    if len(rows):
+        trips = np.ceil((items[rows, 2] - mids[rows]) / 8) + 0.35 * np.ceil((mids[rows] - items[rows, 1]) / 8)
+        by_cost = rows[np.argsort(-trips, kind="stable")]
+        pair_cost = trips[by_cost - n_pieces][0::2] + 1.0   # the heavier row of each pair sets the trip count
+        import heapq
+        heap = [(float(l), w) for w, l in enumerate(load_of)]
+        heapq.heapify(heap)
+        slot_of_pair = np.empty(len(pair_cost), dtype=np.int64)
+        for j, c in enumerate(pair_cost.tolist()):
+            l, w = heap[0]
+            slot_of_pair[j] = w
+            heapq.heapreplace(heap, (l + c, w))
+        slot_of_row = np.repeat(slot_of_pair, 2)[: len(by_cost)]
+        order_r = np.argsort(slot_of_row, kind="stable")  # by slot, heaviest pair first, pairs kept adjacent
+        perm = by_cost[order_r]
+        warp_ptr[1:] = np.cumsum(np.bincount(slot_of_row, minlength=n_slots))
+        items[n_pieces:], mids[n_pieces:] = items[perm], mids[perm]
     i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)  # noqa: E731
     mk = lambda: torch.zeros(n + 1, 64, dtype=torch.bfloat16, device=device)  # noqa: E731
     return LightgcnBf16Plan(torch.from_numpy(enc.copy()).to(device), i32(items if len(items) else np.zeros((1, 4))), i32(mids),
                             i32(longs if len(longs) else np.zeros((1, 3))), i32(hot if n_hot else np.zeros(1)),
-                            base.n_items, base.n_long, n_hot, n, mk(), mk(),
+                            base.n_items, n_pieces, i32(warp_ptr), n_slots, base.n_long, n_hot, n, mk(), mk(),
                             torch.empty(max(base.n_slots, 1), 64, dtype=torch.float32, device=device),
-                            torch.zeros(33 + max(base.n_long, 1) + 32, dtype=torch.int32, device=device))
+                            torch.zeros(33 + max(base.n_long, 1) + 32 + 2 * 256, dtype=torch.int32, device=device))
 
 
 def lightgcn_propagate_bf16(plan: LightgcnBf16Plan, dinv, E0, n_layers: int, out=None):
@@ -196,7 +229,9 @@ def lightgcn_propagate_bf16(plan: LightgcnBf16Plan, dinv, E0, n_layers: int, out
     assert n == plan.n_rows and d == 64 and E0.dtype == torch.float32 and E0.is_contiguous()
     if out is None:
         out = torch.empty_like(E0)
-    check(load().gdmcf_lightgcn_propagate_bf16(ptr(plan.col), ptr(plan.items), ptr(plan.mids), plan.n_items, ptr(plan.long_rows), plan.n_long,
+    check(load().gdmcf_lightgcn_propagate_bf16(ptr(plan.col), ptr(plan.items), ptr(plan.mids), plan.n_items, plan.n_pieces,
+                                               ptr(plan.warp_ptr), plan.n_slots,
+                                               ptr(plan.long_rows), plan.n_long,
                                                ptr(plan.hot_rows), plan.n_hot, ptr(dinv), ptr(E0), ptr(plan.u0), ptr(plan.u1),
                                                ptr(out), ptr(plan.scratch), ptr(plan.sync), n, d, n_layers, stream()),
           "lightgcn_propagate_bf16")

@@ -197,10 +197,16 @@ int gdmcf_onehot_noise(const float* x0, int64_t ld_x0, const int32_t* ts, float 
  * accumulation; E0 / out stay fp32), the gdmcf_lightgcn_hot_rows() most frequently gathered rows are staged in shared
  * memory every layer. Plan (host): items / long_rows from gdmcf_spmm_plan with items[.].row replaced by -(long index + 1)
  * for hub-row pieces; every row's neighbour list reordered hot-first with a hot neighbour encoded as 0x80000000 | slot;
- * item_mids[i] = end of item i's hot prefix; hot_rows[slot] = row id. u0 / u1: bf16 [n + 1, 64] with row n zero; scratch: fp32 [n_slots, 64]; sync_block: 33 + n_long + 32
- * zero-initialised uint32 (counters, left zeroed, + 32 words of phase timestamps). d must be 64. Deterministic. Normwise error vs fp32 ~1e-3. */
+ * item_mids[i] = end of item i's hot prefix; the first n_pieces items are the hub-row pieces (dealt round-robin, one
+ * per warp); the whole-row items that warp slot w (= CTA * 32 + warp) walks, two at a time, are
+ * items[n_pieces + warp_ptr[w] .. n_pieces + warp_ptr[w + 1]) — the plan balances estimated cost over the n_warp_slots
+ * slots (a multiple of 32; the grid is n_warp_slots / 32 CTAs and must fit the device: cooperative launch).
+ * hot_rows[slot] = row id. u0 / u1: bf16 [n + 1, 64] with row n zero; scratch: fp32 [n_slots, 64]; sync_block:
+ * 33 + n_long + 32 + 512 zero-initialised uint32 (counters, left zeroed, + phase timestamps for diagnostics). d must
+ * be 64. Deterministic. Normwise error vs fp32 ~1e-3. */
 int gdmcf_lightgcn_hot_rows(void);
-int gdmcf_lightgcn_propagate_bf16(const int32_t* col_hot_first, const int32_t* items, const int32_t* item_mids, int n_items, const int32_t* long_rows,
+int gdmcf_lightgcn_propagate_bf16(const int32_t* col_hot_first, const int32_t* items, const int32_t* item_mids, int n_items, int n_pieces,
+                                  const int32_t* warp_ptr, int n_warp_slots, const int32_t* long_rows,
                                   int n_long, const int32_t* hot_rows, int n_hot, const float* dinv, const float* E0,
                                   void* u0_bf16, void* u1_bf16, float* out, float* scratch, uint32_t* sync_block, int n, int d,
                                   int n_layers, gdmcf_stream_t stream);

@@ -37,6 +37,10 @@ def main():
     dbg = lg.plan16.sync[33 + lg.plan16.n_long:].tolist()
     print("phase stamps (ns since entry; after phase 0, barrier, then per layer: hot staged, items done, barrier): CTA 0", dbg[:11],
           "last CTA", dbg[16:27])
+    import numpy as _np
+    per = _np.array(dbg[32:32 + 2 * 148]).reshape(-1, 2)
+    for name, v in (("hub pieces done", per[:, 0]), ("rows done", per[:, 1])):
+        print(f"layer 0 per CTA, {name}: min {v.min() / 1e3:.1f} median {_np.median(v) / 1e3:.1f} max {v.max() / 1e3:.1f} us")
     N, nnz = n_user + n_item, lg.plan16.col.numel()
     bytes_alg = layers * (nnz * 8 + (N + 1) * 4 + 2 * N * 64 * 4)
     t = sorted(ts[2:])[len(ts[2:]) // 2] if len(ts) > 2 else ts[-1]
