@@ -59,6 +59,8 @@ def parse():
                     help="N = 1: SMs that run AdamW of the big matrices on a side stream while denoise+rank runs on the rest (0: serial; measured slower, see engine.py)")
     ap.add_argument("--replicated_optimizer", action="store_true",
                     help="N > 1: all-reduce + full AdamW on every rank instead of reduce-scatter + sharded AdamW + all-gather")
+    ap.add_argument("--no_factor_exchange", action="store_true",
+                    help="N > 1: reduce-scatter the item table's [n_item, 3d] gradient instead of exchanging its rank-B factors")
     ap.add_argument("--kernel_times", action="store_true", help="print a per-kernel device-time table (torch.profiler) to stderr")
     ap.add_argument("--cpu_sample_users", type=int, default=3200)
     ap.add_argument("--configs", default="all", choices=["all", "fast", "none"],
@@ -387,7 +389,7 @@ def run_engine(args):
                      cap_train_nnz=window_nnz(train_sp), cap_gt_nnz=window_nnz(test_sp), reweight=True,
                      graphs=not args.no_graphs, rank_before_update=not args.rank_after_update, nccl_sms=args.nccl_sms,
                      shard_optimizer=not args.replicated_optimizer, train=args.mode == "train+rank",
-                     overlap_sms=args.overlap_sms)
+                     overlap_sms=args.overlap_sms, factor_exchange=not args.no_factor_exchange)
     eng.load_resident(train_dev, test_dev, *users_of(0))
     eng.capture(warmup=3)
 

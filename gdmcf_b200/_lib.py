@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgdmcf_sm100.so")
 
-MAX_SEG = 3
+MAX_SEG = 8
 EPI_STORE, EPI_BIAS_ACT, EPI_COSINE = 0, 1, 2
 ACT_NONE, ACT_TANH, ACT_RELU = 0, 1, 2
 

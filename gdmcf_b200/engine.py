@@ -35,7 +35,8 @@ class StepEngine:
                  cap_train_nnz: int, cap_gt_nnz: int, reweight: bool = True, graphs: bool = True, device=None,
                  rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
                  shard_min_bytes: int = 64 << 20, train: bool = True, overlap_sms: int = 0,
-                 lazy_user_rows: bool = True, rank: bool = True, sampling_steps: int = 0, sampling_noise: bool = False):
+                 lazy_user_rows: bool = True, rank: bool = True, sampling_steps: int = 0, sampling_noise: bool = False,
+                 factor_exchange: bool = True):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
@@ -80,6 +81,13 @@ class StepEngine:
         # only (1/G of the optimizer pass) and the updated blocks are all-gathered; the derived tensors are then refreshed
         # from the gathered weights. Same communication volume as an all-reduce, 1/G of the optimizer's HBM traffic.
         self._shards = {}
+        # ... except the item table (half of all gradient bytes): its gradient is the rank-B product Gs^T hc' (B = batch rows),
+        # so the ranks exchange the FACTORS instead of the [n_item, 3d] product — every rank receives the row block of each
+        # peer's Gs^T that belongs to its shard (all-to-all, n_item/G x B bf16 per peer) plus each peer's hc'^T (all-gather)
+        # and forms its block of the SUMMED gradient as one contraction whose K runs over the ranks (one K segment per
+        # rank). Same flops as the local gradient contraction it replaces; 24 MB sent per rank and step instead of 360 MB
+        # (Yelp shape, 8 ranks). bf16 mode only (the operands of the local contraction are these bf16 factors anyway).
+        self.factor_exchange = bool(factor_exchange) and G <= _lib.MAX_SEG and not getattr(model, "_lo", True)
         if G > 1 and shard_optimizer and train:
             self._setup_shards(shard_min_bytes)
         self.sparse_user_rows = G > 1 and hasattr(model, "embedding_user")
@@ -109,6 +117,12 @@ class StepEngine:
             p.data = pbuf[:rows]  # the parameter now lives in a row-padded buffer: equal blocks for the all-gather
             views[name] = gbuf[:rows, :cols]
             self._shards[name] = dict(p=p, R=R, gbuf=gbuf, pbuf=pbuf, gview=views[name])
+            if name == "embedding_item.weight" and self.factor_exchange and self.defer_item_norm:
+                Bp = K.round_up(self.B, 64)
+                z = lambda *shape: torch.zeros(*shape, dtype=torch.bfloat16, device=dev)  # noqa: E731
+                # sendA: Gs^T [G * R, Bp] (rows >= n_item and columns >= B stay zero); sendB: hc'^T [3d, Bp]
+                self._shards[name]["fx"] = dict(sendA=z(R * G, Bp), sendB=z(cols, Bp), recvA=z(G, R, Bp), recvB=z(G, cols, Bp))
+                self.model._item_factor_send = (self._shards[name]["fx"]["sendA"], self._shards[name]["fx"]["sendB"])
         self.model._grad_views = views
         self.model.weights_updated()
 
@@ -184,6 +198,12 @@ class StepEngine:
             idx, sums = self._rank_and_metrics()
             self._result = (torch.zeros((), dtype=torch.float64, device=self.dev), idx, sums)
             return
+        if (G > 1 or self.overlap_sms > 0) and self.do_rank and getattr(model, "can_project", lambda: False)():
+            # The ranking phase runs next to the optimizer stream, which rewrites the fp32 master weights in place (row block
+            # update + all-gather). Everything the ranking reads must therefore be derived BEFORE the fork: the projection
+            # operand P = W1 diag(ri) E is the one tensor the reverse loop would otherwise build from fp32 W1 on first use.
+            with torch.no_grad():
+                model._projection_operand()
         model.train()
         opt.zero_grad(set_to_none=True)
         params = dict(model.named_parameters())
@@ -202,6 +222,10 @@ class StepEngine:
                 user_gi = len(groups)
             for n in names:
                 sh = self._shards.get(n)
+                if grads[n] is None:  # exchanged as factors (see __init__): this rank's block is formed in finish_group
+                    assert sh is not None and "fx" in sh
+                    params[n].grad = None
+                    continue
                 if sh is not None and grads[n].data_ptr() != sh["gview"].data_ptr():
                     sh["gview"].copy_(grads[n])  # gradient not produced in place (no _grad_buffer hook for this weight)
                     grads[n] = sh["gview"]
@@ -212,11 +236,12 @@ class StepEngine:
             if G > 1:
                 dense = [grads[n] for n in names
                          if not (self.sparse_user_rows and n == "embedding_user.weight") and n not in self._shards]
+                fx = [n for n in names if grads[n] is None]
                 dense += [row_coef[id(params[n])] for n in names if id(params[n]) in row_coef]  # summed like the gradient
-                rs = [n for n in names if n in self._shards]
-                if not rs and sum(t.numel() * t.element_size() for t in dense) < (64 << 20):
+                rs = [n for n in names if n in self._shards and n not in fx]
+                if not rs and not fx and sum(t.numel() * t.element_size() for t in dense) < (64 << 20):
                     self._small_keys.add(len(groups) - 1)
-                dense = (dense, rs)
+                dense = (dense, rs, fx)
                 if self.sparse_user_rows and has_user:
                     # only B rows of the user table carry a gradient: exchange (ids, rows) instead of the dense table
                     idx, rows = model._user_grad_rows
@@ -257,6 +282,12 @@ class StepEngine:
             mine = [by_param[id(p)] for p in plist if id(p) in by_param] if sharded_rows else []
             for n, sh in mine:  # this rank's row block of the reduce-scattered gradient
                 r0 = self.dist.rank * sh["R"]
+                if "fx" in sh and sh["p"].grad is None:
+                    # factor exchange: block = sum over ranks of Gs_r^T[block rows] hc'_r, K = (rank, batch row)
+                    fx_, cols_ = sh["fx"], sh["p"].shape[1]
+                    K.gemm([fx_["recvA"][r_] for r_ in range(G)], [fx_["recvB"][r_] for r_ in range(G)], sh["R"], cols_,
+                           [self.B] * G, out_f32=sh["gbuf"][r0:r0 + sh["R"], :cols_], splits=1)
+                    # (splits=1: no split-K workspace — this runs on the optimizer stream next to the ranking contractions)
                 opt.update_rows(sh["p"], sh["gview"], r0, r0 + sh["R"], grad_scale=1.0 / G, row_coef=row_coef.get(id(sh["p"])))
             return mine
 
@@ -377,12 +408,16 @@ class StepEngine:
                 works.append(td.all_gather_into_tensor(pbuf.view(-1), pbuf.view(G, -1)[rank], async_op=True))
             self._works[key], self._after[key] = works, []
             return
-        tensors, rs = payload
+        tensors, rs, fx = payload
         group = self.dist.small_group if key in self._small_keys else None
         works, after = self.dist.all_reduce_async(tensors, group=group)
         for n in rs:  # reduce-scatter by row blocks, in place: block `rank` of the buffer receives the sum
             gbuf = self._shards[n]["gbuf"]
             works.append(td.reduce_scatter_tensor(gbuf.view(G, -1)[rank], gbuf.view(-1), op=td.ReduceOp.SUM, async_op=True))
+        for n in fx:  # factors of a rank-B gradient: row blocks of Gs^T to their owners, hc'^T to everyone
+            b = self._shards[n]["fx"]
+            works.append(td.all_to_all_single(b["recvA"].view(-1), b["sendA"].view(-1), async_op=True))
+            works.append(td.all_gather_into_tensor(b["recvB"].view(-1), b["sendB"].view(-1), async_op=True))
         if action == "gather_rows":
             works.append(td.all_gather_into_tensor(self._recv_idx.view(-1), self._send_idx, group=group, async_op=True))
             works.append(td.all_gather_into_tensor(self._recv_rows.view(-1), self._send_rows.view(-1), group=group, async_op=True))

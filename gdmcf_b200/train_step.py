@@ -285,7 +285,10 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     Bp = K.round_up(B, 64)
     # ---- dL/d out, fused with operand production and the norm-term reductions
     Gs = Bf16Mat.empty(B, I, dev, lo, zero=True)
-    GsT = Bf16Mat.empty(I, B, dev, lo, zero=False)
+    # data-parallel engine, bf16 mode: the item table's gradient is exchanged as its factors (engine.StepEngine); Gs^T is
+    # then produced straight into the engine's persistent send buffer and the local contraction is skipped
+    fsend = getattr(model, "_item_factor_send", None) if (defer_item_norm and not lo) else None
+    GsT = Bf16Mat(fsend[0], None, I, B) if fsend is not None else Bf16Mat.empty(I, B, dev, lo, zero=False)
     n_cb = (I + 31) // 32
     colsum = torch.empty(I, dtype=torch.float32, device=dev)
     rowpart = torch.empty(n_cb, B, dtype=torch.float32, device=dev)
@@ -295,7 +298,12 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     hcpT = K.cast_bf16_transpose(c.hcp_f32, with_lo=lo)  # [3d, B]
     gE = _grad_buffer(P["embedding_item.weight"], model, "embedding_item.weight")
     coef_i = -(c.inv_i * c.inv_i) * colsum
-    if defer_item_norm:
+    if fsend is not None:
+        assert fsend[1].shape == hcpT.hi.shape
+        fsend[1].copy_(hcpT.hi)
+        model._item_grad_rowcoef = coef_i
+        yield {"embedding_item.weight": None}
+    elif defer_item_norm:
         # engine path: the row-wise norm term -E_i * ri^2 * c_i is applied by the optimizer pass, which reads E anyway
         # (FusedAdamW.update(row_coef=...)); the contraction then writes 412 MB instead of reading and writing it
         _mm_auto(model, GsT, hcpT, I, d3, B, out_f32=gE)
@@ -304,7 +312,8 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
         _mm_auto(model, GsT, hcpT, I, d3, B, out_f32=gE, row_t=_arange32(model, I, dev),
                  c1=_ones(model, I, dev), c2=coef_i, xt=P["embedding_item.weight"].detach())
         model._item_grad_rowcoef = None
-    yield {"embedding_item.weight": gE}
+    if fsend is None:
+        yield {"embedding_item.weight": gE}
     # ---- cosine backward w.r.t. the user tower: d hc' = Gs E - hc' * ru^2 * r_b
     r_b = K.colsum_f32(rowpart, n_cb, B)
     eT = model._weight_operand("E", model.embedding_item.weight, transpose=True)  # [3d, I]

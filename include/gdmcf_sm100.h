@@ -92,10 +92,12 @@ int gdmcf_build_norm_adj(const int32_t* r_rowptr, const int32_t* r_col, const in
  * K3-K7 — denoiser contractions: C[M,N] = sum_s A_s[M,K_s] * B_s[N,K_s]^T, bf16 operands, fp32
  * accumulation in tensor memory (tcgen05.mma fed by TMA), fused epilogue.
  * Replaces nn.Linear/torch.mm at models/DNN.py:79-86, :1240-1252, :1082-1100 (user rows), :1320-1325.
- * Up to three K segments let one launch consume a concatenated input ([h, h_U, e_user]) or a
- * hi/lo bf16 split of fp32 operands ("fp32 mode": a_hi*b_hi + a_hi*b_lo + a_lo*b_hi).
+ * Up to GDMCF_MAX_SEG K segments let one launch consume a concatenated input ([h, h_U, e_user]), a
+ * hi/lo bf16 split of fp32 operands ("fp32 mode": a_hi*b_hi + a_hi*b_lo + a_lo*b_hi), or the per-rank
+ * factors of a data-parallel weight gradient (sum over ranks of Gs_r^T hc'_r as ONE contraction whose K
+ * runs over the ranks: the factor exchange of engine.StepEngine, 8 ranks = 8 segments).
  * ---------------------------------------------------------------------------------------------- */
-#define GDMCF_MAX_SEG 3
+#define GDMCF_MAX_SEG 8
 
 typedef struct {
   const void* a[GDMCF_MAX_SEG]; /* bf16 [m, k[s]], leading dim lda[s] (multiple of 8), 16B aligned */

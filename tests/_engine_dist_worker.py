@@ -1,7 +1,9 @@
 """Data-parallel check of engine.StepEngine under torchrun (N >= 2, NCCL): the graph-segment engine with overlapped
-all-reduces must equal the same program run eagerly, ranks must stay bit-identical, and the sparse user-row exchange
-+ row-sparse AdamW with exact catch-up must equal a dense all-reduce of the user table's gradient + dense AdamW, and the reduce-scatter + sharded AdamW + all-gather path
-must equal the all-reduce + replicated AdamW path.
+collectives must equal the same program run eagerly (bit for bit), ranks must stay bit-identical; the sparse user-row
+exchange + row-sparse AdamW with exact catch-up must equal a dense all-reduce of the user table's gradient + dense AdamW;
+reduce-scatter + sharded AdamW + all-gather must equal all-reduce + replicated AdamW; and the factor exchange of the item
+table's gradient (all-to-all of Gs^T row blocks + all-gather of hc'^T, one contraction with K over the ranks) must give
+the reduce-scattered gradient block to fp32 rounding.
 usage: torchrun --nproc-per-node N tests/_engine_dist_worker.py  (driven by tests/test_engine_gpu.py::test_engine_data_parallel_torchrun)"""
 import os
 import sys
@@ -32,7 +34,7 @@ def main():
     train_sp, test_sp = mk(tr), mk(te)
     train_dev, test_dev = data_utils.DeviceInteractions(train_sp, dev), data_utils.DeviceInteractions(test_sp, dev)
 
-    def make(graphs, sparse=True, shard=True):
+    def make(graphs, sparse=True, shard=True, fx=True):
         torch.manual_seed(0)
         model = DNNOneHotEmbeddingGCN([n_item, D], [D, n_item], 10, item_num=n_item, user_num=n_user).to(dev)
         diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, T, dev,
@@ -42,16 +44,19 @@ def main():
         opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0, modules=[model], capturable=True)
         eng = StepEngine(model, diff, opt, dist, batch_size=B, n_item=n_item, topk=k, topN=[10, k],
                          cap_train_nnz=int(train_sp.nnz), cap_gt_nnz=int(test_sp.nnz), graphs=graphs, nccl_sms=32,
-                         shard_optimizer=shard, shard_min_bytes=1 << 16, lazy_user_rows=sparse)
+                         shard_optimizer=shard, shard_min_bytes=1 << 16, lazy_user_rows=sparse, factor_exchange=fx)
         eng.sparse_user_rows = eng.sparse_user_rows and sparse
         return model, diff, eng
 
-    # graph segments + sharded optimizer | same program eagerly | eager, dense user-table all-reduce, replicated optimizer
-    engines = [make(True), make(False), make(False, sparse=False, shard=False)]
+    # 0: graph segments + sharded optimizer + factor exchange of the item table's gradient | 1: the same program eagerly |
+    # 2: eager, item table reduce-scattered like the other matrices | 3: eager, dense user-table all-reduce, replicated optimizer
+    engines = [make(True), make(False), make(False, fx=False), make(False, sparse=False, shard=False)]
     for _, _, e in engines:
         e.load_resident(train_dev, test_dev, rank * B, (rank + 1) * B)
-        e.capture(warmup=2)
+        e.capture(warmup=2, preserve_state=True)
+    assert "fx" in engines[0][2]._shards["embedding_item.weight"] and "fx" not in engines[2][2]._shards["embedding_item.weight"]
     n_seg = len(engines[0][2]._segments)
+    ok = True
     for s in range(1, 5):
         lo = ((s * G + rank) * B) % (n_user - B)
         outs = []
@@ -59,22 +64,38 @@ def main():
             e.load_resident(train_dev, test_dev, lo, lo + B)
             loss, idx, sums = e.step()
             outs.append((loss.clone(), idx.clone(), sums.clone()))
-        for j, o in enumerate(outs[1:], 1):
-            same = torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2])
-            if not same:
-                print(f"rank {rank} step {s}: engine 0 vs {j}: loss {outs[0][0].item():.9f} vs {o[0].item():.9f}, "
-                      f"top-k index agreement {(outs[0][1] == o[1]).float().mean().item():.4f}", flush=True)
+        if not (torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])):
+            ok = False
+            print(f"rank {rank} step {s}: graph vs eager: loss {outs[0][0].item():.9f} vs {outs[1][0].item():.9f}, "
+                  f"top-k index agreement {(outs[0][1] == outs[1][1]).float().mean().item():.4f}", flush=True)
+        if s == 1:
+            # all engines started this step from the same weights: this rank's block of the summed item-table gradient, formed
+            # from the exchanged factors (one contraction, K over the ranks) vs reduce-scattered (per-rank products summed by
+            # NCCL) — the same sum in another fp32 association
+            torch.cuda.synchronize()
+            sh0, sh2 = engines[0][2]._shards["embedding_item.weight"], engines[2][2]._shards["embedding_item.weight"]
+            R, c3 = sh0["R"], sh0["p"].shape[1]
+            g0, g2 = sh0["gbuf"][rank * R:(rank + 1) * R, :c3], sh2["gbuf"][rank * R:(rank + 1) * R, :c3]
+            rel = ((g0 - g2).abs().max() / g2.abs().max()).item()
+            print(f"rank {rank}: item-table gradient block, factor exchange vs reduce-scatter: max rel diff {rel:.2e}", flush=True)
+            if not rel < 2e-6:
+                ok = False
     for _, _, e in engines:
         e.flush()  # row-sparse user-table updates: replay the pending zero-gradient steps before comparing weights
     torch.cuda.synchronize()
-    ok = True
-    for (n, pg), (_, pe), (_, pd) in zip(*[m.named_parameters() for m, _, _ in engines]):
+    lr = 1e-3
+    for (n, pg), (_, pe), (_, pr), (_, pd) in zip(*[m.named_parameters() for m, _, _ in engines]):
         if not torch.equal(pg, pe):
             ok = False
             print(f"rank {rank}: graph != eager for {n}: {(pg - pe).abs().max().item():.3e}", flush=True)
-        if not torch.allclose(pg, pd, rtol=0, atol=1e-6):
+        if not torch.allclose(pr, pd, rtol=0, atol=1e-6):
             ok = False
-            print(f"rank {rank}: sharded/sparse != replicated/dense exchange for {n}: {(pg - pd).abs().max().item():.3e}", flush=True)
+            print(f"rank {rank}: sharded/sparse != replicated/dense exchange for {n}: {(pr - pd).abs().max().item():.3e}", flush=True)
+        # factor exchange vs reduce-scatter: gradients equal to fp32 rounding (checked above); AdamW's first steps (second
+        # moment ~ g^2 of very few steps) amplify the rounding, so after 4 steps the weights agree to a fraction of one step
+        if not torch.allclose(pg, pr, rtol=0, atol=0.2 * lr):
+            ok = False
+            print(f"rank {rank}: factor exchange != reduce-scatter for {n}: {(pg - pr).abs().max().item():.3e}", flush=True)
         # ranks identical
         ref = pg.detach().clone()
         td.broadcast(ref, src=0)
