@@ -622,7 +622,7 @@ def run_engine(args):
         tot = sum(e.device_time_total for e in rows)
         if rank == 0:
             print(f"kernel times over 3 steps: total {tot / 3e3:.3f} ms/step", file=sys.stderr)
-            for e in rows[:45]:
+            for e in rows[:90]:
                 print(f"{e.device_time_total / 3e3:9.3f} ms/step  x{e.count / 3:6.1f}  {e.key[:100]}", file=sys.stderr)
 
     cpu, parity = None, None

@@ -130,6 +130,7 @@ SIGNATURES = {
     "gdmcf_ntxent_rows": (_I, [_P, _L, _I, _F, _F, _P, _P, _P, _L, _P]),
     "gdmcf_scatter_rows_add": (_I, [_P, _L, _P, _P, _L, _I, _I, _P]),
     "gdmcf_lt_history_update": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "gdmcf_loss_terms": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "gdmcf_sample_timesteps": (_I, [_P, _P, _I, _I, _I, C.c_double, _U64, _U64, _P, _P, _P, _P, _P]),
 }
 

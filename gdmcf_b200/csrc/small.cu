@@ -148,8 +148,19 @@ colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int cols,
   for (int c0 = blockIdx.x * 32; c0 < cols; c0 += gridDim.x * 32) {
     const int c = c0 + tx;
     float s = 0.f;
-    if (c < cols)
-      for (int r = ty; r < rows; r += 8) s += x[(long long)r * ld + c];
+    if (c < cols) {
+      // 4 independent partial sums per thread (rows ty, ty + 8, ty + 16, ty + 24 mod 32): the loads of a trip are in
+      // flight together instead of one dependent add per L2 round trip; combined in a fixed order
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int r = ty;
+      for (; r + 24 < rows; r += 32) {
+        const float a0 = x[(long long)r * ld + c], a1 = x[(long long)(r + 8) * ld + c];
+        const float a2 = x[(long long)(r + 16) * ld + c], a3 = x[(long long)(r + 24) * ld + c];
+        s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      }
+      for (; r < rows; r += 8) s0 += x[(long long)r * ld + c];
+      s = (s0 + s1) + (s2 + s3);
+    }
     red[ty][tx] = s;
     __syncthreads();
     if (ty == 0 && c < cols) {
@@ -176,11 +187,23 @@ skinny_nn_kernel(const float* __restrict__ A, long long lda, const float* __rest
     float acc[NMAX];
 #pragma unroll
     for (int j = 0; j < NMAX; ++j) acc[j] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float a = A[(long long)m * lda + k];
+    // Branch-free inner loops: column j >= N re-reads column N - 1 (a valid address) into an accumulator that is never
+    // stored, so the loads of a trip are independent of any predicate and issue back to back.
+    const long long sk = tb ? 1 : ldb, sj = tb ? ldb : 1;
+    for (int k0 = lane; k0 < K; k0 += 128) {  // 4 K-steps per trip, their loads issued together (same summation order)
+      float a[4];
 #pragma unroll
-      for (int j = 0; j < NMAX; ++j)
-        if (j < N) acc[j] = fmaf(a, tb ? B[(long long)j * ldb + k] : B[(long long)k * ldb + j], acc[j]);
+      for (int u = 0; u < 4; ++u) a[u] = (k0 + 32 * u < K) ? A[(long long)m * lda + k0 + 32 * u] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = min(k0 + 32 * u, K - 1);   // past the end: a[u] = 0 multiplies a valid element
+        float bv[NMAX];
+        const float* b = B + (long long)k * sk;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) bv[j] = b[(long long)min(j, N - 1) * sj];
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) acc[j] = fmaf(a[u], bv[j], acc[j]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < NMAX; ++j) acc[j] = warp_sum(acc[j]);
@@ -204,6 +227,7 @@ skinny_tn_kernel(const float* __restrict__ A, long long lda, const float* __rest
   extern __shared__ float sB[];  // [K][N] when stage_b
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (stage_b) {
+#pragma unroll 4
     for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
       const int k = i / N, j = i - k * N;
       sB[i] = tb ? B[(long long)j * ldb + k] : B[(long long)k * ldb + j];
@@ -226,16 +250,14 @@ skinny_tn_kernel(const float* __restrict__ A, long long lda, const float* __rest
           for (int u = 0; u < 4; ++u) {
             const float* b = sB + (k + 8 * u) * N;  // same address for the whole warp: broadcast
 #pragma unroll
-            for (int j = 0; j < NMAX; ++j)
-              if (j < N) acc[j] = fmaf(a[u], b[j], acc[j]);
+            for (int j = 0; j < NMAX; ++j) acc[j] = fmaf(a[u], b[min(j, N - 1)], acc[j]);
           }
         }
         for (; k < K; k += 8) {
           const float a = A[(long long)k * lda + m];
           const float* b = sB + k * N;
 #pragma unroll
-          for (int j = 0; j < NMAX; ++j)
-            if (j < N) acc[j] = fmaf(a, b[j], acc[j]);
+          for (int j = 0; j < NMAX; ++j) acc[j] = fmaf(a, b[min(j, N - 1)], acc[j]);
         }
       } else {
         for (int k = ty; k < K; k += 8) {

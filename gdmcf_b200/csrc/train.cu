@@ -318,6 +318,34 @@ lt_history_kernel(const long long* __restrict__ ts, const double* __restrict__ l
   if (lane == 0) count[t] = (long long)min(total, H);
 }
 
+// Per-row loss terms of training_losses (models/gaussian_diffusion.py:906-957, START_X with reweighting) in one launch:
+//   weight_b = t_b == 0 ? 1 : SNR(t_b - 1) - SNR(t_b),  SNR(t) = ac[t] / (1 - ac[t])       (:915-917, :163-165)
+//   hist_b   = weight_b * mse_b                     -> Lt_history update                   (:935)
+//   loss_b   = hist_b / pt_b + 0.1 * closs          -> the step's loss is mean_b(loss_b)   (:951-955)
+//   g_b      = float(weight_b / pt_b * (1 / B))     = d mean(loss) / d mse_b, the seed of the backward pass
+// fp64 like the reference's schedule tensors; every operation is a single correctly rounded IEEE operation in the order
+// the tensor expressions evaluate them (no contraction), so the values equal the tensor-op form bit for bit.
+__global__ void __launch_bounds__(256)
+loss_terms_kernel(const long long* __restrict__ ts, const double* __restrict__ pt, const float* __restrict__ mse,
+                  const double* __restrict__ ac, const float* __restrict__ closs, int B, int T, int reweight,
+                  double* __restrict__ hist_loss, double* __restrict__ loss, float* __restrict__ g_mse) {
+  pdl_entry();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long t = ts[b];
+  double w = 1.0;
+  if (reweight && t > 0 && t < T) {
+    const double a1 = ac[t - 1], a0 = ac[t];
+    w = __dsub_rn(__ddiv_rn(a1, __dsub_rn(1.0, a1)), __ddiv_rn(a0, __dsub_rn(1.0, a0)));
+  }
+  const double h = __dmul_rn(w, (double)mse[b]);
+  hist_loss[b] = h;
+  double l = __ddiv_rn(h, pt[b]);
+  if (closs) l = __dadd_rn(l, (double)__fmul_rn(closs[0], 0.1f));
+  loss[b] = l;
+  g_mse[b] = __double2float_rn(__dmul_rn(__ddiv_rn(w, pt[b]), __ddiv_rn(1.0, (double)B)));
+}
+
 // sample_timesteps(method="importance") of models/gaussian_diffusion.py:959-986 without leaving the device: while any
 // Lt_count[t] < H the draw is uniform with pt = 1 (:961-962); afterwards p = sqrt(mean(Lt_history^2)) normalised,
 // mixed with uniform_prob, t ~ Categorical(p) by inverse CDF, pt = p[t] * T (:964-978). One CTA; thread 0 builds the
@@ -396,6 +424,20 @@ extern "C" int gdmcf_lt_history_update(const int64_t* ts, const double* loss, do
   launch_kernel(lt_history_kernel, (steps + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(ts), loss, lt_history, reinterpret_cast<long long*>(lt_count), batch, steps, history);
   return cuda_check_launch("lt_history_kernel");
+}
+
+extern "C" int gdmcf_loss_terms(const int64_t* ts, const double* pt, const float* mse, const double* alphas_cumprod,
+                                const float* closs, int batch, int steps, int reweight, double* hist_loss, double* loss,
+                                float* g_mse, gdmcf_stream_t stream) {
+  if (!ts || !pt || !mse || !alphas_cumprod || !hist_loss || !loss || !g_mse || batch <= 0 || steps <= 0) {
+    set_error("loss_terms: bad arguments");
+    return GDMCF_EBADARG;
+  }
+  int rc = gdmcf_device_check();
+  if (rc) return rc;
+  launch_kernel(loss_terms_kernel, (batch + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream),
+                reinterpret_cast<const long long*>(ts), pt, mse, alphas_cumprod, closs, batch, steps, reweight, hist_loss, loss, g_mse);
+  return cuda_check_launch("loss_terms_kernel");
 }
 
 extern "C" int gdmcf_sample_timesteps(const double* lt_history, const int64_t* lt_count, int steps, int history, int batch,

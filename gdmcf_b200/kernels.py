@@ -721,6 +721,21 @@ def scatter_rows_add(v, idx, grad, rows: int, cols: int) -> None:
           "scatter_rows_add")
 
 
+def loss_terms(ts, pt, mse, alphas_cumprod, closs, reweight: bool):
+    """(hist_loss f64 [B], loss f64 [B], g_mse f32 [B]) of training_losses in one launch (gdmcf_loss_terms)."""
+    require_cuda(ts, pt, mse, alphas_cumprod, closs)
+    B = ts.numel()
+    assert ts.dtype == torch.int64 and pt.dtype == torch.float64 and mse.dtype == torch.float32 and alphas_cumprod.dtype == torch.float64
+    assert closs is None or closs.dtype == torch.float32
+    assert ts.is_contiguous() and pt.is_contiguous() and mse.is_contiguous() and alphas_cumprod.is_contiguous()
+    hist = torch.empty(B, dtype=torch.float64, device=ts.device)
+    loss = torch.empty(B, dtype=torch.float64, device=ts.device)
+    g = torch.empty(B, dtype=torch.float32, device=ts.device)
+    check(load().gdmcf_loss_terms(ptr(ts), ptr(pt), ptr(mse), ptr(alphas_cumprod), ptr(closs), B, alphas_cumprod.numel(),
+                                  int(bool(reweight)), ptr(hist), ptr(loss), ptr(g), stream()), "loss_terms")
+    return hist, loss, g
+
+
 def lt_history_update(ts, loss, lt_history, lt_count) -> None:
     """In-place Lt_history/Lt_count update (gaussian_diffusion.py:935-949). ts int64 [B], loss fp64 [B]."""
     require_cuda(ts, loss, lt_history, lt_count)

@@ -407,6 +407,11 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
                                                            2 * self.n_item, l2.bias.detach(), T, out=prev))[0]
         return tb1, tb2
 
+    def _emb_table(self, T: int) -> torch.Tensor:
+        """[T, e] time-embedding rows emb_layer(timestep_embedding(t)) — produced together with the bias tables."""
+        self._tables(T)
+        return self._ops.peek(f"tb1.{T}")[1]
+
     def _onehot_tables(self):
         w2 = self.in_layers2[0].weight
         def build(prev):

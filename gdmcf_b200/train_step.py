@@ -284,7 +284,11 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     ones1 = _ones(model, 1, dev)
     Bp = K.round_up(B, 64)
     # ---- dL/d out, fused with operand production and the norm-term reductions
-    Gs = Bf16Mat.empty(B, I, dev, lo, zero=True)
+    Gs = Bf16Mat.empty(B, I, dev, lo, zero=False)  # loss_grad writes every [B, I] element; only the K tail needs zeros
+    if Gs.ld > I:
+        Gs.hi[:, I:].zero_()
+        if Gs.lo is not None:
+            Gs.lo[:, I:].zero_()
     # data-parallel engine, bf16 mode: the item table's gradient is exchanged as its factors (engine.StepEngine); Gs^T is
     # then produced straight into the engine's persistent send buffer and the local contraction is skipped
     fsend = getattr(model, "_item_factor_send", None) if (defer_item_norm and not lo) else None
@@ -414,8 +418,7 @@ def _first_layer_grads(model, diff, c: _Ctx, d_hc_tot, g_closs, P):
     K.ew_binary(K.EW_TANH_BWD, dhU_tot, c.hc_f32[:, d:2 * d], B, d, out_f32=dhU_pre)
     dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)     # [d, B]
     dhU_preT = K.cast_bf16_transpose(dhU_pre, with_lo=lo)
-    emb_table = K.time_bias_table(model.emb_layer.weight.detach(), model.emb_layer.bias.detach(),
-                                  model.in_layers[0].weight.detach(), I, None, T)[1]   # [T, e]
+    emb_table = model._emb_table(T)   # [T, e], produced with the forward's bias tables (same weights)
     emb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
     temb_rows = torch.empty(B, e, dtype=torch.float32, device=dev)
     K.gather_rows(emb_table, c.ts, B, e, out_f32=emb_rows)
@@ -628,16 +631,24 @@ def fused_train_stages(diff, model, x_start, reweight=False, index=None, inject:
     else:
         c = _dnn_forward(model, diff, x0, B, I, ts32, inject)
         closs = None
-    weight = _loss_weight(diff, ts, B, dev, reweight)
-    loss = weight * c.mse
-    diff._update_history(ts, loss)
-    loss = loss / pt
-    if closs is not None:
-        loss = loss + closs * 0.1
+    if (not _is_eps(diff) and c.mse.is_cuda and c.mse.dtype == torch.float32 and pt.dtype == torch.float64
+            and ts.dtype == torch.int64):
+        # the per-row loss terms (weight, history entry, loss, backward seed) in one launch instead of ~20 tensor ops
+        diff.alphas_cumprod = diff.alphas_cumprod.to(dev)
+        hist, loss, g_mse = K.loss_terms(ts.contiguous(), pt.contiguous(), c.mse.contiguous(), diff.alphas_cumprod.contiguous(),
+                                         closs.reshape(1) if closs is not None else None, reweight)
+        diff._update_history(ts, hist)
+    else:
+        weight = _loss_weight(diff, ts, B, dev, reweight)
+        loss = weight * c.mse
+        diff._update_history(ts, loss)
+        loss = loss / pt
+        if closs is not None:
+            loss = loss + closs * 0.1
+        g_mse = (weight / pt / B).float()
     yield "loss", loss.mean()
-    g_mse = (weight / pt / B).float()
     if gdmcf:
-        g_closs = torch.full((), 0.1, dtype=torch.float32, device=dev)
+        g_closs = _vec_cache(model, ("g_closs", str(dev)), lambda: torch.full((), 0.1, dtype=torch.float32, device=dev))
         # sparse_user_grad: the user table's gradient is NOT materialised as a dense [n_user, d] tensor; the caller
         # consumes model._user_grad_rows = (user ids [B], gradient rows [B, d]) after the second stage
         for stage in _gdmcf_backward_stages(model, diff, c, g_mse, g_closs, defer_item_norm, sparse_user_grad):

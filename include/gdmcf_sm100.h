@@ -405,6 +405,14 @@ int gdmcf_ntxent_rows(const float* S, int64_t ld_s, int n, float tau, float eps,
  * ts int64 [batch], loss fp64 [batch], lt_history fp64 [steps, history], lt_count int64 [steps]. */
 int gdmcf_lt_history_update(const int64_t* ts, const double* loss, double* lt_history, int64_t* lt_count, int batch,
                             int steps, int history, gdmcf_stream_t stream);
+/* Per-row loss terms of training_losses (models/gaussian_diffusion.py:906-957; START_X, optional reweighting) in one
+ * launch: weight = t == 0 ? 1 : SNR(t-1) - SNR(t) with SNR = ac / (1 - ac); hist_loss = weight * mse (feeds
+ * gdmcf_lt_history_update); loss = hist_loss / pt + 0.1 * closs[0] (closs may be NULL); g_mse = float(weight / pt / batch),
+ * the backward seed d mean(loss) / d mse. ts int64, pt / alphas_cumprod / hist_loss / loss fp64, mse / closs / g_mse fp32.
+ * Bit-identical to the tensor-op evaluation (single correctly rounded operations in the same order). */
+int gdmcf_loss_terms(const int64_t* ts, const double* pt, const float* mse, const double* alphas_cumprod,
+                     const float* closs, int batch, int steps, int reweight, double* hist_loss, double* loss,
+                     float* g_mse, gdmcf_stream_t stream);
 /* sample_timesteps(method="importance") (models/gaussian_diffusion.py:959-986) on the device, no host sync:
  * uniform draws with pt = 1 until every lt_count[t] == history, then t ~ Categorical(p), p = sqrt(mean(Lt_history^2))
  * normalised and mixed with uniform_prob, pt = p[t] * steps. ts_in != NULL: only pt for the given timesteps.

@@ -579,3 +579,63 @@ def test_onehot_gather_heavy_rows(K):
     assert ((S1 - ref).norm() / ref.norm()).item() < 1e-5 and torch.equal(S1, S2)
     ws = [v for k, v in K._gather_ws.items() if k[2:] == (n_users, d)][0]
     assert int(ws[1].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("m,n,k,trans_a,trans_b,beta", [
+    (400, 10, 1000, False, False, 0.0),   # time-embedding gradient: skinny NN, B staged transposed in shared memory
+    (400, 10, 1000, False, True, 1.0),    # B stored [n, k]
+    (400, 16, 3000, False, False, 0.5),   # B too large to stage (192 KB): global-memory form
+    (10, 10, 400, True, False, 0.0),      # emb_layer weight gradient: skinny TN, one CTA
+    (1000, 10, 400, True, False, 1.0),    # first-layer time columns: skinny TN
+    (70, 45, 130, False, False, 0.0),     # general small form
+    (70, 45, 130, True, True, 2.0),
+])
+def test_sgemm_small_forms(K, m, n, k, trans_a, trans_b, beta):
+    """Every dispatch of gdmcf_sgemm_small (fp32 FMA kernels for the 10-wide time-embedding products, models/DNN.py:1240,
+    :75-77) against torch.mm in fp64."""
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    A = torch.randn((k, m) if trans_a else (m, k), generator=g, device="cuda")
+    B = torch.randn((n, k) if trans_b else (k, n), generator=g, device="cuda")
+    C0 = torch.randn(m, n, generator=g, device="cuda")
+    C = C0.clone()
+    K.sgemm_small(A, B, C, m, n, k, trans_a=trans_a, trans_b=trans_b, alpha=0.75, beta=beta)
+    ref = 0.75 * ((A.t() if trans_a else A).double() @ (B.t() if trans_b else B).double()) + beta * C0.double()
+    assert (C.double() - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    again = C0.clone()
+    K.sgemm_small(A, B, again, m, n, k, trans_a=trans_a, trans_b=trans_b, alpha=0.75, beta=beta)
+    assert torch.equal(C, again)  # fixed summation order
+
+
+@pytest.mark.parametrize("rows,cols", [(400, 1000), (1075, 400), (7, 33), (1, 5)])
+def test_colsum_f32(K, rows, cols):
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    x = torch.randn(rows, cols + 3, generator=g, device="cuda")[:, :cols]  # padded leading dimension
+    got = K.colsum_f32(x, rows, cols)
+    ref = x.double().sum(0)
+    assert (got.double() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(got, K.colsum_f32(x, rows, cols))
+
+
+@pytest.mark.parametrize("reweight,with_closs", [(True, True), (True, False), (False, True)])
+def test_loss_terms_bit_identical_to_tensor_ops(K, reweight, with_closs):
+    """gdmcf_loss_terms == the tensor-op evaluation of training_losses' loss bookkeeping
+    (models/gaussian_diffusion.py:906-957), bit for bit, including t == 0 rows."""
+    T, B = 5, 400
+    g = torch.Generator(device="cuda").manual_seed(5)
+    betas = torch.linspace(1e-4, 0.02, T, dtype=torch.float64, device="cuda")
+    ac = torch.cumprod(1.0 - betas, 0)
+    ts = torch.randint(0, T, (B,), generator=g, device="cuda")
+    ts[:3] = 0
+    pt = torch.rand(B, generator=g, device="cuda", dtype=torch.float64) + 0.5
+    mse = torch.rand(B, generator=g, device="cuda") * 3
+    closs = torch.rand((), generator=g, device="cuda") if with_closs else None
+    hist, loss, g_mse = K.loss_terms(ts, pt, mse, ac, closs.reshape(1) if with_closs else None, reweight)
+    snr = lambda t: ac[t] / (1 - ac[t])  # noqa: E731
+    weight = torch.where(ts == 0, 1.0, snr(ts - 1) - snr(ts)) if reweight else torch.ones(B, device="cuda")
+    l0 = weight * mse
+    l1 = l0 / pt
+    if with_closs:
+        l1 = l1 + closs * 0.1
+    assert hist.dtype == torch.float64 and torch.equal(hist, l0.double())
+    assert torch.equal(loss, l1.double())
+    assert torch.equal(g_mse, (weight / pt / B).float())
