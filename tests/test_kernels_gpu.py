@@ -38,6 +38,10 @@ def _ref_mm(a, b, k):
     (400, 1000, 34395, None),  # encoder shape (Yelp), auto split-K
     (512, 34395, 3000, 1),  # scorer shape (Yelp)
     (37, 50, 100, 3),       # tiny with explicit split-K
+    (4000, 3000, 400, 1),   # weight-gradient shape (K = batch): A-stationary pair kernel, 192 units on 74 clusters
+    (1000, 20011, 400, 1),  # 4 m-pairs x 79 n-tiles: clusters change m-pair mid-range, ragged N
+    (5001, 2999, 130, 1),   # A-stationary with a ragged K (3 k-blocks) and ragged M / N
+    (34395, 3000, 400, 1),  # dE at the Yelp shape
 ])
 def test_gemm_store(K, m, n, k, splits):
     a = _bf16_operand(m, k, 1)
