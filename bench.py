@@ -61,6 +61,8 @@ def parse():
                     help="N > 1: all-reduce + full AdamW on every rank instead of reduce-scatter + sharded AdamW + all-gather")
     ap.add_argument("--no_factor_exchange", action="store_true",
                     help="N > 1: reduce-scatter the item table's [n_item, 3d] gradient instead of exchanging its rank-B factors")
+    ap.add_argument("--no_bf16_gather", action="store_true",
+                    help="N > 1: all-gather the item table's updated rows as fp32 master weights instead of the bf16 operand rows")
     ap.add_argument("--kernel_times", action="store_true", help="print a per-kernel device-time table (torch.profiler) to stderr")
     ap.add_argument("--cpu_sample_users", type=int, default=3200)
     ap.add_argument("--configs", default="all", choices=["all", "fast", "none"],
@@ -389,7 +391,8 @@ def run_engine(args):
                      cap_train_nnz=window_nnz(train_sp), cap_gt_nnz=window_nnz(test_sp), reweight=True,
                      graphs=not args.no_graphs, rank_before_update=not args.rank_after_update, nccl_sms=args.nccl_sms,
                      shard_optimizer=not args.replicated_optimizer, train=args.mode == "train+rank",
-                     overlap_sms=args.overlap_sms, factor_exchange=not args.no_factor_exchange)
+                     overlap_sms=args.overlap_sms, factor_exchange=not args.no_factor_exchange,
+                     bf16_gather=not args.no_bf16_gather)
     eng.load_resident(train_dev, test_dev, *users_of(0))
     eng.capture(warmup=3)
 
@@ -535,6 +538,10 @@ def run_engine(args):
                 else "events around eager launches", "launches_per_step": len(records) / n_prof,
                 "gemm_ms_per_step": gemm_ms / n_prof, "gemm_share_of_step": (gemm_ms / n_prof) / (ms / Kst),
                 "flops_per_step": gemm_flops / n_prof, "by_shape": breakdown}
+    if G > 1:
+        roofline["note"] = ("N > 1: the contractions run next to NCCL on an SM budget (nccl_sms), and the gradient-block "
+                            "contraction of the factor exchange runs on the optimizer stream concurrently with the ranking "
+                            "contractions — every interval is counted in full, so frac understates the N = 1 kernel quality")
 
     # ---- SpMM (lightGCN propagation, K=3, d=64) on the same interaction graph, HBM roofline
     spmm = None

@@ -36,7 +36,7 @@ class StepEngine:
                  rank_before_update: bool = True, nccl_sms: int = 0, shard_optimizer: bool = True,
                  shard_min_bytes: int = 64 << 20, train: bool = True, overlap_sms: int = 0,
                  lazy_user_rows: bool = True, rank: bool = True, sampling_steps: int = 0, sampling_noise: bool = False,
-                 factor_exchange: bool = True):
+                 factor_exchange: bool = True, bf16_gather: bool = True):
         self.model, self.diffusion, self.opt, self.dist = model, diffusion, optimizer, dist
         self.B, self.n_item, self.k, self.topN, self.reweight = batch_size, n_item, topk, list(topN), reweight
         self.use_graphs = graphs
@@ -88,6 +88,13 @@ class StepEngine:
         # rank). Same flops as the local gradient contraction it replaces; 24 MB sent per rank and step instead of 360 MB
         # (Yelp shape, 8 ranks). bf16 mode only (the operands of the local contraction are these bf16 factors anyway).
         self.factor_exchange = bool(factor_exchange) and G <= _lib.MAX_SEG and not getattr(model, "_lo", True)
+        # ... and its updated rows travel back as the bf16 operand the contractions read (plus the row norms) instead of
+        # the fp32 master weights: half the all-gather bytes of the largest matrix, and the owner derives the operand
+        # while the updated values are still in registers. The fp32 master of the item table is then current only on
+        # the rows a rank owns; flush() all-gathers it (checkpoints, state_dict, evaluation of the weights elsewhere).
+        self.bf16_gather = bool(bf16_gather) and not getattr(model, "_lo", True)
+        self._stale_masters = False
+        self._bf16_gather_active = False
         if G > 1 and shard_optimizer and train:
             self._setup_shards(shard_min_bytes)
         self.sparse_user_rows = G > 1 and hasattr(model, "embedding_user")
@@ -117,6 +124,11 @@ class StepEngine:
             p.data = pbuf[:rows]  # the parameter now lives in a row-padded buffer: equal blocks for the all-gather
             views[name] = gbuf[:rows, :cols]
             self._shards[name] = dict(p=p, R=R, gbuf=gbuf, pbuf=pbuf, gview=views[name])
+            if name == "embedding_item.weight" and self.bf16_gather:
+                sh_ = self._shards[name]
+                sh_["hi_sh"] = torch.zeros(R * G, K.round_up(cols, 64), dtype=torch.bfloat16, device=dev)
+                sh_["inv_sh"] = torch.zeros(R * G, dtype=torch.float32, device=dev)
+                sh_["rowpart_sh"] = torch.empty(K.round_up(cols, 64) // 64 * R, dtype=torch.float32, device=dev)  # any split count
             if name == "embedding_item.weight" and self.factor_exchange and self.defer_item_norm:
                 Bp = K.round_up(self.B, 64)
                 z = lambda *shape: torch.zeros(*shape, dtype=torch.bfloat16, device=dev)  # noqa: E731
@@ -260,6 +272,16 @@ class StepEngine:
         order = sorted(range(len(groups)), key=lambda gi: (0 if gi in self._small_keys else 1, gi))
         by_param = {id(sh["p"]): (n, sh) for n, sh in self._shards.items()}
         gathers, refreshed = [], []
+        # parameters whose row blocks are all-gathered as bf16 operand rows (see __init__): needs the operand, its transpose
+        # and the row norms to exist (they do once the model has run), bf16 mode
+        use16 = {}
+        if G > 1 and self.bf16_gather:
+            for n_, sh_ in self._shards.items():
+                spec_ = model.refresh_specs().get(id(sh_["p"])) if "hi_sh" in sh_ else None
+                if spec_ is not None and {"op", "op_t", "inv_norm"} <= set(spec_[0]) and spec_[0]["op"].lo is None \
+                        and spec_[0]["op"].hi.shape[1] == sh_["hi_sh"].shape[1]:
+                    use16[id(sh_["p"])] = spec_
+        self._bf16_gather_active = bool(use16)
 
         def finish_group(gi, sharded_rows: bool, replicated: bool):
             plist = groups[gi]
@@ -288,7 +310,11 @@ class StepEngine:
                     K.gemm([fx_["recvA"][r_] for r_ in range(G)], [fx_["recvB"][r_] for r_ in range(G)], sh["R"], cols_,
                            [self.B] * G, out_f32=sh["gbuf"][r0:r0 + sh["R"], :cols_], splits=1)
                     # (splits=1: no split-K workspace — this runs on the optimizer stream next to the ranking contractions)
-                opt.update_rows(sh["p"], sh["gview"], r0, r0 + sh["R"], grad_scale=1.0 / G, row_coef=row_coef.get(id(sh["p"])))
+                blk = None
+                if id(sh["p"]) in use16:  # derive this block's bf16 operand rows + row norms into the shadow buffers
+                    blk = dict(op_hi=sh["hi_sh"], inv=sh["inv_sh"], rowpart=sh["rowpart_sh"])
+                opt.update_rows(sh["p"], sh["gview"], r0, r0 + sh["R"], grad_scale=1.0 / G, row_coef=row_coef.get(id(sh["p"])),
+                                refresh=blk)
             return mine
 
         side_opt = bool(self._shards) and self.rank_before_update
@@ -338,7 +364,7 @@ class StepEngine:
             for gi in big:
                 yield ("wait", gi, None)
                 mine = finish_group(gi, True, False)
-                yield ("gather", ("ag", gi), [n for n, _ in mine])
+                yield ("gather", ("ag", gi), [(n, id(sh_["p"]) in use16) for n, sh_ in mine])
                 gathers.append((("ag", gi), mine))
             yield ("to_main", None, None)
             idx, sums = rank_and_metrics()
@@ -363,14 +389,23 @@ class StepEngine:
                     yield ("wait", gi, None)
                 mine = finish_group(gi, True, True)
                 if mine:
-                    yield ("gather", ("ag", gi), [n for n, _ in mine])
+                    yield ("gather", ("ag", gi), [(n, id(sh_["p"]) in use16) for n, sh_ in mine])
                     gathers.append((("ag", gi), mine))
         specs = model.refresh_specs() if gathers else {}
         for key, mine in gathers:
             yield ("wait", key, None)
             for n, sh in mine:
                 spec = specs.get(id(sh["p"]))
-                if spec is not None:  # derived tensors from the gathered weights (same producer as the fused refresh)
+                if id(sh["p"]) in use16:
+                    # the gathered rows ARE the operand: copy into the live operand (the ranking phase was still reading
+                    # it while the all-gather ran), transpose for the dgrad operand, adopt the gathered row norms
+                    kw_, names_ = use16[id(sh["p"])]
+                    rows_, cols_ = sh["p"].shape
+                    kw_["op"].hi[:rows_].copy_(sh["hi_sh"][:rows_])
+                    K.transpose_bf16(kw_["op"].hi, rows_, cols_, kw_["op_t"].hi)
+                    kw_["inv_norm"].copy_(sh["inv_sh"][:rows_])
+                    refreshed.append((sh["p"], names_))
+                elif spec is not None:  # derived tensors from the gathered weights (same producer as the fused refresh)
                     K.refresh_derived(sh["p"].data, **spec[0])
                     refreshed.append((sh["p"], spec[1]))
         opt.end_step()
@@ -403,7 +438,11 @@ class StepEngine:
             return
         if action == "gather":  # all-gather of the updated row blocks, in place in the parameter's padded buffer
             works = []
-            for n in payload:
+            for n, as_bf16 in payload:
+                if as_bf16:
+                    for buf in (self._shards[n]["hi_sh"], self._shards[n]["inv_sh"]):
+                        works.append(td.all_gather_into_tensor(buf.view(-1), buf.view(G, -1)[rank], async_op=True))
+                    continue
                 pbuf = self._shards[n]["pbuf"]
                 works.append(td.all_gather_into_tensor(pbuf.view(-1), pbuf.view(G, -1)[rank], async_op=True))
             self._works[key], self._after[key] = works, []
@@ -427,6 +466,13 @@ class StepEngine:
         """Bring lazily updated tables (lazy_user_rows) up to the current optimizer step. Call before the parameters are
         read outside step(): evaluation of other users, state_dict(), checkpoints, comparisons."""
         if self.train:
+            if self._stale_masters:
+                # bf16_gather: the fp32 master rows of the other ranks' blocks were not exchanged during the steps
+                G, rank = self.dist.world_size, self.dist.rank
+                for sh in self._shards.values():
+                    if "hi_sh" in sh:
+                        td.all_gather_into_tensor(sh["pbuf"].view(-1), sh["pbuf"].view(G, -1)[rank])
+                self._stale_masters = False
             self.opt.flush_lazy()
             self.model.weights_updated()
             if hasattr(self.model, "refresh_inference_operands"):
@@ -439,6 +485,7 @@ class StepEngine:
                 self._comm(action, key, tensors)
         finally:
             torch.cuda.set_stream(self._main_stream)
+        self._stale_masters = self._stale_masters or self._bf16_gather_active
         return self._result
 
     # -- state snapshot around the warm-up steps -------------------------------------------------------
@@ -479,6 +526,7 @@ class StepEngine:
                                 st[k] = 0 if old is None else old[k]
         # the captured step reads the bf16 operands / tables derived from the weights at fixed addresses and only rewrites
         # them in its own optimizer pass: re-derive them in place from the restored weights
+        self._stale_masters = False  # every row of every master was just restored from the (complete) snapshot
         self.model.weights_updated()
         by_id = {id(p): p for p in self.model.parameters()}
         for pid, (kw, names) in self.model.refresh_specs().items():
@@ -491,6 +539,8 @@ class StepEngine:
         needs at least one warm-up step (a re-capture of a warmed engine may pass 0). preserve_state: weights, optimizer
         state, Lt_history and RNG counters are put back (in place) after the warm-up, so that the warm-up steps are not
         part of the training run (main.py); the benchmark lets them count as training steps."""
+        if self._stale_masters:
+            self.flush()
         snap = self._snapshot() if preserve_state and warmup > 0 else None
         try:
             self._capture(warmup)
@@ -562,4 +612,5 @@ class StepEngine:
         finally:
             torch.cuda.set_stream(self._main_stream)
         self.model.weights_updated()  # keeps the eager API coherent: its cached operands are stale after a replay
+        self._stale_masters = self._stale_masters or self._bf16_gather_active
         return self._result

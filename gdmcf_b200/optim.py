@@ -85,10 +85,12 @@ class FusedAdamW(torch.optim.Optimizer):
                     K.adamw_fused(p.data, g, st["exp_avg"], st["exp_avg_sq"], **hyper)
 
     @torch.no_grad()
-    def update_rows(self, p, grad, r0: int, r1: int, grad_scale: float = 1.0, row_coef=None) -> None:
+    def update_rows(self, p, grad, r0: int, r1: int, grad_scale: float = 1.0, row_coef=None, refresh=None) -> None:
         """AdamW on rows [r0, r1) of the 2-D parameter p only (a rank's shard of a reduce-scattered gradient). `grad` is
-        the full-shape gradient view whose rows [r0, r1) hold the reduced values. Derived tensors are NOT refreshed: the
-        caller all-gathers the parameter and calls kernels.refresh_derived on the whole matrix."""
+        the full-shape gradient view whose rows [r0, r1) hold the reduced values. Derived tensors are NOT refreshed (the
+        caller all-gathers the parameter and calls kernels.refresh_derived on the whole matrix) unless `refresh` =
+        dict(op_hi=[>= rows, ld] bf16, inv=[>= rows] fp32, rowpart=workspace) is given: then rows [r0, r1) of the bf16
+        operand and of the inverse row norms are produced by the same pass (the caller all-gathers THOSE)."""
         assert p.dim() == 2 and p.is_contiguous() and grad.shape == p.shape and grad.stride(1) == 1
         group = next(g for g in self.param_groups if any(q is p for q in g["params"]))
         st = self.state[p]
@@ -101,10 +103,14 @@ class FusedAdamW(torch.optim.Optimizer):
         if r1 <= r0:
             return
         b1, b2 = group["betas"]
+        derived = {}
+        if refresh is not None:
+            derived = dict(op=K.Bf16Mat(refresh["op_hi"][r0:r1], None, r1 - r0, p.shape[1]), inv_norm=refresh["inv"][r0:r1],
+                           rowpart=refresh["rowpart"])
         K.adamw_refresh(p.data[r0:r1], grad[r0:r1], st["exp_avg"][r0:r1], st["exp_avg_sq"][r0:r1], lr=group["lr"], beta1=b1,
                         beta2=b2, eps=group["eps"], weight_decay=group["weight_decay"], step=st["step"],
                         step_dev=self._step_dev if self._capturable else None, grad_scale=grad_scale,
-                        row_coef=row_coef[r0:r1] if row_coef is not None else None)
+                        row_coef=row_coef[r0:r1] if row_coef is not None else None, **derived)
 
     # -- row-sparse parameters (embedding_user: only the batch's rows carry a gradient) ---------------------------------
     def _lazy_state(self, p):

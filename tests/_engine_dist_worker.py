@@ -44,17 +44,20 @@ def main():
         opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.0, modules=[model], capturable=True)
         eng = StepEngine(model, diff, opt, dist, batch_size=B, n_item=n_item, topk=k, topN=[10, k],
                          cap_train_nnz=int(train_sp.nnz), cap_gt_nnz=int(test_sp.nnz), graphs=graphs, nccl_sms=32,
-                         shard_optimizer=shard, shard_min_bytes=1 << 16, lazy_user_rows=sparse, factor_exchange=fx)
+                         shard_optimizer=shard, shard_min_bytes=1 << 16, lazy_user_rows=sparse, factor_exchange=fx,
+                         bf16_gather=fx)
         eng.sparse_user_rows = eng.sparse_user_rows and sparse
         return model, diff, eng
 
-    # 0: graph segments + sharded optimizer + factor exchange of the item table's gradient | 1: the same program eagerly |
-    # 2: eager, item table reduce-scattered like the other matrices | 3: eager, dense user-table all-reduce, replicated optimizer
+    # 0: graph segments + sharded optimizer + factor exchange of the item table's gradient + its rows all-gathered as the
+    #    bf16 operand | 1: the same program eagerly | 2: eager, item table reduce-scattered / fp32 all-gather like the other
+    #    matrices | 3: eager, dense user-table all-reduce, replicated optimizer
     engines = [make(True), make(False), make(False, fx=False), make(False, sparse=False, shard=False)]
     for _, _, e in engines:
         e.load_resident(train_dev, test_dev, rank * B, (rank + 1) * B)
         e.capture(warmup=2, preserve_state=True)
     assert "fx" in engines[0][2]._shards["embedding_item.weight"] and "fx" not in engines[2][2]._shards["embedding_item.weight"]
+    assert engines[0][2]._bf16_gather_active and not engines[2][2]._bf16_gather_active
     n_seg = len(engines[0][2]._segments)
     ok = True
     for s in range(1, 5):
