@@ -19,6 +19,7 @@ The training half is `train_step.fused_train_stages` — the kernels and arithme
 `metrics_from_device` are the public calls. `graphs=False` runs the same program without capture (parity tests)."""
 from __future__ import annotations
 
+import os
 from typing import Sequence
 
 import torch
@@ -96,7 +97,8 @@ class StepEngine:
         self._stale_masters = False
         self._bf16_gather_active = False
         if G > 1 and shard_optimizer and train:
-            self._setup_shards(shard_min_bytes)
+            # GDMCF_SHARD_MIN_BYTES: size from which a matrix is row-sharded (tests shard toy-sized models through main.py)
+            self._setup_shards(int(os.environ.get("GDMCF_SHARD_MIN_BYTES", shard_min_bytes)))
         self.sparse_user_rows = G > 1 and hasattr(model, "embedding_user")
         # The user table's gradient has B non-zero rows per rank. lazy_user_rows: AdamW touches only those rows; the
         # zero-gradient updates every other row would have received (decaying moments still move the weights) are replayed
@@ -477,6 +479,29 @@ class StepEngine:
             self.model.weights_updated()
             if hasattr(self.model, "refresh_inference_operands"):
                 self.model.refresh_inference_operands()
+
+    def gather_optimizer_state(self) -> None:
+        """Row-sharded optimizer (world_size > 1): every rank holds the AdamW moments of its own row block only. Collective:
+        all-gathers the blocks so that optimizer.state_dict() is complete on every rank (checkpoints). No-op with one rank."""
+        G, rank = self.dist.world_size, self.dist.rank
+        if G == 1 or not self._shards or self.opt is None:
+            return
+        for sh in self._shards.values():
+            st = self.opt.state.get(sh["p"])
+            if not st:
+                continue
+            rows, cols = sh["p"].shape
+            R = sh["R"]
+            r0, r1 = rank * R, min((rank + 1) * R, rows)
+            for key in ("exp_avg", "exp_avg_sq"):
+                t = st[key]
+                blk = torch.zeros(R, cols, dtype=t.dtype, device=t.device)
+                if r1 > r0:
+                    blk[:r1 - r0].copy_(t[r0:r1])
+                full = torch.empty(G * R, cols, dtype=t.dtype, device=t.device)
+                td.all_gather_into_tensor(full.view(-1), blk.view(-1))
+                t.copy_(full[:rows])
+                del blk, full
 
     def _eager_step(self):
         self._main_stream = torch.cuda.current_stream(self.dev)

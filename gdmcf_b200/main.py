@@ -317,6 +317,9 @@ def main(args):
                     print('model_path:', model_path)
                     torch.save(model, model_path)
         if args.checkpoint_every and epoch % args.checkpoint_every == 0:
+            if train_eng is not None:
+                train_eng.flush()  # lazily updated user rows; with several ranks also the fp32 masters gathered as bf16 operands
+                train_eng.gather_optimizer_state()  # row-sharded AdamW: the moments of the other ranks' row blocks
             save_checkpoint(os.path.join(out_path, 'checkpoint.pt'), epoch, model, optimizer, diffusion, rng,
                             (best_recall, best_epoch, best_test_results), dist)
         stats["train_s"].append(train_s)

@@ -75,3 +75,24 @@ def test_main_yelp_shape_epoch_reaches_engine_throughput(tmp_path):
     print(f"main.py yelp shape: train {cli_rate:.0f} users/s, evaluate {eval_rate:.0f} users/s")
     # 136 steps at <= 3.2 ms (the training half of the benchmarked step is ~2.7 ms on B200) and ranking at >= 250 k users/s
     assert cli_rate >= 400 / 3.2e-3 and eval_rate >= 250e3, (cli_rate, eval_rate)
+
+
+@pytest.mark.parametrize("world", [2])
+def test_main_data_parallel_torchrun(tmp_path, world):
+    """main.py under torchrun + NCCL with the big-matrix machinery forced on for the toy model (row-sharded AdamW, factor
+    exchange of the item table's gradient, bf16 operand all-gather): checkpoint + resume == uninterrupted run, bit for bit
+    (tests/_main_dist_worker.py)."""
+    import socket
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_main_dist_worker.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), worker, str(tmp_path)],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stderr.count("main_dist_check rank") == world and "FAILED" not in res.stderr, res.stderr[-2000:]
