@@ -80,8 +80,12 @@ def config_of(args, n_gpus):
             "parallelism": f"dp{n_gpus} (user batches; grad all-reduce)", "l2": "inputs larger than L2 (weights+state ~4 GB)",
             "precision": args.precision,
             "step_order": "train(fwd+bwd) -> AdamW -> denoise+rank" if args.rank_after_update else "train(fwd+bwd) -> denoise+rank -> AdamW",
+            "reverse_loop": "recurrence carried in the first layer's pre-activation space (projection operand rebuilt every step); "
+                            "only the last of the T steps runs the catalogue-wide scorer",
             "nccl_sms": args.nccl_sms, "overlap_sms": args.overlap_sms if n_gpus == 1 else 0,
-            "optimizer": "replicated" if (args.replicated_optimizer or n_gpus == 1) else "row-sharded (reduce-scatter / all-gather)"}
+            "optimizer": "replicated" if (args.replicated_optimizer or n_gpus == 1) else
+            "row-sharded (reduce-scatter / all-gather" + ("" if args.no_factor_exchange else "; item-table gradient exchanged as its rank-B factors")
+            + ("" if args.no_bf16_gather else "; item-table rows gathered as the bf16 operand") + ")"}
 
 
 def peaks():
@@ -522,14 +526,16 @@ def run_engine(args):
     pk = peaks()
     # DRAM traffic of the dominant launch shape (the reverse-step scorer) from the committed ncu --set full capture
     traffic, traffic_src = None, None
-    ncu_path = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
-    if args.workload == "yelp" and os.path.exists(ncu_path):
-        with open(ncu_path) as f:
-            cap = json.load(f).get("gemm_scorer_post")
-        if cap:
-            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
-            traffic_src = ("profiles/r1_ncu_summary.json: scorer launch (400 x 34395 x 3000, posterior epilogue), algorithmic "
-                           f"{cap['algorithmic_bytes']} B")
+    for fname, key, what in (("r2_ncu_summary.json", "gemm_scorer", "cosine epilogue"),
+                             ("r1_ncu_summary.json", "gemm_scorer_post", "posterior epilogue")):
+        ncu_path = os.path.join(ROOT, "profiles", fname)
+        if traffic is None and args.workload == "yelp" and os.path.exists(ncu_path):
+            with open(ncu_path) as f:
+                cap = json.load(f).get(key)
+            if cap:
+                traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+                traffic_src = (f"profiles/{fname}: scorer launch (400 x 34395 x 3000, {what}; 2 of the step's 21 contraction "
+                               f"launches, the largest share of contraction time), algorithmic {cap['algorithmic_bytes']} B")
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_2cta_kernel / gemm_bf16_tn_kernel<128> (+ splitk_reduce_kernel)", "achieved": achieved,
                 "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_of": traffic_src,

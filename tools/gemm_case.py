@@ -1,5 +1,5 @@
 """Stand-alone GEMM cases of the hot path for event timing and ncu captures.
-usage: python tools/gemm_case.py <case> [iters]     cases: scorer_post | scorer_plain | dE | dW1 | enc"""
+usage: python tools/gemm_case.py <case> [iters]     cases: scorer_post | scorer_plain | dE | dE_plain | dW1 | enc"""
 import os
 import sys
 
@@ -38,6 +38,10 @@ def main():
         out = torch.empty(m, n, device="cuda")
         kw = dict(out_f32=out, row_t=torch.arange(m, dtype=torch.int32, device="cuda"), c1=torch.ones(m, device="cuda"),
                   c2=torch.rand(m, device="cuda"), xt=torch.randn(m, n, device="cuda"))
+    elif case == "dE_plain":  # the engine's form: plain fp32 store (the row-norm term is applied by the optimizer pass)
+        m, n, k = I, 3 * d, B
+        a, b = op(m, k, 1), op(n, k, 2)
+        kw = dict(out_f32=torch.empty(m, n, device="cuda"))
     elif case == "dW1":
         m, n, k = d, I, B
         a, b = op(m, k, 1), op(n, k, 2)
