@@ -348,12 +348,12 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         assert out_dims[0] == in_dims[-1], "In and out dimensions must equal to each other."
         if time_type != "cat":
             raise ValueError("Unimplemented timestep embedding type %s" % time_type)
-        if len(in_dims) != 2:
-            raise NotImplementedError("the hot path covers one hidden layer (dims=[d]); got %s" % (in_dims,))
+        if len(in_dims) < 2:
+            raise ValueError("in_dims needs the input width and at least one hidden width; got %s" % (in_dims,))
         if norm:
             raise NotImplementedError("norm=True is outside the configured hot path")
-        if in_dims[1] % 8:
-            raise NotImplementedError("dims[0] must be a multiple of 8 (16-byte aligned segments of the user tower)")
+        if any(w % 8 for w in in_dims[1:]):
+            raise NotImplementedError("every entry of dims must be a multiple of 8 (16-byte aligned operand rows / tower segments)")
         self.time_type, self.time_emb_dim, self.norm = time_type, emb_size, norm
         self.emb_layer = nn.Linear(emb_size, emb_size)
         in_t = [in_dims[0] + emb_size] + in_dims[1:]
@@ -393,7 +393,18 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
 
     @property
     def hidden(self) -> int:
+        """Width of h / h_U / e_user, the three segments of the user tower = the LAST entry of dims (models/DNN.py:1143-1147)."""
+        return self.in_dims[-1]
+
+    @property
+    def d1(self) -> int:
+        """Output width of the first (catalogue-wide) encoder layers; == hidden for dims=[d]."""
         return self.in_dims[1]
+
+    @property
+    def deep(self) -> bool:
+        """dims has more than one entry: the encoders are tanh MLPs (models/DNN.py:1240-1252 loop over in_layers / in_layers2)."""
+        return len(self.in_dims) > 2
 
     # -- operands ------------------------------------------------------------------------------
     def _tables(self, T: int):
@@ -415,7 +426,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
     def _onehot_tables(self):
         w2 = self.in_layers2[0].weight
         def build(prev):
-            d, I = self.hidden, self.n_item
+            d, I = self.d1, self.n_item
             ok = prev is not None and prev[0].shape == (d,) and prev[1].shape == (I, K.round_up(d, 4)) and prev[0].device == w2.device
             base = prev[0] if ok else torch.empty(d, dtype=torch.float32, device=w2.device)
             delta = prev[1] if ok else torch.zeros(I, K.round_up(d, 4), dtype=torch.float32, device=w2.device)
@@ -470,7 +481,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
             hc_f32=torch.empty(B, 3 * d, dtype=torch.float32, device=dev), hc=Bf16Mat.empty(B, 3 * d, dev, self._lo),
             g1=Bf16Mat.empty(B, 512, dev, self._lo), g2=torch.empty(B, 3 * d, dtype=torch.float32, device=dev),
             hcp=Bf16Mat.empty(B, 3 * d, dev, self._lo), inv_u=torch.empty(B, dtype=torch.float32, device=dev),
-            xop=Bf16Mat.empty(B, self.n_item, dev, self._lo), S=torch.empty(B, d, dtype=torch.float32, device=dev)))
+            xop=Bf16Mat.empty(B, self.n_item, dev, self._lo), S=torch.empty(B, self.d1, dtype=torch.float32, device=dev)))
 
     def _seg(self, bufs, s: int):
         """fp32 / bf16 views of segment s (h | h_U | e_user) of the concatenated user tower."""
@@ -478,18 +489,60 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         hc = bufs["hc"]
         return (bufs["hc_f32"][:, s * d:(s + 1) * d], hc.hi[:, s * d:], hc.lo[:, s * d:] if hc.lo is not None else None)
 
+    # -- deep encoders (dims with more than one entry) ------------------------------------------------
+    def _deep_layers(self, branch: int):
+        """The layers after the first of in_layers (branch 0) / in_layers2 (branch 1), with their parameter name prefixes."""
+        name = "in_layers" if branch == 0 else "in_layers2"
+        return [(f"{name}.{i}", l) for i, l in enumerate(getattr(self, name)) if i > 0]
+
+    def _first_out(self, bufs, branch: int, B: int):
+        """Where the first layer of an encoder writes tanh(W1 [x, emb] + b): straight into its segment of the user tower for
+        dims=[d]; into a [B, d1] activation buffer that _deep_forward continues from otherwise. Returns (f32, hi, lo)."""
+        if not self.deep:
+            return self._seg(bufs, branch)
+        acts = bufs.setdefault("acts", {})
+        if branch not in acts or acts[branch][0][1].rows != B:
+            dev = bufs["hc_f32"].device
+            widths = [l.weight.shape[0] for _, l in self._deep_layers(branch)][:-1]
+            with_lo = bufs["hc"].lo is not None
+            acts[branch] = [(torch.empty(B, w, dtype=torch.float32, device=dev), Bf16Mat.empty(B, w, dev, with_lo))
+                            for w in [self.d1] + widths]
+        f32, op = acts[branch][0]
+        return f32, op.hi, op.lo
+
+    def _deep_forward(self, bufs, branch: int, B: int) -> None:
+        """h <- tanh(layer(h)) for the layers after the first (models/DNN.py:1240-1242, :1249-1251); the last one writes its
+        segment of the user tower. Activations stay in bufs["acts"][branch] (the training backward reads them)."""
+        if not self.deep:
+            return
+        acts = bufs["acts"][branch]
+        layers = self._deep_layers(branch)
+        for li, (name, layer) in enumerate(layers):
+            n_out, n_in = layer.weight.shape
+            a_op = acts[li][1]
+            if li == len(layers) - 1:
+                f32, hi, lo = self._seg(bufs, branch)
+            else:
+                f32, hi, lo = acts[li + 1][0], acts[li + 1][1].hi, acts[li + 1][1].lo
+            w = self._weight_operand(name, layer.weight)
+            a_in = a_op if self._lo else Bf16Mat(a_op.hi, None, B, n_in)
+            self._mm(a_in, w, B, n_out, n_in, act=K.ACT_TANH, bias=layer.bias.detach(), out_f32=f32, out_bf16=hi,
+                     out_bf16_lo=lo)
+
     def _encode_x(self, bufs, x_op: Bf16Mat, B: int, ts, t_const: int, T: int):
         tb1, _ = self._tables(T)
         w1 = self._weight_operand("in0", self.in_layers[0].weight, cols=self.n_item)
-        f32, hi, lo = self._seg(bufs, 0)
-        self._mm(x_op, w1, B, self.hidden, self.n_item, act=K.ACT_TANH, bias=tb1, ld_bias=self.hidden, row_t=ts,
+        f32, hi, lo = self._first_out(bufs, 0, B)
+        self._mm(x_op, w1, B, self.d1, self.n_item, act=K.ACT_TANH, bias=tb1, ld_bias=self.d1, row_t=ts,
                  t_const=t_const, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+        self._deep_forward(bufs, 0, B)
 
     def _encode_onehot_from_S(self, bufs, B: int, ts, t_const: int, T: int):
         _, tb2 = self._tables(T)
-        f32, hi, lo = self._seg(bufs, 1)
-        K.bias_act_rows(bufs["S"], B, self.hidden, bias=tb2, ld_bias=self.hidden, row_t=ts, t_const=t_const,
+        f32, hi, lo = self._first_out(bufs, 1, B)
+        K.bias_act_rows(bufs["S"], B, self.d1, bias=tb2, ld_bias=self.d1, row_t=ts, t_const=t_const,
                         act=K.ACT_TANH, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+        self._deep_forward(bufs, 1, B)
 
     def _x_branch_operand(self, x_op: Bf16Mat, xu_op_hi: Optional[torch.Tensor], B: int) -> Bf16Mat:
         """Input of the continuous encoder: x (models/DNN.py:1238), or with noise_type 1 the first n_item columns of the
@@ -512,26 +565,28 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         """h_U from a dense one-hot-branch operand [B, 2I] (training / noised inference): tensor-core GEMM. lo: residual of
         the operand in fp32 mode when it is not exact in bf16 (noise_type 2 feeds continuous values)."""
         w2 = self._weight_operand("in2", self.in_layers2[0].weight, cols=2 * self.n_item)
-        k = 2 * self.n_item
+        k, d1 = 2 * self.n_item, self.d1
         if lo is not None and self._lo:
             assert not to_S
             _, tb2 = self._tables(T)
-            f32, hi, lo_out = self._seg(bufs, 1)
-            K.gemm([xu_op_hi, xu_op_hi, lo], [w2.hi, w2.lo, w2.hi], B, self.hidden, [k, k, k], act=K.ACT_TANH, bias=tb2,
-                   ld_bias=self.hidden, row_t=ts, t_const=t_const, out_f32=f32, out_bf16=hi, out_bf16_lo=lo_out)
+            f32, hi, lo_out = self._first_out(bufs, 1, B)
+            K.gemm([xu_op_hi, xu_op_hi, lo], [w2.hi, w2.lo, w2.hi], B, d1, [k, k, k], act=K.ACT_TANH, bias=tb2,
+                   ld_bias=d1, row_t=ts, t_const=t_const, out_f32=f32, out_bf16=hi, out_bf16_lo=lo_out)
+            self._deep_forward(bufs, 1, B)
             return
         if to_S:  # pre-activation only (step-invariant part, hoisted out of the reverse loop)
-            K.gemm([xu_op_hi], [w2.hi], B, self.hidden, [k], out_f32=bufs["S"]) if not self._lo else \
-                K.gemm([xu_op_hi, xu_op_hi], [w2.hi, w2.lo], B, self.hidden, [k, k], out_f32=bufs["S"])
+            K.gemm([xu_op_hi], [w2.hi], B, d1, [k], out_f32=bufs["S"]) if not self._lo else \
+                K.gemm([xu_op_hi, xu_op_hi], [w2.hi, w2.lo], B, d1, [k, k], out_f32=bufs["S"])
             return
         _, tb2 = self._tables(T)
-        f32, hi, lo = self._seg(bufs, 1)
-        epi = dict(act=K.ACT_TANH, bias=tb2, ld_bias=self.hidden, row_t=ts, t_const=t_const, out_f32=f32, out_bf16=hi,
+        f32, hi, lo = self._first_out(bufs, 1, B)
+        epi = dict(act=K.ACT_TANH, bias=tb2, ld_bias=d1, row_t=ts, t_const=t_const, out_f32=f32, out_bf16=hi,
                    out_bf16_lo=lo)
         if self._lo:  # the one-hot operand is exact in bf16 ({0,1,2}): only the weight needs the lo term
-            K.gemm([xu_op_hi, xu_op_hi], [w2.hi, w2.lo], B, self.hidden, [k, k], **epi)
+            K.gemm([xu_op_hi, xu_op_hi], [w2.hi, w2.lo], B, d1, [k, k], **epi)
         else:
-            K.gemm([xu_op_hi], [w2.hi], B, self.hidden, [k], **epi)
+            K.gemm([xu_op_hi], [w2.hi], B, d1, [k], **epi)
+        self._deep_forward(bufs, 1, B)
 
     def _user_tower(self, bufs, B: int):
         """GCN on the user rows + sumW mix + row norms (models/DNN.py:1274-1288, :1320)."""
@@ -574,7 +629,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         Same arithmetic as the reference up to rounding order; P is rebuilt whenever W1 or E change (one 2*d*3d*I
         contraction per weight version)."""
         W1, E = self.in_layers[0].weight, self.embedding_item.weight
-        d, d3, I = self.hidden, 3 * self.hidden, self.n_item
+        d, d3, I = self.d1, 3 * self.hidden, self.n_item
 
         def build(prev):
             _, inv_i = self._item_operands()
@@ -605,7 +660,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         """The p_sample loop (models/gaussian_diffusion.py:695-752) with the recurrence carried in the encoder's
         pre-activation space (see _projection_operand). Requires c1[0] = 1, c2[0] = 0 (START_X, every schedule: the last
         reverse step returns the model output) and no per-step noise. Returns the fp32 buffer [B, ld4] holding x_0."""
-        I, d, dev = self.n_item, self.hidden, x0_f32.device
+        I, d, dh, dev = self.n_item, self.d1, self.hidden, x0_f32.device
         ld4 = x0_f32.shape[1]
         bufs = self._hc_buffers(B, dev)
         rb = self._buf(("proj", B, ld4), lambda: dict(out=torch.empty(B, ld4, dtype=torch.float32, device=dev),
@@ -620,7 +675,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
             self._user_rows_staged = False
         else:
             f32, hi, lo = self._seg(bufs, 2)
-            K.gather_rows(self.embedding_user.weight.detach(), index, B, d, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+            K.gather_rows(self.embedding_user.weight.detach(), index, B, dh, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
         x_op = x0_op
         if x_op is None:
             x_op = bufs["xop"]
@@ -632,14 +687,15 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
         P = self._projection_operand()
         tb1, _ = self._tables(steps_total)
         for t in reversed(range(steps_total)):
-            f32, hi, lo = self._seg(bufs, 0)
+            f32, hi, lo = self._first_out(bufs, 0, B)
             K.bias_act_rows(cur, B, d, bias=tb1, ld_bias=d, t_const=t, act=K.ACT_TANH, out_f32=f32, out_bf16=hi, out_bf16_lo=lo)
+            self._deep_forward(bufs, 0, B)
             self._encode_onehot_from_S(bufs, B, None, t, steps_total)
             self._user_tower(bufs, B)
             if t == 0:
                 self._score(bufs, B, rb["out"])          # x_0 = the model output of the last step
             else:
-                self._mm(bufs["hcp"], P, B, d, 3 * d, row_scale=bufs["inv_u"], c1=c1, c2=c2, xt=cur, t_const=t, out_f32=nxt)
+                self._mm(bufs["hcp"], P, B, d, 3 * dh, row_scale=bufs["inv_u"], c1=c1, c2=c2, xt=cur, t_const=t, out_f32=nxt)
                 cur, nxt = nxt, cur
         return rb["out"]
 
@@ -783,7 +839,7 @@ class DNNOneHotEmbeddingGCN(_EngineModule):
             self._encode_onehot_dense(bufs, xu_op, B, None, 0, steps_total, to_S=True)
         else:
             base, delta = self._onehot_tables()
-            K.encode_onehot_gather(csr[0], csr[1], users, B, base, delta, d, bufs["S"])
+            K.encode_onehot_gather(csr[0], csr[1], users, B, base, delta, self.d1, bufs["S"])
         if getattr(self, "_user_rows_staged", False):
             self._user_rows_staged = False  # gathered ahead of the loop by stage_user_rows()
         else:

@@ -178,6 +178,16 @@ _GDMCF_PARAMS = ("emb_layer.weight", "emb_layer.bias", "in_layers.0.weight", "in
                  "gcn_model.conv1.lin.weight", "gcn_model.conv2.bias", "gcn_model.conv2.lin.weight", "sumW")
 
 
+def _gdmcf_names(model):
+    """Trained parameters of the configured model, in a fixed order: the base set + the encoder layers after the first."""
+    have = dict(model.named_parameters())
+    names = [n for n in _GDMCF_PARAMS if n in have]
+    for branch in (0, 1):
+        for name, _ in model._deep_layers(branch):
+            names += [name + ".weight", name + ".bias"]
+    return names
+
+
 def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc, ts, inject) -> _Ctx:
     dev, d, T = x0.device, model.hidden, diff.steps
     inject = inject or {}
@@ -195,6 +205,7 @@ def _gdmcf_forward(model: DNNOneHotEmbeddingGCN, diff, x0, B, I, idx32, ts_disc,
     c.hc_f32 = torch.empty(B, 3 * d, dtype=torch.float32, device=dev)
     c.hc = Bf16Mat.empty(B, 3 * d, dev, True)
     bufs = dict(hc_f32=c.hc_f32, hc=c.hc, S=None)
+    c.bufs = bufs  # deep encoders (dims with more than one entry) leave their layer activations in bufs["acts"]
     # encoder inputs: noise_type 1 feeds columns of the interleaved one-hot matrix to the continuous encoder (DNN.py:1236),
     # noise_type 2 feeds [x, x] to the one-hot encoder (:1246); they are also the wgrad operands of the backward pass
     c.enc1_in = model._x_branch_operand(c.A1, c.A2, B)
@@ -389,6 +400,34 @@ def _gdmcf_backward_stages(model: DNNOneHotEmbeddingGCN, diff, c: _Ctx, g_mse: t
     yield _first_layer_grads(model, diff, c, d_hc_tot, g_closs, P)  # stage 3: the two first-layer weights (+ biases, emb_layer)
 
 
+def _deep_backward(model, c: _Ctx, branch: int, dh_out, grads, B, dev):
+    """Backward through the encoder layers after the first: dh_out = dL/d(last layer's tanh output) [B, hidden]. Adds the
+    layers' weight / bias gradients to `grads`; returns (dL/d a1, a1) with a1 = the first layer's tanh output [B, d1]."""
+    lo = model._lo
+    acts = c.bufs["acts"][branch]            # acts[i] = (f32, operand) INPUT of deep layer i; acts[0] = first-layer output
+    layers = model._deep_layers(branch)
+    seg = c.hc_f32[:, branch * model.hidden:(branch + 1) * model.hidden]
+    dh = dh_out
+    for li in reversed(range(len(layers))):
+        name, layer = layers[li]
+        n_out, n_in = layer.weight.shape
+        a_out = seg if li == len(layers) - 1 else acts[li + 1][0]
+        a_in_f32 = acts[li][0]
+        dpre = torch.empty(B, n_out, dtype=torch.float32, device=dev)
+        dpre_op = Bf16Mat.empty(B, n_out, dev, lo, zero=True)
+        K.ew_binary(K.EW_TANH_BWD, dh, a_out, B, n_out, out_f32=dpre, out_bf16=dpre_op.hi, out_bf16_lo=dpre_op.lo)
+        dpreT = K.cast_bf16_transpose(dpre, with_lo=lo)        # [n_out, B]
+        a_inT = K.cast_bf16_transpose(a_in_f32, with_lo=lo)    # [n_in, B]
+        gW = torch.empty_like(layer.weight)
+        _mm_auto(model, dpreT, a_inT, n_out, n_in, B, out_f32=gW)
+        grads[name + ".weight"] = gW
+        grads[name + ".bias"] = K.colsum_f32(dpre, B, n_out)
+        wT = model._weight_operand(name, layer.weight, transpose=True)   # [n_in, n_out]
+        dh = torch.empty(B, n_in, dtype=torch.float32, device=dev)
+        _mm_auto(model, dpre_op, wT, B, n_in, n_out, out_f32=dh)
+    return dh, acts[0][0]
+
+
 def _first_layer_grads(model, diff, c: _Ctx, d_hc_tot, g_closs, P):
     """Stage 3 of the GDMCF backward: contrastive-loss gradient into h / h_U, tanh backward, the two first-layer weight
     gradients and the time-embedding layer."""
@@ -411,11 +450,17 @@ def _first_layer_grads(model, diff, c: _Ctx, d_hc_tot, g_closs, P):
         _mm3(dST_op, hT, B, d, B, out_f32=dhU_tot, c1=ones1, c2=ones1, xt=d_hc_tot[:, d:2 * d], t_const=0)
     else:  # noise_type != 0: the contrastive loss is multiplied by zero (DNN.py:1258-1259)
         dh_tot, dhU_tot = d_hc_tot[:, :d], d_hc_tot[:, d:2 * d]
+    # ---- deep encoders: back through the tanh layers after the first (DNN.py:1240-1242, :1249-1251)
+    h1, hU1, d1 = c.hc_f32[:, :d], c.hc_f32[:, d:2 * d], d
+    if model.deep:
+        dh_tot, h1 = _deep_backward(model, c, 0, dh_tot, grads, B, dev)
+        dhU_tot, hU1 = _deep_backward(model, c, 1, dhU_tot, grads, B, dev)
+        d = d1 = model.d1  # from here on d is the width of the first layers' outputs
     # ---- tanh backward, first-layer weight gradients
     dh_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
     dhU_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
-    K.ew_binary(K.EW_TANH_BWD, dh_tot, c.hc_f32[:, :d], B, d, out_f32=dh_pre)
-    K.ew_binary(K.EW_TANH_BWD, dhU_tot, c.hc_f32[:, d:2 * d], B, d, out_f32=dhU_pre)
+    K.ew_binary(K.EW_TANH_BWD, dh_tot, h1, B, d, out_f32=dh_pre)
+    K.ew_binary(K.EW_TANH_BWD, dhU_tot, hU1, B, d, out_f32=dhU_pre)
     dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)     # [d, B]
     dhU_preT = K.cast_bf16_transpose(dhU_pre, with_lo=lo)
     emb_table = model._emb_table(T)   # [T, e], produced with the forward's bias tables (same weights)
@@ -452,7 +497,7 @@ class _GdmcfTrainFn(torch.autograd.Function):
     def forward(ctx, model, diff, x0, B, I, idx32, ts_disc, ts, inject, *params):
         c = _gdmcf_forward(model, diff, x0, B, I, idx32, ts_disc, ts, inject)
         ctx.c, ctx.model, ctx.diff = c, model, diff
-        ctx.names = [n for n in _GDMCF_PARAMS if n in dict(model.named_parameters())]
+        ctx.names = _gdmcf_names(model)
         closs = c.closs_rows.mean()
         ctx.mark_non_differentiable(c.out)
         return c.mse, closs, c.out
@@ -599,7 +644,7 @@ def training_losses(diff, model, x_start, reweight=False, index=None, inject: Op
     params = dict(model.named_parameters())
     if gdmcf:
         mse, closs, out = _GdmcfTrainFn.apply(model, diff, x0, B, I, idx32, ts_disc, ts32, inject,
-                                              *[params[n] for n in _GDMCF_PARAMS if n in params])
+                                              *[params[n] for n in _gdmcf_names(model)])
     else:
         mse, out = _DnnTrainFn.apply(model, diff, x0, B, I, ts32, inject, *[params[n] for n in _DNN_PARAMS])
         closs = None

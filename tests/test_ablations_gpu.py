@@ -188,3 +188,40 @@ def test_faithful_graph_bookkeeping(g):
     faithful = d.p_sample(m, x0, 0, index=index)
     # (the default path carries the recurrence in the encoder's pre-activation space: same values up to fp32 rounding order)
     assert rel(faithful, base) < 1e-5 and m.last_gcn_all.shape == (B + I, 3 * D)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["deep2.", "deep3."])
+def test_deep_encoders(lib, tag, precision):
+    """dims with more than one entry (`--dims '[d_a, d_b]'`, main.py:198-206): the encoders are tanh MLPs (models/DNN.py:1240-1252),
+    the user tower works on the LAST width, the projected reverse loop carries the FIRST layer's pre-activation. Against
+    tests/golden/deep.npz (unmodified reference): eval forward, p_sample (dense and CSR input), training steps with every
+    gradient incl. the deep layers'; and the captured engine step == the eager one."""
+    from gdmcf_b200.models.DNN import DNNOneHotEmbeddingGCN
+    g = dict(np.load(os.path.join(GOLD, "deep.npz")))
+    dims = [int(x) for x in g[tag + "in_dims"]]
+    a = types.SimpleNamespace(user_guided=1, gcnLayerNum=2, noise_type=0)
+    m = DNNOneHotEmbeddingGCN(list(dims), list(dims[::-1]), E, item_num=I, user_num=U, args=a, precision=precision)
+    m.load_state_dict(sd(g, tag), strict=True)
+    m = m.cuda().eval()
+    assert m.deep and m.d1 == dims[1] and m.hidden == dims[-1]
+    x0, index = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["index"]).cuda()
+    x_U = torch.nn.functional.one_hot(x0.long(), 2).float()
+    tol = TOL[precision]["score"]
+    out = m(torch.from_numpy(g["fwd_x"]).cuda(), torch.from_numpy(g["fwd_ts"]).cuda(), x_U, index=index, graph=x_U.long())
+    assert rel(out, g[tag + "fwd_eval"]) < tol
+    d = diffusion()
+    assert m.can_project()
+    assert rel(d.p_sample(m, x0, 0, index=index), g[tag + "p_sample_s0"]) < tol          # projected loop
+    os.environ["GDMCF_PROJECTED_LOOP"] = "0"
+    try:
+        assert rel(d.p_sample(m, x0, 0, index=index), g[tag + "p_sample_s0"]) < tol      # step-by-step loop
+    finally:
+        del os.environ["GDMCF_PROJECTED_LOOP"]
+    import scipy.sparse as sp
+    from gdmcf_b200 import data_utils
+    full = np.zeros((U, I), dtype=np.float32)
+    full[g["index"]] = g["x0"]
+    batch = data_utils.DeviceInteractions(sp.csr_matrix(full), "cuda").batch(g["index"].astype(np.int32))
+    assert rel(d.p_sample(m, batch, 0), g[tag + "p_sample_s0"]) < tol                     # sparse one-hot encoder
+    replay(g, tag, m, diffusion(), True, precision)

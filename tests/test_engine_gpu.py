@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _setup(seed_model=0, U=700, I=1203, D=64, B=64, T=5, k=20):
+def _setup(seed_model=0, U=700, I=1203, D=64, B=64, T=5, k=20, dims=None):
     from gdmcf_b200 import data_utils, dist_utils
     from gdmcf_b200.engine import StepEngine
     from gdmcf_b200.models import gaussian_diffusion as gd
@@ -24,7 +24,8 @@ def _setup(seed_model=0, U=700, I=1203, D=64, B=64, T=5, k=20):
 
     def make(graphs, **engine_kw):
         torch.manual_seed(seed_model)
-        model = DNNOneHotEmbeddingGCN([n_item, D], [D, n_item], 10, item_num=n_item, user_num=n_user).to(dev)
+        in_dims = [n_item] + list(dims or [D])
+        model = DNNOneHotEmbeddingGCN(in_dims, in_dims[::-1], 10, item_num=n_item, user_num=n_user).to(dev)
         diff = gd.GaussianDiffusionDiscrete(gd.ModelMeanType.START_X, "linear-var", 0.01, 0.001, 0.01, T, dev,
                                             discrete=0.9995, CatOneHot=True)
         diff.indexIn = True
@@ -35,6 +36,33 @@ def _setup(seed_model=0, U=700, I=1203, D=64, B=64, T=5, k=20):
         return model, diff, eng
 
     return make, train_dev, test_dev, train_sp, test_sp, B, n_user
+
+
+def test_graph_step_equals_eager_step_deep_encoders():
+    """dims = [96, 64] (two-layer tanh encoders): the captured step (deep forward + backward, operands of the small layers
+    re-derived inside the graph) == the eager step, bit for bit, and every deep parameter trains."""
+    make, train_dev, test_dev, _, _, B, n_user = _setup(dims=[96, 64])
+    m_g, d_g, e_g = make(True)
+    m_e, d_e, e_e = make(False)
+    assert m_g.deep
+    before = {n: p.detach().clone() for n, p in m_g.named_parameters() if n.startswith(("in_layers.1", "in_layers2.1"))}
+    assert len(before) == 4
+    for e in (e_g, e_e):
+        e.load_resident(train_dev, test_dev, 0, B)
+        e.capture(warmup=2)
+    for s in range(1, 5):
+        lo = (s * B) % (n_user - B)
+        outs = []
+        for e in (e_g, e_e):
+            e.load_resident(train_dev, test_dev, lo, lo + B)
+            loss, idx, sums = e.step()
+            outs.append((loss.clone(), idx.clone(), sums.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2]), s
+    e_g.flush(); e_e.flush()
+    for (n, pg), (_, pe) in zip(m_g.named_parameters(), m_e.named_parameters()):
+        assert torch.equal(pg, pe), n
+    for n, p0 in before.items():
+        assert not torch.equal(p0, dict(m_g.named_parameters())[n].detach()), n
 
 
 def test_graph_step_equals_eager_step():
