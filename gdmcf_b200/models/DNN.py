@@ -185,7 +185,9 @@ def _init_linear(layer: nn.Linear):
 
 
 class DNN(_EngineModule):
-    """models/DNN.py:11-88 — `[x, emb(t)] -> tanh(Linear(n_item+e -> d)) -> Linear(d -> n_item)`."""
+    """models/DNN.py:11-88 — `[x, emb(t)] -> tanh(Linear(n_item+e -> d)) -> Linear(d -> n_item)`; with more than one entry in
+    dims: tanh after every in_layer and after every out_layer but the last (:79-86). The first in_layer and the last out_layer
+    are the catalogue-wide contractions; the layers between them ("middle") are small."""
 
     def __init__(self, in_dims, out_dims, emb_size, time_type="cat", norm=False, dropout=0.5, precision="bf16"):
         super().__init__()
@@ -193,8 +195,10 @@ class DNN(_EngineModule):
         assert out_dims[0] == in_dims[-1], "In and out dimensions must equal to each other."
         if time_type != "cat":
             raise ValueError("Unimplemented timestep embedding type %s" % time_type)
-        if len(in_dims) != 2 or len(out_dims) != 2:
-            raise NotImplementedError("the hot path covers one hidden layer (dims=[d]); got %s" % (in_dims,))
+        if len(in_dims) < 2 or len(out_dims) < 2:
+            raise ValueError("in_dims / out_dims need at least one hidden width; got %s / %s" % (in_dims, out_dims))
+        if any(w % 8 for w in list(in_dims[1:]) + list(out_dims[:-1])):
+            raise NotImplementedError("every entry of dims must be a multiple of 8 (16-byte aligned operand rows)")
         if norm:
             raise NotImplementedError("norm=True (F.normalize on the input) is outside the configured hot path")
         self.time_type, self.time_emb_dim, self.norm = time_type, emb_size, norm
@@ -217,7 +221,43 @@ class DNN(_EngineModule):
 
     @property
     def hidden(self) -> int:
+        """Output width of the first (catalogue-wide) layer."""
         return self.in_dims[1]
+
+    @property
+    def d_dec(self) -> int:
+        """Input width of the last (catalogue-wide) out_layer; == hidden for dims=[d]."""
+        return self.out_dims[-2]
+
+    @property
+    def deep(self) -> bool:
+        return len(self.in_dims) > 2 or len(self.out_dims) > 2
+
+    @property
+    def _dec_name(self) -> str:
+        return f"out_layers.{len(self.out_layers) - 1}"
+
+    def _middle(self):
+        """The small tanh layers between the two catalogue-wide contractions: in_layers[1:] then out_layers[:-1]."""
+        return ([(f"in_layers.{i}", l) for i, l in enumerate(self.in_layers) if i > 0] +
+                [(f"out_layers.{j}", l) for j, l in enumerate(self.out_layers) if j < len(self.out_layers) - 1])
+
+    def _mid_forward(self, h: Bf16Mat, B: int, acts=None) -> Bf16Mat:
+        """h <- tanh(layer(h)) through the middle layers; returns the decoder's input operand. acts (training): a list that
+        receives (fp32, operand) of every layer output for the backward pass; inference reuses cached buffers."""
+        cur, dev = h, h.hi.device
+        for name, layer in self._middle():
+            n_out, n_in = layer.weight.shape
+            if acts is not None:
+                f32, op = torch.empty(B, n_out, dtype=torch.float32, device=dev), Bf16Mat.empty(B, n_out, dev, self._lo)
+                acts.append((f32, op))
+            else:
+                f32 = None
+                op = self._buf(("mid", name, B), lambda: Bf16Mat.empty(B, n_out, dev, self._lo))
+            self._mm(cur, self._weight_operand(name, layer.weight), B, n_out, n_in, act=K.ACT_TANH, bias=layer.bias.detach(),
+                     out_f32=f32, out_bf16=op.hi, out_bf16_lo=op.lo)
+            cur = op
+        return cur
 
     def _tables(self, T: int):
         l0 = self.in_layers[0]
@@ -227,11 +267,11 @@ class DNN(_EngineModule):
 
     def build_derived(self) -> None:
         self._weight_operand("in0", self.in_layers[0].weight, cols=self.n_item)
-        self._weight_operand("out0", self.out_layers[0].weight)
+        self._weight_operand("out0", self.out_layers[-1].weight)
 
     def refresh_specs(self):
         pr, out = self.precision, {}
-        w1, wo = self.in_layers[0].weight, self.out_layers[0].weight
+        w1, wo = self.in_layers[0].weight, self.out_layers[-1].weight
         for prm, ent in ((w1, self._refresh_entry(w1, op="in0" + pr, tcols="in_layers.0.tcols", cols_used=self.n_item)),
                          (wo, self._refresh_entry(wo, op="out0" + pr, op_t="out0.T" + pr))):
             if ent is not None:
@@ -245,8 +285,8 @@ class DNN(_EngineModule):
                  row_t=ts, t_const=t_const, out_bf16=h_out.hi, out_bf16_lo=h_out.lo, out_f32=h_f32)
 
     def _decode(self, h: Bf16Mat, B: int, out_f32, out_op: Optional[Bf16Mat] = None, **post):
-        wo = self._weight_operand("out0", self.out_layers[0].weight)
-        self._mm(h, wo, B, self.n_item, self.hidden, bias=self.out_layers[0].bias.detach(), out_f32=out_f32,
+        wo = self._weight_operand("out0", self.out_layers[-1].weight)
+        self._mm(h, wo, B, self.n_item, self.d_dec, bias=self.out_layers[-1].bias.detach(), out_f32=out_f32,
                  out_bf16=out_op.hi if out_op is not None else None, out_bf16_lo=out_op.lo if out_op is not None else None,
                  **post)
 
@@ -263,7 +303,7 @@ class DNN(_EngineModule):
         h = self._buf(("h", B), lambda: Bf16Mat.empty(B, self.hidden, x.device, self._lo))
         self._encode(x_op, B, ts, 0, _MAX_T_TABLE, h)
         out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=x.device)
-        self._decode(h, B, out)
+        self._decode(self._mid_forward(h, B), B, out)
         return out[:, :I]
 
     @torch.no_grad()
@@ -285,7 +325,7 @@ class DNN(_EngineModule):
         for t in reversed(range(steps_total)):
             self._encode(x_op, B, None, t, steps_total, bufs["h"])
             last = t == 0
-            self._decode(bufs["h"], B, nxt, None if last else bufs["xop"], c1=c1, c2=c2, xt=cur, t_const=t)
+            self._decode(self._mid_forward(bufs["h"], B), B, nxt, None if last else bufs["xop"], c1=c1, c2=c2, xt=cur, t_const=t)
             if noise_hook is not None and not last:
                 noise_hook(nxt, bufs["xop"], t)  # sampling_noise: x_{t-1} = mean + sigma[t] * z (gaussian_diffusion.py:745-750)
             x_op = bufs["xop"]

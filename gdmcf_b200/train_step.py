@@ -527,9 +527,18 @@ def _dnn_forward(model: DNN, diff, x0, B, I, ts, inject) -> _Ctx:
     c.h = Bf16Mat.empty(B, d, dev, model._lo)
     model._encode(c.A1, B, ts, 0, T, c.h, h_f32=c.h_f32)
     c.out = torch.empty(B, K.round_up(I, 4), dtype=torch.float32, device=dev)
-    model._decode(c.h, B, c.out)
+    c.acts = []  # (fp32, operand) outputs of the middle layers (dims with more than one entry)
+    model._decode(model._mid_forward(c.h, B, acts=c.acts), B, c.out)
     c.mse = _row_mse(c, B, I)
     return c
+
+
+def _dnn_names(model):
+    """Trained parameters in a fixed order: emb_layer, first layer, the middle layers, the last out_layer."""
+    names = ["emb_layer.weight", "emb_layer.bias", "in_layers.0.weight", "in_layers.0.bias"]
+    for name, _ in model._middle():
+        names += [name + ".weight", name + ".bias"]
+    return names + [model._dec_name + ".weight", model._dec_name + ".bias"]
 
 
 def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
@@ -542,16 +551,33 @@ def _dnn_backward(model: DNN, diff, c: _Ctx, g_mse: torch.Tensor):
     GT = Bf16Mat.empty(I, B, dev, lo, zero=False)
     colsum = torch.empty(I, dtype=torch.float32, device=dev)
     K.loss_grad(c.out, c.target, _loss_seed(c, g_mse), B, I, G, GT=GT, with_out=False, colsum=colsum)
-    grads["out_layers.0.bias"] = colsum
-    # d W_out [I, d] = G^T h
-    hT = K.cast_bf16_transpose(c.h_f32, with_lo=lo)  # [d, B]
-    gWo = torch.empty_like(P["out_layers.0.weight"])
-    _mm_auto(model, GT, hT, I, d, B, out_f32=gWo)
-    grads["out_layers.0.weight"] = gWo
-    # d h = G W_out  (B operand = W_out^T [d, I])
-    woT = model._weight_operand("out0", model.out_layers[0].weight, transpose=True)
-    dh = torch.empty(B, d, dtype=torch.float32, device=dev)
-    _mm_auto(model, G, woT, B, d, I, out_f32=dh)
+    dec, dd = model._dec_name, model.d_dec
+    dec_in = c.acts[-1][0] if c.acts else c.h_f32   # the last out_layer's input [B, dd]
+    grads[dec + ".bias"] = colsum
+    # d W_out [I, dd] = G^T h
+    hT = K.cast_bf16_transpose(dec_in, with_lo=lo)  # [dd, B]
+    gWo = torch.empty_like(P[dec + ".weight"])
+    _mm_auto(model, GT, hT, I, dd, B, out_f32=gWo)
+    grads[dec + ".weight"] = gWo
+    # d h = G W_out  (B operand = W_out^T [dd, I])
+    woT = model._weight_operand("out0", model.out_layers[-1].weight, transpose=True)
+    dh = torch.empty(B, dd, dtype=torch.float32, device=dev)
+    _mm_auto(model, G, woT, B, dd, I, out_f32=dh)
+    # middle layers (dims with more than one entry), last to first: tanh', weight / bias gradient, input gradient
+    mid = model._middle()
+    for li in reversed(range(len(mid))):
+        name, layer = mid[li]
+        n_out, n_in = layer.weight.shape
+        a_in = c.acts[li - 1][0] if li > 0 else c.h_f32
+        dpre = torch.empty(B, n_out, dtype=torch.float32, device=dev)
+        dpre_op = Bf16Mat.empty(B, n_out, dev, lo, zero=True)
+        K.ew_binary(K.EW_TANH_BWD, dh, c.acts[li][0], B, n_out, out_f32=dpre, out_bf16=dpre_op.hi, out_bf16_lo=dpre_op.lo)
+        gWm = torch.empty_like(layer.weight)
+        _mm_auto(model, K.cast_bf16_transpose(dpre, with_lo=lo), K.cast_bf16_transpose(a_in, with_lo=lo), n_out, n_in, B, out_f32=gWm)
+        grads[name + ".weight"] = gWm
+        grads[name + ".bias"] = K.colsum_f32(dpre, B, n_out)
+        dh = torch.empty(B, n_in, dtype=torch.float32, device=dev)
+        _mm_auto(model, dpre_op, model._weight_operand(name, layer.weight, transpose=True), B, n_in, n_out, out_f32=dh)
     dh_pre = torch.empty(B, d, dtype=torch.float32, device=dev)
     K.ew_binary(K.EW_TANH_BWD, dh, c.h_f32, B, d, out_f32=dh_pre)
     dh_preT = K.cast_bf16_transpose(dh_pre, with_lo=lo)
@@ -587,7 +613,7 @@ class _DnnTrainFn(torch.autograd.Function):
     def backward(ctx, g_mse, g_out):
         grads = _dnn_backward(ctx.model, ctx.diff, ctx.c, g_mse)
         ctx.c = None
-        return (None,) * 7 + _hand_over(ctx.model, grads, _DNN_PARAMS)
+        return (None,) * 7 + _hand_over(ctx.model, grads, _dnn_names(ctx.model))
 
 
 # ======================================================================================================
@@ -646,7 +672,7 @@ def training_losses(diff, model, x_start, reweight=False, index=None, inject: Op
         mse, closs, out = _GdmcfTrainFn.apply(model, diff, x0, B, I, idx32, ts_disc, ts32, inject,
                                               *[params[n] for n in _gdmcf_names(model)])
     else:
-        mse, out = _DnnTrainFn.apply(model, diff, x0, B, I, ts32, inject, *[params[n] for n in _DNN_PARAMS])
+        mse, out = _DnnTrainFn.apply(model, diff, x0, B, I, ts32, inject, *[params[n] for n in _dnn_names(model)])
         closs = None
     terms = {}
     terms["loss"] = _loss_weight(diff, ts, B, dev, reweight) * mse

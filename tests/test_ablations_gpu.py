@@ -225,3 +225,23 @@ def test_deep_encoders(lib, tag, precision):
     batch = data_utils.DeviceInteractions(sp.csr_matrix(full), "cuda").batch(g["index"].astype(np.int32))
     assert rel(d.p_sample(m, batch, 0), g[tag + "p_sample_s0"]) < tol                     # sparse one-hot encoder
     replay(g, tag, m, diffusion(), True, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_deep_dnn_backbone(lib, precision):
+    """Plain DNN backbone with dims=[a, b] (two in_layers + two out_layers, tanh between, models/DNN.py:72-88) against
+    tests/golden/deep.npz: eval forward, p_sample, 2 training steps with every gradient."""
+    from gdmcf_b200.models.DNN import DNN
+    g, tag = dict(np.load(os.path.join(GOLD, "deep.npz"))), "dnn_deep."
+    dims = [int(x) for x in g[tag + "in_dims"]]
+    m = DNN(list(dims), list(dims[::-1]), E, precision=precision)
+    m.load_state_dict(sd(g, tag), strict=True)
+    m = m.cuda().eval()
+    assert m.deep and m.hidden == dims[1] and m.d_dec == dims[1]
+    x0, index = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["index"]).cuda()
+    tol = TOL[precision]["score"]
+    assert rel(m(torch.from_numpy(g["fwd_x"]).cuda(), torch.from_numpy(g["fwd_ts"]).cuda()), g[tag + "fwd_eval"]) < tol
+    d = diffusion(cat=False, index_in=False)
+    # 5 reverse steps through 4 layers each: bf16 mode re-rounds x_t and three activations per step (measured 5.9e-3)
+    assert rel(d.p_sample(m, x0, 0, index=index), g[tag + "p_sample_s0"]) < tol * (2 if precision == "bf16" else 1)
+    replay(g, tag, m, diffusion(cat=False, index_in=False), False, precision)
