@@ -85,6 +85,16 @@ class Dist:
         for p in model.parameters():
             td.broadcast(p.data, src=0)
 
+    def exchange_factors(self, send_rows, send_small, recv_rows, recv_small, group=None):
+        """Exchange of a rank-B gradient's factors (engine.StepEngine: dE = Gs^T hc' summed over ranks, row-sharded):
+        send_rows [G * R, B] — block q of its rows goes to rank q (all-to-all) -> recv_rows [G, R, B] (slot r = rank r's
+        block of MY rows); send_small [C, B] goes to everyone (all-gather) -> recv_small [G, C, B]. Rank q then forms
+        sum_r recv_rows[r] @ recv_small[r]^T = rows [q * R, (q + 1) * R) of the summed product. Returns the async works."""
+        G = self.world_size
+        assert recv_rows.shape[0] == G and recv_small.shape[0] == G and send_rows.numel() == recv_rows.numel()
+        return [td.all_to_all_single(recv_rows.view(-1), send_rows.view(-1), group=group, async_op=True),
+                td.all_gather_into_tensor(recv_small.view(-1), send_small.view(-1), group=group, async_op=True)]
+
     def barrier(self) -> None:
         if self.world_size > 1:
             td.barrier()

@@ -457,8 +457,7 @@ class StepEngine:
             works.append(td.reduce_scatter_tensor(gbuf.view(G, -1)[rank], gbuf.view(-1), op=td.ReduceOp.SUM, async_op=True))
         for n in fx:  # factors of a rank-B gradient: row blocks of Gs^T to their owners, hc'^T to everyone
             b = self._shards[n]["fx"]
-            works.append(td.all_to_all_single(b["recvA"].view(-1), b["sendA"].view(-1), async_op=True))
-            works.append(td.all_gather_into_tensor(b["recvB"].view(-1), b["sendB"].view(-1), async_op=True))
+            works += self.dist.exchange_factors(b["sendA"], b["sendB"], b["recvA"], b["recvB"])
         if action == "gather_rows":
             works.append(td.all_gather_into_tensor(self._recv_idx.view(-1), self._send_idx, group=group, async_op=True))
             works.append(td.all_gather_into_tensor(self._recv_rows.view(-1), self._send_rows.view(-1), group=group, async_op=True))

@@ -54,7 +54,19 @@ def main(out_dir):
     for fn in after:
         fn()
     async_ok = all(torch.equal(a, b) for a, b in zip(own, expect))
-    torch.save({"rank": dist.rank, "mine": mine, "sums": sums, "async_ok": async_ok,
+    # factor exchange of a rank-B gradient (engine.StepEngine, item table): block q of the summed product Gs^T hc' from the
+    # exchanged factors == rows of the all-reduced full product
+    G, R, Bf, C = dist.world_size, 37, 8, 24
+    gen = torch.Generator().manual_seed(500 + dist.rank)
+    gsT, hcT = torch.randn(G * R, Bf, generator=gen), torch.randn(C, Bf, generator=gen)
+    recv_rows, recv_small = torch.zeros(G, R, Bf), torch.zeros(G, C, Bf)
+    for w in dist.exchange_factors(gsT, hcT, recv_rows, recv_small):
+        w.wait()
+    block = sum(recv_rows[r] @ recv_small[r].t() for r in range(G))
+    full = gsT @ hcT.t()
+    dist.all_reduce(full)
+    fx_err = (block - full[dist.rank * R:(dist.rank + 1) * R]).abs().max().item()
+    torch.save({"rank": dist.rank, "mine": mine, "sums": sums, "async_ok": async_ok, "fx_err": fx_err,
                 "params": {k: v.detach().clone() for k, v in model.named_parameters()},
                 "grads": {k: (v.grad.clone() if v.grad is not None else None) for k, v in model.named_parameters()},
                 "draws": draws, "users": users, "dense": dense},

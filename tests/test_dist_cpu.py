@@ -35,6 +35,7 @@ def test_two_rank_gloo_equivalence(tmp_path):
         assert torch.equal(r0["params"][k], r1["params"][k]), k
     assert r0["mine"] == [0, 2, 4] and r1["mine"] == [1, 3, 5]
     assert r0["async_ok"] and r1["async_ok"]  # all_reduce_async: large / flattened small / padded-view tensors
+    assert r0["fx_err"] < 1e-4 and r1["fx_err"] < 1e-4  # factor exchange: block mapping of all-to-all + all-gather
     assert torch.equal(r0["sums"], torch.full((2, 4), 3.0, dtype=torch.float64)) and torch.equal(r0["sums"], r1["sums"])
     # all-reduced gradients identical on both ranks and equal to the single-process sum over the two batches
     from oracle import gdmcf_oracle as O
