@@ -10,7 +10,8 @@ sys.path.insert(0, ROOT)
 from gdmcf_b200 import data_utils, kernels as K  # noqa: E402
 from gdmcf_b200.lightGCN import LightGCN  # noqa: E402
 
-SHAPES = {"yelp": (54574, 34395, 1402736, 0), "amazon": (108822, 94949, 3146256, 1), "tiny": (2000, 1500, 40000, 3)}
+SHAPES = {"yelp": (54574, 34395, 1402736, 0), "amazon": (108822, 94949, 3146256, 1), "tiny": (2000, 1500, 40000, 3),
+          "scaled": (1000000, 200000, 50000000, 2)}
 
 
 def main():
