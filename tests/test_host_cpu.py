@@ -124,6 +124,16 @@ def test_engine_modules_match_oracle_state_dict():
     assert sum(p.numel() for p in e.parameters()) == sum(p.numel() for p in o.parameters())
     e2, o2 = DNN([150, 32], [32, 150], 10), O.OracleDNN([150, 32], [32, 150], 10)
     assert {k: tuple(v.shape) for k, v in e2.state_dict().items()} == {k: tuple(v.shape) for k, v in o2.state_dict().items()}
+    # dims with more than one entry (main.py:198-206): same modules, keys and shapes as the reference's construction
+    for dims in ([150, 48, 32], [150, 48, 40, 32]):
+        e3 = DNNOneHotEmbeddingGCN(list(dims), list(dims[::-1]), 10, item_num=150, user_num=40)
+        o3 = O.OracleGDMCF(list(dims), list(dims[::-1]), 10, item_num=150, user_num=40)
+        assert {k: tuple(v.shape) for k, v in e3.state_dict().items()} == {k: tuple(v.shape) for k, v in o3.state_dict().items()}
+        assert e3.deep and e3.d1 == dims[1] and e3.hidden == dims[-1]
+        e4, o4 = DNN(list(dims), list(dims[::-1]), 10), O.OracleDNN(list(dims), list(dims[::-1]), 10)
+        assert {k: tuple(v.shape) for k, v in e4.state_dict().items()} == {k: tuple(v.shape) for k, v in o4.state_dict().items()}
+        assert [n for n, _ in e4._middle()] == [f"in_layers.{i}" for i in range(1, len(dims) - 1)] + \
+            [f"out_layers.{j}" for j in range(len(dims) - 2)]
     # parameter counts at the Yelp shape with n_user=3000
     n = lambda i, d, u: (i + 10) * d + d + (2 * i + 10) * d + d + (2 * d) * i + i + i * 3 * d + u * d + 110 + 3 * d * 512 + 512 + 512 * 3 * d + 3 * d + 1  # noqa: E731
     assert n(34395, 1000, 3000) == 281292018
